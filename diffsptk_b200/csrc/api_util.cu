@@ -1,0 +1,104 @@
+// Error reporting, device-property cache and the twiddle-table cache of the C ABI.
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "common.cuh"
+
+namespace dsb200 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(DSB200_E_CUDA, "CUDA error '%s' in %s", cudaGetErrorString(e), what);
+}
+
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+static std::mutex g_mu;
+static std::map<int, cudaDeviceProp> g_props;
+
+static const cudaDeviceProp* props(int device) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto it = g_props.find(device);
+  if (it == g_props.end()) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, device) != cudaSuccess) return nullptr;
+    it = g_props.emplace(device, p).first;
+  }
+  return &it->second;
+}
+
+int sm_count(int device) {
+  const cudaDeviceProp* p = props(device);
+  return p ? p->multiProcessorCount : 148;
+}
+
+int max_dynamic_smem(int device) {
+  const cudaDeviceProp* p = props(device);
+  return p ? static_cast<int>(p->sharedMemPerBlockOptin) : 227 * 1024;
+}
+
+template <typename T>
+__global__ void fill_twiddles(T* tw, int n) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  double s, c;
+  sincospi(-2.0 * static_cast<double>(k) / static_cast<double>(n), &s, &c);
+  tw[2 * k] = static_cast<T>(c);
+  tw[2 * k + 1] = static_cast<T>(s);
+}
+
+static std::map<std::tuple<int, int, bool>, void*> g_tw;
+
+const void* twiddle_table(int device, int n, bool is_f64, cudaStream_t stream) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  auto key = std::make_tuple(device, n, is_f64);
+  auto it = g_tw.find(key);
+  if (it != g_tw.end()) return it->second;
+  void* p = nullptr;
+  size_t bytes = static_cast<size_t>(n) * 2 * (is_f64 ? sizeof(double) : sizeof(float));
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  int threads = 128, blocks = (n + threads - 1) / threads;
+  if (is_f64)
+    fill_twiddles<double><<<blocks, threads, 0, stream>>>(static_cast<double*>(p), n);
+  else
+    fill_twiddles<float><<<blocks, threads, 0, stream>>>(static_cast<float*>(p), n);
+  count_launch();
+  // First use only: make the table visible to every stream before it is cached.
+  if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(stream) != cudaSuccess) {
+    cudaFree(p);
+    return nullptr;
+  }
+  g_tw[key] = p;
+  return p;
+}
+
+}  // namespace dsb200
+
+extern "C" {
+
+int dsb200_version(void) { return DSB200_VERSION; }
+
+const char* dsb200_last_error(void) { return dsb200::g_err; }
+
+int64_t dsb200_launch_count(void) { return dsb200::g_launches.load(std::memory_order_relaxed); }
+
+int64_t dsb200_num_frames(int64_t T, int32_t frame_period) {
+  if (T <= 0 || frame_period <= 0) return 0;
+  return (T - 1) / frame_period + 1;
+}
+
+}  // extern "C"

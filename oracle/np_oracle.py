@@ -1,0 +1,558 @@
+"""numpy restatement of the reference's frame-rate analysis path (CPU oracle).
+
+TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.  Parity status: pinned
+(doctest known answers + reference-generated golden vectors).
+
+Every function follows the *algorithm the reference uses* (FFT-based
+autocorrelation, dense Toeplitz solve, matrix frequency transform, ...), not
+the algorithm the CUDA kernels use, so a kernel bug and an oracle bug cannot
+cancel.  All ``file:line`` citations are relative to ``/root/reference``.
+
+Arithmetic runs in the dtype of the input array (float32 or float64), like the
+reference.  Host tables (window, warping matrices, filter bank, DCT basis,
+lifter) are built in float64 and cast, as the reference does for every table
+except the window, which the reference builds directly in the module dtype
+(``diffsptk/modules/window.py:134-183``); the resulting <= 2e-8 table
+difference is far inside the stated tolerances.
+"""
+
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+__all__ = [
+    "frame", "window_table", "window", "fftr", "spec", "stft", "acorr", "levdur",
+    "lpc", "freqt_matrix", "freqt", "coef_freqt_matrix", "mcep", "fbank_matrix",
+    "fbank", "dct_matrix", "dct", "mfcc", "lifter_vector",
+]
+
+_PAD_MODE = {"constant": "constant", "reflect": "reflect", "replicate": "edge", "circular": "wrap"}
+
+
+def _as_float(x):
+    x = np.asarray(x)
+    if x.dtype not in (np.float32, np.float64):
+        x = x.astype(np.float32)
+    return x
+
+
+# ----------------------------------------------------------------------------- frame
+def frame(x, frame_length=400, frame_period=80, center=True, zmean=False, mode="constant"):
+    """Overlapping frames of a waveform.  diffsptk/modules/frame.py:120-141.
+
+    ``y[..., i, j] = xpad[..., i*P + j]`` with ``xpad = pad(x, (L//2, (L-1)//2))``
+    when centred, ``(0, L-1)`` otherwise (frame.py:130-137); frame count is the
+    ``unfold`` count ``(T-1)//P + 1`` (frame.py:138).
+    """
+    if frame_length <= 0:
+        raise ValueError("frame_length must be positive.")
+    if frame_period <= 0:
+        raise ValueError("frame_period must be positive.")
+    x = np.asarray(x)
+    L, P = frame_length, frame_period
+    left, right = (L // 2, (L - 1) // 2) if center else (0, L - 1)
+    widths = [(0, 0)] * (x.ndim - 1) + [(left, right)]
+    xp = np.pad(x, widths, mode=_PAD_MODE[mode])
+    n = (xp.shape[-1] - L) // P + 1
+    idx = (np.arange(n) * P)[:, None] + np.arange(L)[None, :]
+    y = xp[..., idx]
+    if zmean:
+        y = y - y.mean(-1, keepdims=True)
+    return y
+
+
+# ----------------------------------------------------------------------------- window
+def _cos_sum(L, periodic, coefs):
+    n_den = L if periodic else L - 1
+    if L == 1:
+        return np.ones(1)
+    n = np.arange(L, dtype=np.float64)
+    w = np.zeros(L)
+    for k, c in enumerate(coefs):
+        w += c * np.cos(2.0 * math.pi * k * n / n_den)
+    return w
+
+
+def _sine_window(L, symmetric):
+    # torch.signal.windows.cosine: sin(pi * (n + 0.5) / M), M = L (sym) or L + 1.
+    if L == 1:
+        return np.ones(1)
+    M = L if symmetric else L + 1
+    n = np.arange(L, dtype=np.float64)
+    return np.sin(math.pi * (n + 0.5) / M)
+
+
+def window_table(in_length, window="blackman", norm="power", symmetric=True, dtype=np.float64):
+    """The window table.  diffsptk/modules/window.py:122-183."""
+    L = in_length
+    if L <= 0:
+        raise ValueError("in_length must be positive.")
+    periodic = not symmetric
+    if window in (0, "blackman"):
+        w = _cos_sum(L, periodic, (0.42, -0.5, 0.08))
+    elif window in (1, "hamming"):
+        w = _cos_sum(L, periodic, (0.54, -0.46))
+    elif window in (2, "hanning"):
+        w = _cos_sum(L, periodic, (0.5, -0.5))
+    elif window in (3, "bartlett", 4, "trapezoidal"):
+        if L == 1:
+            w = np.ones(1)
+        else:
+            den = L if periodic else L - 1
+            w = 1.0 - np.abs(2.0 * np.arange(L, dtype=np.float64) / den - 1.0)
+        if window in (4, "trapezoidal"):
+            w = np.minimum(2.0 * w, 1.0)
+    elif window in (5, "rectangular"):
+        w = np.ones(L)
+    elif window in (6, "nuttall"):
+        size = L if periodic else L - 1
+        c1 = np.array([0.355768, -0.487396, 0.144232, -0.012604])
+        c2 = np.arange(0, 8, 2, dtype=np.float64) * (math.pi / size)
+        w = (c1 * np.cos(np.outer(np.arange(L, dtype=np.float64), c2))).sum(1)
+    elif window == "povey":
+        w = _cos_sum(L, periodic, (0.5, -0.5)) ** 0.85
+    elif window == "sine":
+        w = _sine_window(L, symmetric)
+    elif window == "vorbis":
+        w = np.sin(0.5 * math.pi * _sine_window(L, symmetric) ** 2)
+    elif window == "kbd":
+        if periodic:
+            raise ValueError("periodic is not supported for kbd window.")
+        seed = np.kaiser(L // 2 + 1, 12.0)
+        cs = np.cumsum(seed)
+        half = np.sqrt(cs[:-1] / cs[-1])
+        w = np.concatenate([half, half[::-1]])
+    else:
+        raise ValueError(f"window {window} is not supported.")
+    if norm in (0, "none"):
+        pass
+    elif norm in (1, "power"):
+        w = w / math.sqrt(float((w * w).sum()))
+    elif norm in (2, "magnitude"):
+        w = w / float(w.sum())
+    else:
+        raise ValueError(f"norm {norm} is not supported.")
+    return w.astype(dtype)
+
+
+def window(x, out_length=None, *, window="blackman", norm="power", symmetric=True, table=None):
+    """Multiply by the window, then right zero-pad.  window.py:185-193."""
+    x = _as_float(x)
+    L = x.shape[-1]
+    w = window_table(L, window, norm, symmetric, x.dtype) if table is None else np.asarray(table)
+    y = x * w
+    if out_length is not None:
+        if out_length >= L:
+            widths = [(0, 0)] * (y.ndim - 1) + [(0, out_length - L)]
+            y = np.pad(y, widths)
+        else:  # F.pad with a negative width truncates
+            y = y[..., :out_length]
+    return y
+
+
+# ----------------------------------------------------------------------------- fftr / spec / stft
+def fftr(x, fft_length=None, out_format="complex"):
+    """Real FFT + output formatter.  diffsptk/modules/fftr.py:110-121,136-151."""
+    if fft_length is not None and (fft_length <= 0 or fft_length % 2 == 1):
+        raise ValueError("fft_length must be positive even.")
+    x = _as_float(x)
+    y = np.fft.rfft(x, n=fft_length, axis=-1)
+    if out_format in (0, "complex"):
+        return y
+    if out_format in (1, "real"):
+        return y.real
+    if out_format in (2, "imaginary"):
+        return y.imag
+    if out_format in (3, "amplitude"):
+        return np.abs(y)
+    if out_format in (4, "power"):
+        return np.square(np.abs(y))
+    raise ValueError(f"out_format {out_format} is not supported.")
+
+
+def _remove_gain(a):
+    # diffsptk/utils/private.py:200-209
+    K = a[..., :1]
+    a = np.concatenate([np.ones_like(K), a[..., 1:]], axis=-1)
+    return K, a
+
+
+def spec(b=None, a=None, *, fft_length=512, eps=0.0, relative_floor=None, out_format="power"):
+    """Power spectrum of b / a.  diffsptk/modules/spec.py:152-178."""
+    if fft_length <= 1:
+        raise ValueError("fft_length must be greater than 1.")
+    if eps < 0:
+        raise ValueError("eps must be non-negative.")
+    if relative_floor is not None and 0 <= relative_floor:
+        raise ValueError("relative_floor must be negative.")
+    if b is not None and a is not None:
+        K, a = _remove_gain(_as_float(a))
+        X = K * (fftr(b, fft_length, "amplitude") / fftr(a, fft_length, "amplitude"))
+    elif b is not None:
+        X = fftr(b, fft_length, "amplitude")
+    elif a is not None:
+        K, a = _remove_gain(_as_float(a))
+        X = K / fftr(a, fft_length, "amplitude")
+    else:
+        raise ValueError("Either b or a must be specified.")
+    dt = X.dtype
+    s = np.square(X) + dt.type(eps)
+    if relative_floor is not None:
+        rf = 10 ** (relative_floor / 10)  # spec.py:121-122
+        s = np.maximum(s, s.max(-1, keepdims=True) * dt.type(rf))
+    if out_format in (0, "db"):
+        return (10 * np.log10(s)).astype(dt)
+    if out_format in (1, "log-magnitude"):
+        return (0.5 * np.log(s)).astype(dt)
+    if out_format in (2, "magnitude"):
+        return np.sqrt(s)
+    if out_format in (3, "power"):
+        return s
+    raise ValueError(f"out_format {out_format} is not supported.")
+
+
+def stft(x, *, frame_length=400, frame_period=80, fft_length=512, center=True, zmean=False,
+         mode="constant", window="blackman", norm="power", symmetric=True, eps=1e-9,
+         relative_floor=None, out_format="power", window_table_override=None):
+    """spec(window(frame(x))).  diffsptk/modules/stft.py:158-241 (defaults :92-100)."""
+    x = _as_float(x)
+    f = frame(x, frame_length, frame_period, center, zmean, mode)
+    g = globals()["window"](f, fft_length, window=window, norm=norm, symmetric=symmetric,
+                            table=window_table_override)
+    if out_format == "complex":
+        return fftr(g, fft_length, "complex")
+    return spec(g, fft_length=fft_length, eps=eps, relative_floor=relative_floor, out_format=out_format)
+
+
+# ----------------------------------------------------------------------------- acorr / levdur / lpc
+def acorr(x, acr_order, out_format="naive"):
+    """FFT-based autocorrelation.  diffsptk/modules/acorr.py:95-120."""
+    x = _as_float(x)
+    L = x.shape[-1]
+    if L <= 0:
+        raise ValueError("frame_length must be positive.")
+    if L <= acr_order:
+        raise ValueError("acr_order must be less than frame_length.")
+    n = L + acr_order
+    n += n % 2
+    X = np.square(np.abs(np.fft.rfft(x, n=n, axis=-1)))
+    r = np.fft.irfft(X, axis=-1)[..., : acr_order + 1].astype(x.dtype)
+    if out_format in (0, "naive"):
+        return r
+    if out_format in (1, "normalized"):
+        return r / r[..., :1]
+    if out_format in (2, "biased"):
+        return r / x.dtype.type(L)
+    if out_format in (3, "unbiased"):
+        return (r / np.arange(L, L - acr_order - 1, -1)).astype(x.dtype)
+    raise ValueError(f"out_format {out_format} is not supported.")
+
+
+def _toeplitz(r):
+    # diffsptk/utils/private.py:291-295: R[i, j] = r[|i - j|]
+    d = r.shape[-1]
+    idx = np.abs(np.arange(d)[:, None] - np.arange(d)[None, :])
+    return r[..., idx]
+
+
+def _hankel(x):
+    # diffsptk/utils/private.py:298-302: Q[i, j] = x[i + j], n = (d + 1) // 2
+    n = (x.shape[-1] + 1) // 2
+    idx = np.arange(n)[:, None] + np.arange(n)[None, :]
+    return x[..., idx]
+
+
+def levdur(r, eps=None):
+    """Yule-Walker solve by a dense Toeplitz system.  diffsptk/modules/levdur.py:98-127."""
+    r = _as_float(r)
+    M = r.shape[-1] - 1
+    if eps is None:
+        eps = 1e-5 if r.dtype == np.float32 else 0.0  # levdur.py:108-110
+    if eps < 0:
+        raise ValueError("eps must be non-negative.")
+    r0, r1 = r[..., :1], r[..., 1:]
+    if M == 0:
+        return np.sqrt(r0)
+    R = _toeplitz(r[..., :-1]) + (np.eye(M, dtype=r.dtype) * r.dtype.type(eps))
+    a = np.linalg.solve(R, -r1[..., None])[..., 0].astype(r.dtype)
+    K = np.sqrt((r1 * a).sum(-1, keepdims=True) + r0)
+    return np.concatenate([K, a], axis=-1)
+
+
+def lpc(x, lpc_order, eps=None):
+    """levdur(acorr(x)).  diffsptk/modules/lpc.py:106-139."""
+    return levdur(acorr(x, lpc_order), eps)
+
+
+# ----------------------------------------------------------------------------- freqt
+def freqt_matrix(in_order, out_order, alpha):
+    """All-pass warping matrix in float64, shape (M1+1, M2+1).  freqt.py:115-139."""
+    if in_order < 0:
+        raise ValueError("in_order must be non-negative.")
+    if out_order < 0:
+        raise ValueError("out_order must be non-negative.")
+    if 1 <= abs(alpha):
+        raise ValueError("alpha must be in (-1, 1).")
+    L1, L2 = in_order + 1, out_order + 1
+    beta = 1 - alpha * alpha
+    ramp = np.arange(L1, dtype=np.float64)
+    A = np.zeros((L2, L1))
+    A[0, :] = alpha ** ramp
+    if 1 < L2 and 1 < L1:
+        A[1, 1:] = A[0, :-1] * beta * ramp[1:]
+    for i in range(2, L2):
+        for j in range(1, L1):
+            A[i, j] = A[i - 1, j - 1] + alpha * (A[i, j - 1] - A[i - 1, j])
+    return np.ascontiguousarray(A.T)
+
+
+def freqt(c, out_order, alpha=0.0):
+    """c @ A.  diffsptk/modules/freqt.py:141-143."""
+    c = _as_float(c)
+    A = freqt_matrix(c.shape[-1] - 1, out_order, alpha).astype(c.dtype)
+    return c @ A
+
+
+def coef_freqt_matrix(in_order, out_order, alpha):
+    """mcep-internal warping of autocorrelation-like sequences.  mcep.py:264-288."""
+    L1, L2 = in_order + 1, out_order + 1
+    A = np.zeros((L2, L1))
+    A[:, 0] = (-alpha) ** np.arange(L2, dtype=np.float64)
+    for i in range(1, L2):
+        for j in range(1, L1):
+            A[i, j] = A[i - 1, j - 1] + alpha * (A[i, j - 1] - A[i - 1, j])
+    return np.ascontiguousarray(A.T)
+
+
+# ----------------------------------------------------------------------------- mcep
+def mcep(x, cep_order, alpha=0.0, n_iter=0):
+    """Mel-cepstral analysis of a power spectrum.  diffsptk/modules/mcep.py:189-224."""
+    x = _as_float(x)
+    dt = x.dtype
+    H = x.shape[-1] - 1
+    fft_length = 2 * H
+    M = cep_order
+    if fft_length <= 1:
+        raise ValueError("fft_length must be greater than 1.")
+    if M < 0:
+        raise ValueError("cep_order must be non-negative.")
+    if fft_length < 2 * M:
+        raise ValueError("cep_order must be less than or equal to fft_length // 2.")
+    if 1 <= abs(alpha):
+        raise ValueError("alpha must be in (-1, 1).")
+    if n_iter < 0:
+        raise ValueError("n_iter must be non-negative.")
+    A_f = freqt_matrix(H, M, alpha).astype(dt)
+    A_i = freqt_matrix(M, H, -alpha).astype(dt)
+    A_r = coef_freqt_matrix(H, 2 * M, alpha).astype(dt)
+    alpha_vector = ((-alpha) ** np.arange(M + 1, dtype=np.float64)).astype(dt)  # mcep.py:179-181
+
+    log_x = np.log(x)
+    c = np.fft.irfft(log_x, axis=-1).astype(dt)
+    c[..., 0] *= 0.5
+    c[..., H] *= 0.5
+    mc = c[..., : H + 1] @ A_f
+    for _ in range(n_iter):
+        c = mc @ A_i
+        d = np.fft.rfft(c, n=fft_length, axis=-1).real.astype(dt)
+        d = np.exp(log_x - d - d)
+        rd = np.fft.irfft(d, axis=-1).astype(dt)
+        rt = rd[..., : H + 1] @ A_r
+        r = rt[..., : M + 1]
+        ra = r - alpha_vector
+        RQ = _toeplitz(r) + _hankel(rt)
+        grad = np.linalg.solve(RQ, ra[..., None])[..., 0].astype(dt)
+        mc = mc + grad
+    return mc
+
+
+# ----------------------------------------------------------------------------- fbank / dct / mfcc
+def _hz_to_auditory(f, scale):
+    # diffsptk/utils/private.py:241-274
+    if scale == "htk":
+        return 1127 * np.log1p(f / 700)
+    if scale in ("oshaughnessy", "mel"):
+        return 2595 * np.log10(1 + f / 700)
+    if scale in ("chakroborty", "inverted-mel"):
+        return 2195.286 - 2595 * np.log10(1 + (4031.25 - f) / 700)
+    if scale in ("traunmuller", "bark"):
+        return (26.81 * f) / (1960 + f) - 0.53
+    if scale == "linear":
+        return f
+    raise ValueError(f"scale {scale} is not supported.")
+
+
+def _auditory_to_hz(z, scale):
+    # diffsptk/utils/private.py:277-288
+    if scale == "htk":
+        return 700 * np.expm1(z / 1127)
+    if scale in ("oshaughnessy", "mel"):
+        return 700 * (np.power(10, z / 2595) - 1)
+    if scale in ("chakroborty", "inverted-mel"):
+        return 4031.25 - 700 * (np.power(10, (2195.286 - z) / 2595) - 1)
+    if scale in ("traunmuller", "bark"):
+        return 1960 * (z + 0.53) / (26.28 - z)
+    if scale == "linear":
+        return z
+    raise ValueError(f"scale {scale} is not supported.")
+
+
+def fbank_matrix(fft_length, n_channel, sample_rate, f_min=0.0, f_max=None, scale="htk", erb_factor=None):
+    """Triangular filter-bank weights H[L/2+1, C] in float64.  fbank.py:233-293."""
+    if fft_length <= 1:
+        raise ValueError("fft_length must be greater than 1.")
+    if n_channel <= 0:
+        raise ValueError("n_channel must be positive.")
+    if sample_rate <= 0:
+        raise ValueError("sample_rate must be positive.")
+    if f_min < 0 or sample_rate / 2 <= f_min:
+        raise ValueError("Invalid f_min.")
+    if f_max is not None and not (f_min < f_max <= sample_rate / 2):
+        raise ValueError("Invalid f_min and f_max.")
+    if erb_factor is not None and erb_factor <= 0:
+        raise ValueError("erb_factor must be positive.")
+    if f_max is None:
+        f_max = sample_rate / 2
+    K = fft_length // 2 + 1
+    C = n_channel
+    H = np.zeros((K, C))
+    if erb_factor is None:
+        z_lo = _hz_to_auditory(np.asarray(f_min, dtype=np.float64), scale)
+        z_hi = _hz_to_auditory(np.asarray(f_max, dtype=np.float64), scale)
+        k_lo = max(1, int(f_min / sample_rate * fft_length + 1.5))
+        k_hi = min(fft_length // 2, int(f_max / sample_rate * fft_length + 0.5))
+        centers = (z_hi - z_lo) / (C + 1) * np.arange(1, C + 2) + z_lo
+        widths = centers - np.concatenate([[z_lo], centers[:-1]])
+        for k in range(k_lo, k_hi):
+            z = _hz_to_auditory(np.float64(sample_rate * k / fft_length), scale)
+            m = int(np.argmax(z <= centers))  # first centre at or above this bin
+            w = (centers[m] - z) / widths[m]
+            if 0 < m:
+                H[k, m - 1] = w
+            if m < C:
+                H[k, m] = 1 - w
+    else:
+        a = erb_factor * 6.23e-6
+        b = erb_factor * 93.39e-3
+        c = erb_factor * 28.52
+
+        def centre(f, first):
+            s = 1 if first else -1
+            a_h = s * 0.5 / (700 + f)
+            b_h = s * 700 / (700 + f)
+            c_h = -s * 0.5 * f * (1 + 700 / (700 + f))
+            b_b = (b - b_h) / (a - a_h)
+            c_b = (c - c_h) / (a - a_h)
+            return 0.5 * (-b_b + np.sqrt(b_b ** 2 - 4 * c_b))
+
+        z1 = _hz_to_auditory(centre(f_min, True), scale)
+        zc = _hz_to_auditory(centre(f_max, False), scale)
+        fc = _auditory_to_hz(np.linspace(z1, zc, C), scale)
+        erb = a * fc ** 2 + b * fc + c
+        fl = -(700 + erb) + np.sqrt(erb ** 2 + (700 + fc) ** 2)
+        fh = fl + 2 * erb
+        f = np.linspace(0, sample_rate / 2, K)
+        for m in range(C):
+            up = (fl[m] <= f) & (f < fc[m])
+            H[up, m] = (f[up] - fl[m]) / (fc[m] - fl[m])
+            dn = (fc[m] <= f) & (f <= fh[m])
+            H[dn, m] = (fh[m] - f[dn]) / (fh[m] - fc[m])
+    return H
+
+
+def fbank(x, n_channel, sample_rate, f_min=0.0, f_max=None, floor=1e-5, gamma=0.0, scale="htk",
+          erb_factor=None, use_power=False, out_format="y"):
+    """Mel filter-bank analysis of a power spectrum.  fbank.py:305-321."""
+    x = _as_float(x)
+    dt = x.dtype
+    if floor <= 0:
+        raise ValueError("floor must be positive.")
+    if 1 < abs(gamma):
+        raise ValueError("gamma must be in [-1, 1].")
+    fft_length = 2 * x.shape[-1] - 2
+    H = fbank_matrix(fft_length, n_channel, sample_rate, f_min, f_max, scale, erb_factor).astype(dt)
+    y = x if use_power else np.sqrt(x)
+    y = np.maximum(y @ H, dt.type(floor))
+    y = np.log(y) if gamma == 0 else (np.power(y, dt.type(gamma)) - 1) / dt.type(gamma)
+    E = (2 * x[..., 1:-1]).sum(-1) + x[..., 0] + x[..., -1]
+    E = np.log(E / dt.type(2 * (x.shape[-1] - 1)))[..., None]
+    if out_format in (0, "y"):
+        return y
+    if out_format in (1, "yE"):
+        return np.concatenate([y, E], axis=-1)
+    if out_format in (2, "y,E"):
+        return y, E
+    raise ValueError(f"out_format {out_format} is not supported.")
+
+
+def dct_matrix(dct_length, dct_type=2):
+    """DCT basis W[n, k] in float64 (y = x @ W).  diffsptk/modules/dct.py:98-133."""
+    L = dct_length
+    if L <= 0:
+        raise ValueError("dct_length must be positive.")
+    if not 1 <= dct_type <= 4:
+        raise ValueError("dct_type must be in [1, 4].")
+    n = np.arange(L, dtype=np.float64)
+    k = np.arange(L, dtype=np.float64)
+    if dct_type in (2, 4):
+        n = n + 0.5
+    if dct_type in (3, 4):
+        k = k + 0.5
+    n = n * (math.pi / ((L - 1) if dct_type == 1 else L))
+    if dct_type == 1:
+        c = 0.5 ** 0.5
+        z0 = np.full(L, 1.0); z0[0] = c; z0[-1] = c
+        z1 = np.full(L, 2.0); z1[0] = 1; z1[-1] = 1
+        z = z0[None, :] * np.sqrt(z1 / (L - 1))[:, None]
+    elif dct_type == 2:
+        z = np.full(L, 2.0); z[0] = 1
+        z = np.sqrt(z / L)[None, :]
+    elif dct_type == 3:
+        z = np.full(L, 2.0); z[0] = 1
+        z = np.sqrt(z / L)[:, None]
+    else:
+        z = (2 / L) ** 0.5
+    return z * np.cos(k[None, :] * n[:, None])
+
+
+def dct(x, dct_type=2):
+    """x @ W.  diffsptk/modules/dct.py:135-137."""
+    x = _as_float(x)
+    return x @ dct_matrix(x.shape[-1], dct_type).astype(x.dtype)
+
+
+def lifter_vector(mfcc_order, lifter):
+    """1 + (lifter/2) sin(pi k / lifter), [0] = sqrt(2).  mfcc.py:233-235."""
+    ramp = np.arange(mfcc_order + 1, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        v = 1 + (lifter / 2) * np.sin((math.pi / lifter) * ramp)
+    v[0] = 2 ** 0.5
+    return v
+
+
+def mfcc(x, mfcc_order, n_channel, sample_rate, lifter=1, f_min=0.0, f_max=None, floor=1e-5,
+         gamma=0.0, scale="htk", erb_factor=None, out_format="y"):
+    """fbank -> DCT-II -> lifter -> split.  diffsptk/modules/mfcc.py:243-256."""
+    x = _as_float(x)
+    if mfcc_order < 0:
+        raise ValueError("mfcc_order must be non-negative.")
+    if n_channel <= mfcc_order:
+        raise ValueError("mfcc_order must be less than n_channel.")
+    if lifter < 0:
+        raise ValueError("lifter must be non-negative.")
+    y, E = fbank(x, n_channel, sample_rate, f_min, f_max, floor, gamma, scale, erb_factor,
+                 use_power=False, out_format="y,E")
+    y = dct(y, 2)
+    y = y[..., : mfcc_order + 1] * lifter_vector(mfcc_order, lifter).astype(x.dtype)
+    c, y = y[..., :1], y[..., 1:]
+    if out_format in (0, "y"):
+        return y
+    if out_format in (1, "yE"):
+        return np.concatenate([y, E], axis=-1)
+    if out_format in (2, "yc"):
+        return np.concatenate([y, c], axis=-1)
+    if out_format in (3, "ycE"):
+        return np.concatenate([y, c, E], axis=-1)
+    raise ValueError(f"out_format {out_format} is not supported.")

@@ -1,0 +1,215 @@
+"""Generate golden input/output vectors by running the REAL reference.
+
+Run in the build container only (``/root/reference`` must exist)::
+
+    python tests/golden/make_golden.py
+
+Writes ``tests/golden/golden_f32.npz``, ``golden_f64.npz`` and
+``manifest.json``.  Every case is ``diffsptk.functional.<op>(*inputs, **params)``
+executed by the unmodified reference on CPU; the shapes mirror the reference's
+own test table (tests/test_frame.py:23-49,
+test_window.py:23-78, test_stft.py:24-68, test_fftr.py:24-70, test_spec.py:23-91,
+test_acorr.py:23-46, test_levdur.py:23-45, test_lpc.py:23-44, test_freqt.py:23-50,
+test_mcep.py:23-54, test_fbank.py:25-106, test_mfcc.py:23-71, test_dct.py:24-58)
+plus the BASELINE.json parameters (fl=400, fp=80, n_fft=512, M=24, alpha=0.42,
+40 mel / 13 cep) at a few hundred frames.
+
+The reference cannot travel to the GPU box, which is why these vectors are
+committed.  ``cases()`` is also imported by the tests to rebuild the inputs.
+"""
+
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+
+
+def _rng(seed):
+    return np.random.default_rng(seed)
+
+
+def speechlike(T, seed=7, sr=16000):
+    """A voiced/unvoiced/silence test signal (synthetic; no reference asset is copied).
+
+    Harmonic source through two resonances, a noise burst, and exact-zero
+    silence -- this produces ill-conditioned autocorrelation matrices and
+    frames that hit the eps / floor paths, like real speech does.
+    """
+    rng = _rng(seed)
+    t = np.arange(T) / sr
+    f0 = 120 + 30 * np.sin(2 * np.pi * 2.0 * t)
+    phase = 2 * np.pi * np.cumsum(f0) / sr
+    src = sum(np.sin(k * phase) / k for k in range(1, 20))
+    y = np.zeros(T)
+    a1, a2 = 2 * 0.97 * np.cos(2 * np.pi * 700 / sr), -0.97 ** 2
+    for n in range(T):
+        y[n] = src[n] + (a1 * y[n - 1] if n > 0 else 0) + (a2 * y[n - 2] if n > 1 else 0)
+    y = 0.1 * y / np.max(np.abs(y))
+    seg = T // 4
+    y[:seg // 2] = 0.0                                   # leading silence (exact zeros)
+    y[2 * seg:3 * seg] = 0.02 * rng.standard_normal(seg)  # unvoiced burst
+    y[3 * seg + seg // 2:] = 0.0                         # trailing silence
+    return y
+
+
+def cases():
+    """Yield (name, op, params, inputs_float64).  Deterministic."""
+    r = _rng(1234)
+    ramp20 = np.arange(20, dtype=np.float64)
+    # ---- frame (tests/test_frame.py:23-49) -------------------------------------------
+    for fl in (1, 2, 3, 4, 5):
+        for fp in (1, 2, 3, 5):
+            for center in (True, False):
+                yield (f"frame_ramp_l{fl}_p{fp}_c{int(center)}", "frame",
+                       dict(frame_length=fl, frame_period=fp, center=center), [ramp20])
+    x_small = r.standard_normal((3, 1000))
+    for mode in ("constant", "reflect", "replicate", "circular"):
+        for center in (True, False):
+            yield (f"frame_400_80_{mode}_c{int(center)}", "frame",
+                   dict(frame_length=400, frame_period=80, center=center, mode=mode), [x_small])
+    yield ("frame_zmean", "frame", dict(frame_length=400, frame_period=80, zmean=True), [x_small])
+    yield ("frame_2048_441", "frame", dict(frame_length=2048, frame_period=441), [r.standard_normal((2, 5000))])
+    for T in (1, 79, 80, 81, 399, 400, 401):
+        yield (f"frame_T{T}", "frame", dict(frame_length=400, frame_period=80), [r.standard_normal((2, T))])
+    # ---- window (tests/test_window.py:23-78) -----------------------------------------
+    step10 = np.ones((2, 10))
+    for w in (0, 1, 2, 3, 4, 5, 6, "povey", "sine", "vorbis", "kbd"):
+        for norm in (0, 1, 2):
+            for sym in (True, False):
+                if w == "kbd" and not sym:
+                    continue
+                for L1, L2 in ((8, 10), (10, 10), (10, None)):
+                    yield (f"window_{w}_n{norm}_s{int(sym)}_{L1}_{L2}", "window",
+                           dict(out_length=L2, window=w, norm=norm, symmetric=sym), [step10[:, :L1]])
+    fr = r.standard_normal((4, 7, 400))
+    yield ("window_400_512", "window", dict(out_length=512), [fr])
+    yield ("window_400_none", "window", dict(out_length=None, window="hamming", norm="none"), [fr])
+    # ---- fftr (tests/test_fftr.py:24-70) ---------------------------------------------
+    x13 = r.standard_normal((3, 13))
+    for of in ("complex", "real", "imaginary", "amplitude", "power"):
+        yield (f"fftr_16_{of}", "fftr", dict(fft_length=16, out_format=of), [x13])
+    yield ("fftr_512", "fftr", dict(fft_length=512), [r.standard_normal((5, 512))])
+    yield ("fftr_none_len24", "fftr", dict(fft_length=None, out_format="power"), [r.standard_normal((2, 24))])
+    yield ("fftr_trunc", "fftr", dict(fft_length=8, out_format="real"), [r.standard_normal((2, 13))])
+    yield ("fftr_424", "fftr", dict(fft_length=424), [r.standard_normal((2, 400))])
+    # ---- spec (tests/test_spec.py:23-91) ---------------------------------------------
+    b = r.standard_normal((3, 5)); a = r.standard_normal((3, 4)); a[:, 0] = np.abs(a[:, 0]) + 0.5
+    for of in ("db", "log-magnitude", "magnitude", "power"):
+        for rf in (None, -40):
+            yield (f"spec_{of}_rf{rf}", "spec",
+                   dict(fft_length=16, eps=0.01, relative_floor=rf, out_format=of), [b, a])
+    yield ("spec_b_only", "spec", dict(fft_length=16, eps=0.01), [b, None])
+    yield ("spec_a_only", "spec", dict(fft_length=16, eps=0.01), [None, a])
+    yield ("spec_512", "spec", dict(fft_length=512, eps=1e-9), [r.standard_normal((6, 400)), None])
+    # ---- stft (tests/test_stft.py:24-68) ---------------------------------------------
+    x100 = r.standard_normal((2, 100))
+    for of in ("power", "complex", "db", "log-magnitude", "magnitude"):
+        yield (f"stft_small_{of}", "stft",
+               dict(frame_length=12, frame_period=10, fft_length=16, window="hamming", norm="power",
+                    eps=1e-6, out_format=of), [x100])
+    x_b = r.standard_normal((3, 8000))
+    yield ("stft_baseline", "stft", dict(), [x_b])
+    yield ("stft_baseline_complex", "stft", dict(out_format="complex"), [x_b[:1, :3000]])
+    yield ("stft_hann_db", "stft", dict(window="hanning", norm="none", out_format="db"), [x_b[:1, :3000]])
+    yield ("stft_rf", "stft", dict(relative_floor=-30.0), [x_b[:2, :2000]])
+    yield ("stft_zmean_reflect", "stft", dict(zmean=True, mode="reflect"), [x_b[:2, :2000]])
+    yield ("stft_nocenter", "stft", dict(center=False, window="rectangular", eps=0.0, out_format="complex"),
+           [x_b[:2, :2000]])
+    yield ("stft_1024", "stft", dict(frame_length=800, frame_period=160, fft_length=1024), [x_b[:2, :4000]])
+    yield ("stft_256", "stft", dict(frame_length=200, frame_period=40, fft_length=256), [x_b[:2, :2000]])
+    yield ("stft_speech", "stft", dict(), [speechlike(8000)])
+    yield ("stft_silence", "stft", dict(), [np.zeros((1, 800))])
+    # ---- acorr / levdur / lpc (tests/test_acorr.py:23-46, test_levdur.py, test_lpc.py)
+    x14 = r.standard_normal((4, 14))
+    for M in (12, 13):
+        for of in ("naive", "normalized", "biased", "unbiased"):
+            yield (f"acorr_14_m{M}_{of}", "acorr", dict(acr_order=M, out_format=of), [x14])
+    wfr = fr * np.blackman(400)
+    yield ("acorr_400_24", "acorr", dict(acr_order=24), [wfr])
+    r52 = r.standard_normal((5, 52))
+    # levdur needs a valid autocorrelation: take it from noise (computed in float64 here)
+    ac30 = np.stack([np.correlate(v, v, "full")[51:51 + 31] for v in r52])
+    yield ("levdur_30", "levdur", dict(), [ac30])
+    yield ("levdur_30_eps", "levdur", dict(eps=1e-3), [ac30])
+    ac24 = np.stack([np.correlate(v, v, "full")[399:399 + 25] for v in wfr.reshape(-1, 400)[:8]])
+    yield ("levdur_24", "levdur", dict(), [ac24])
+    yield ("lpc_30_14", "lpc", dict(lpc_order=14), [r.standard_normal((3, 30))])
+    yield ("lpc_400_24", "lpc", dict(lpc_order=24), [wfr])
+    sp = speechlike(8000)
+    spf = np.stack([sp[i * 80:i * 80 + 400] for i in range(20, 80)]) * np.blackman(400)
+    yield ("lpc_speech_24_eps", "lpc", dict(lpc_order=24, eps=1e-5), [spf])
+    # ---- freqt (tests/test_freqt.py:23-50) -------------------------------------------
+    c20 = r.standard_normal((4, 20))
+    yield ("freqt_19_29", "freqt", dict(out_order=29, alpha=0.1), [c20])
+    yield ("freqt_24_24_042", "freqt", dict(out_order=24, alpha=0.42), [r.standard_normal((6, 25))])
+    yield ("freqt_256_24", "freqt", dict(out_order=24, alpha=0.42), [r.standard_normal((3, 257)) * 0.1])
+    yield ("freqt_0_0", "freqt", dict(out_order=0, alpha=0.3), [r.standard_normal((3, 1))])
+    # ---- mcep (tests/test_mcep.py:23-54) ---------------------------------------------
+    P32 = np.square(np.abs(np.fft.rfft(r.standard_normal((4, 32)), axis=-1))) + 1e-3
+    for M in (0, 7, 8):
+        for it in (0, 3):
+            yield (f"mcep_32_m{M}_i{it}", "mcep", dict(cep_order=M, alpha=0.1, n_iter=it), [P32])
+    import oracle.np_oracle as O  # inputs only (power spectra), not outputs
+    Pb = O.stft(x_b[:2, :4000])
+    yield ("mcep_baseline", "mcep", dict(cep_order=24, alpha=0.42, n_iter=10), [Pb])
+    yield ("mcep_speech", "mcep", dict(cep_order=24, alpha=0.42, n_iter=10), [O.stft(sp)])
+    # ---- fbank / mfcc / dct ----------------------------------------------------------
+    for of in ("y", "yE"):
+        yield (f"fbank_32_{of}", "fbank",
+               dict(n_channel=10, sample_rate=8000, f_min=300, f_max=3400, floor=1.0, out_format=of), [P32 * 50])
+    for sc in ("htk", "mel", "bark", "linear"):
+        yield (f"fbank_512_{sc}", "fbank", dict(n_channel=40, sample_rate=16000, scale=sc, out_format="yE"), [Pb])
+    yield ("fbank_512_erb", "fbank", dict(n_channel=40, sample_rate=16000, erb_factor=1.0), [Pb])
+    yield ("fbank_512_gamma_pow", "fbank", dict(n_channel=40, sample_rate=16000, gamma=-0.5, use_power=True), [Pb])
+    for of in ("y", "yE", "yc", "ycE"):
+        yield (f"mfcc_32_{of}", "mfcc",
+               dict(mfcc_order=4, n_channel=10, sample_rate=8000, lifter=20, f_min=300, f_max=3400,
+                    floor=1.0, out_format=of), [P32 * 50])
+    yield ("mfcc_baseline", "mfcc", dict(mfcc_order=13, n_channel=40, sample_rate=16000), [Pb])
+    yield ("mfcc_baseline_ycE_l22", "mfcc",
+           dict(mfcc_order=13, n_channel=40, sample_rate=16000, lifter=22, out_format="ycE"), [Pb])
+    x8 = r.standard_normal((3, 8))
+    for t in (1, 2, 3, 4):
+        yield (f"dct_8_t{t}", "dct", dict(dct_type=t), [x8])
+    yield ("dct_40", "dct", dict(), [r.standard_normal((5, 40))])
+
+
+def main():
+    sys.path.insert(0, ROOT)
+    import torch
+    from oracle.ref_shim import load_reference
+
+    D = load_reference()
+    if D is None:
+        raise SystemExit("reference not importable: golden vectors can only be made in the build container")
+    F = D.functional
+    manifest = {}
+    for dt_name, tdt, ndt in (("f32", torch.float32, np.float32), ("f64", torch.float64, np.float64)):
+        store = {}
+        for name, op, params, inputs in cases():
+            tin = [None if v is None else torch.from_numpy(np.ascontiguousarray(v.astype(ndt))) for v in inputs]
+            with torch.no_grad():
+                out = getattr(F, op)(*tin, **params)
+            outs = out if isinstance(out, tuple) else (out,)
+            for i, v in enumerate(inputs):
+                if v is not None:
+                    store[f"{name}/in{i}"] = v.astype(ndt)
+            for i, o in enumerate(outs):
+                store[f"{name}/out{i}"] = o.numpy()
+            manifest[name] = dict(op=op, params=params, n_in=len(inputs),
+                                  none_in=[i for i, v in enumerate(inputs) if v is None], n_out=len(outs))
+        np.savez_compressed(os.path.join(HERE, f"golden_{dt_name}.npz"), **store)
+        print(dt_name, len(store), "arrays")
+    with open(os.path.join(HERE, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+    print("cases:", len(manifest))
+
+
+if __name__ == "__main__":
+    main()
