@@ -1,0 +1,29 @@
+"""nn.Module mirror of the hot-path subset of ``diffsptk.modules`` (same names and aliases as
+diffsptk/modules/__init__.py:17-175)."""
+
+from .acorr import Autocorrelation
+from .dct import DiscreteCosineTransform
+from .dct import DiscreteCosineTransform as DCT
+from .fbank import MelFilterBankAnalysis
+from .fbank import MelFilterBankAnalysis as FBANK
+from .fftr import RealValuedFastFourierTransform
+from .frame import Frame
+from .freqt import FrequencyTransform
+from .levdur import LevinsonDurbin
+from .lpc import LinearPredictiveCodingAnalysis
+from .lpc import LinearPredictiveCodingAnalysis as LPC
+from .mcep import MelCepstralAnalysis
+from .mfcc import MelFrequencyCepstralCoefficientsAnalysis
+from .mfcc import MelFrequencyCepstralCoefficientsAnalysis as MFCC
+from .spec import Spectrum
+from .stft import ShortTimeFourierTransform
+from .stft import ShortTimeFourierTransform as STFT
+from .window import Window
+
+__all__ = [
+    "Autocorrelation", "DiscreteCosineTransform", "DCT", "MelFilterBankAnalysis", "FBANK",
+    "RealValuedFastFourierTransform", "Frame", "FrequencyTransform", "LevinsonDurbin",
+    "LinearPredictiveCodingAnalysis", "LPC", "MelCepstralAnalysis",
+    "MelFrequencyCepstralCoefficientsAnalysis", "MFCC", "Spectrum", "ShortTimeFourierTransform", "STFT",
+    "Window",
+]

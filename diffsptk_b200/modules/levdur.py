@@ -1,0 +1,64 @@
+"""Levinson-Durbin (drop-in for diffsptk/modules/levdur.py)."""
+
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ..utils import check_size, filter_values
+from .base import BaseFunctionalModule, Precomputed
+
+
+def default_eps(eps: float | None, dtype: torch.dtype | None) -> float:
+    """1e-5 for float32 modules, 0 otherwise (levdur.py:108-110)."""
+    if eps is not None:
+        return eps
+    return 1e-5 if (dtype or torch.get_default_dtype()) == torch.float else 0.0
+
+
+class LevinsonDurbin(BaseFunctionalModule):
+    """``(..., M+1) -> (..., M+1)`` = [K, a_1..a_M]; kernel ``dsb200_levdur``.
+
+    The reference adds ``eps * I`` to a dense Toeplitz matrix and calls ``torch.linalg.solve``
+    (levdur.py:113-127); the kernel runs the Levinson recursion on the same regularised system.
+    The ``eye`` buffer is kept (name and shape) for state compatibility; eps is read from it.
+    """
+
+    _takes_input_size = True
+
+    def __init__(self, lpc_order: int, eps: float | None = None, device: torch.device | None = None,
+                 dtype: torch.dtype | None = None) -> None:
+        super().__init__()
+        self.in_dim = lpc_order + 1
+        self._register_precomputed(self._precompute(**filter_values(locals())))
+
+    def forward(self, r: torch.Tensor) -> torch.Tensor:
+        check_size(r.size(-1), self.in_dim, "dimension of autocorrelation")
+        return self._call_forward(r)
+
+    @staticmethod
+    def _func(r: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        pre = LevinsonDurbin._precompute(r.size(-1) - 1, *args, **kwargs, device=r.device, dtype=r.dtype)
+        return LevinsonDurbin._apply_precomputed(pre, r=r)
+
+    @staticmethod
+    def _check(lpc_order: int, eps: float | None) -> None:
+        if lpc_order < 0:
+            raise ValueError("lpc_order must be non-negative.")
+        if eps is not None and eps < 0:
+            raise ValueError("eps must be non-negative.")
+
+    @staticmethod
+    def _precompute(lpc_order: int, eps: float | None, device: torch.device | None,
+                    dtype: torch.dtype | None) -> Precomputed:
+        LevinsonDurbin._check(lpc_order, eps)
+        if dtype is not None and not dtype.is_floating_point:
+            dtype = None
+        eps = default_eps(eps, dtype)
+        eye = torch.eye(lpc_order, device=device, dtype=dtype) * eps
+        return Precomputed(values={"eps": float(eps)}, tensors={"eye": eye})
+
+    @staticmethod
+    def _forward(r: torch.Tensor, *, eps: float, eye: torch.Tensor) -> torch.Tensor:
+        ops._no_grad_check(r)
+        return ops.levdur(r, eps)

@@ -1,0 +1,68 @@
+"""Spectrum of b / a (drop-in for diffsptk/modules/spec.py)."""
+
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ..utils import filter_values
+from .base import BaseFunctionalModule, Precomputed
+
+_FORMATS = {"db": 0, "log-magnitude": 1, "magnitude": 2, "power": 3}
+
+
+def spec_format_id(out_format, allow_complex: bool = False) -> int:
+    if isinstance(out_format, str):
+        if out_format in _FORMATS:
+            return _FORMATS[out_format]
+        if allow_complex and out_format == "complex":
+            return 4
+    elif isinstance(out_format, int) and not isinstance(out_format, bool) and 0 <= out_format <= 3:
+        return out_format
+    raise ValueError(f"out_format {out_format} is not supported.")
+
+
+class Spectrum(BaseFunctionalModule):
+    """``(..., M+1) [, (..., N+1)] -> (..., L/2+1)``; kernel ``dsb200_spec``."""
+
+    def __init__(self, fft_length: int, *, eps: float = 0, relative_floor: float | None = None,
+                 out_format: str | int = "power", learnable: bool = False) -> None:
+        super().__init__()
+        self._register_precomputed(self._precompute(**filter_values(locals())))
+
+    def forward(self, b: torch.Tensor | None = None, a: torch.Tensor | None = None) -> torch.Tensor:
+        return self._call_forward(b, a)
+
+    @staticmethod
+    def _func(b: torch.Tensor | None = None, a: torch.Tensor | None = None, *args, **kwargs) -> torch.Tensor:
+        pre = Spectrum._precompute(*args, **kwargs, module=False)
+        return Spectrum._apply_precomputed(pre, b=b, a=a)
+
+    @staticmethod
+    def _check(fft_length: int, eps: float, relative_floor: float | None) -> None:
+        if fft_length <= 1:
+            raise ValueError("fft_length must be greater than 1.")
+        if fft_length % 2 == 1:
+            raise ValueError("fft_length must be positive even.")
+        if eps < 0:
+            raise ValueError("eps must be non-negative.")
+        if relative_floor is not None and 0 <= relative_floor:
+            raise ValueError("relative_floor must be negative.")
+
+    @staticmethod
+    def _precompute(fft_length: int, eps: float, relative_floor: float | None, out_format: str | int,
+                    learnable: bool = False, module: bool = True) -> Precomputed:
+        Spectrum._check(fft_length, eps, relative_floor)
+        if learnable:
+            raise NotImplementedError("learnable DFT basis is not part of the B200 hot path")
+        linear_floor = None if relative_floor is None else 10 ** (relative_floor / 10)  # spec.py:121-122
+        return Precomputed(values={"fft_length": fft_length, "eps": eps, "relative_floor": linear_floor,
+                                   "out_format": spec_format_id(out_format)})
+
+    @staticmethod
+    def _forward(b: torch.Tensor | None, a: torch.Tensor | None, *, fft_length: int, eps: float,
+                 relative_floor: float | None, out_format: int) -> torch.Tensor:
+        if b is None and a is None:
+            raise ValueError("Either b or a must be specified.")
+        ops._no_grad_check(b, a)
+        return ops.spec(b, a, fft_length, eps, -1.0 if relative_floor is None else relative_floor, out_format)

@@ -1,0 +1,424 @@
+"""``torch.ops.diffsptk_b200.*``: the boundary between the nn.Module mirror and the C ABI.
+
+Each op flattens leading batch dims, allocates the output with torch (the
+library owns no data memory), and calls the matching ``dsb200_*`` entry point
+with raw device pointers and the current CUDA stream.  Ops are registered for
+CUDA only: a CPU tensor fails in the dispatcher -- there is no fallback path.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+from torch import Tensor
+
+from . import _native as N
+
+_NS = "diffsptk_b200"
+
+
+# ------------------------------------------------------------------------------------ helpers
+def _f64(t: Tensor) -> bool:
+    return t.dtype == torch.float64
+
+
+def _native_dtype(*ts: Tensor) -> torch.dtype:
+    """float64 if any operand is float64, else float32 (ints / half / bf16 are up-cast)."""
+    return torch.float64 if any(t is not None and t.dtype == torch.float64 for t in ts) else torch.float32
+
+
+def _prep(t: Optional[Tensor], dtype: torch.dtype) -> Optional[Tensor]:
+    if t is None:
+        return None
+    if t.dtype != dtype:
+        t = t.to(dtype)
+    return t.contiguous()
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None or t.numel() == 0 else C.c_void_p(t.data_ptr())
+
+
+def _ptr_or_dummy(t: Tensor):
+    # zero-sized tensors have no storage; the library never dereferences when rows == 0
+    return C.c_void_p(t.data_ptr()) if t.numel() else None
+
+
+def _stream(t: Tensor):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _dev(t: Tensor) -> int:
+    if not t.is_cuda:
+        raise RuntimeError("diffsptk_b200 ops run on CUDA tensors only (no CPU fallback).")
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _no_grad_check(*ts):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
+        raise NotImplementedError(
+            "diffsptk_b200 kernels are forward-only: wrap the call in torch.no_grad() or detach() "
+            "the inputs (autograd for the fused ops is listed under 'next' in DESIGN.md)."
+        )
+
+
+def num_frames(T: int, frame_period: int) -> int:
+    return 0 if T <= 0 else (T - 1) // frame_period + 1
+
+
+def _frame_params(L, P, center, zmean, pad_mode) -> N.FrameParams:
+    return N.FrameParams(int(L), int(P), int(bool(center)), int(bool(zmean)), int(pad_mode))
+
+
+def _spec_params(fft_length, out_format, eps, relative_floor) -> N.SpecParams:
+    has = relative_floor is not None and relative_floor > 0
+    return N.SpecParams(int(fft_length), int(out_format), int(has), 0, float(eps), float(relative_floor) if has else 0.0)
+
+
+# ------------------------------------------------------------------------------------- kernels
+@torch.library.custom_op(f"{_NS}::frame", mutates_args=(), device_types="cuda")
+def frame(x: Tensor, frame_length: int, frame_period: int, center: bool, zmean: bool, pad_mode: int) -> Tensor:
+    dt = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
+    xc = _prep(x, dt)
+    T = xc.shape[-1]
+    if T < 1:
+        raise ValueError("waveform length must be at least 1")
+    lead = xc.shape[:-1]
+    B = xc.numel() // T
+    n = num_frames(T, frame_period)
+    y = torch.empty((*lead, n, frame_length), device=x.device, dtype=dt)
+    p = _frame_params(frame_length, frame_period, center, zmean, pad_mode)
+    N.check(N.typed("dsb200_frame", dt == torch.float64)(_ptr(xc), _ptr(y), B, T, C.byref(p), _dev(x), _stream(x)))
+    return y
+
+
+@frame.register_fake
+def _(x, frame_length, frame_period, center, zmean, pad_mode):
+    dt = x.dtype if x.dtype in (torch.float32, torch.float64) else torch.float32
+    return x.new_empty((*x.shape[:-1], num_frames(x.shape[-1], frame_period), frame_length), dtype=dt)
+
+
+@torch.library.custom_op(f"{_NS}::window", mutates_args=(), device_types="cuda")
+def window(x: Tensor, w: Tensor, out_length: int) -> Tensor:
+    dt = _native_dtype(x, w)
+    xc, wc = _prep(x, dt), _prep(w, dt)
+    L1 = xc.shape[-1]
+    rows = xc.numel() // max(L1, 1)
+    y = torch.empty((*xc.shape[:-1], out_length), device=x.device, dtype=dt)
+    N.check(N.typed("dsb200_window", dt == torch.float64)(_ptr(xc), _ptr(wc), _ptr(y), rows, L1, out_length, _dev(x), _stream(x)))
+    return y
+
+
+@window.register_fake
+def _(x, w, out_length):
+    return x.new_empty((*x.shape[:-1], out_length), dtype=_native_dtype(x, w))
+
+
+@torch.library.custom_op(f"{_NS}::rfft", mutates_args=(), device_types="cuda")
+def rfft(x: Tensor, fft_length: int, out_format: int) -> Tensor:
+    """Returns real [..., K] or, for out_format 0, real [..., K, 2] (view_as_complex by the caller)."""
+    dt = _native_dtype(x)
+    xc = _prep(x, dt)
+    Lin = xc.shape[-1]
+    rows = xc.numel() // max(Lin, 1)
+    K = fft_length // 2 + 1
+    shape = (*xc.shape[:-1], K, 2) if out_format == 0 else (*xc.shape[:-1], K)
+    y = torch.empty(shape, device=x.device, dtype=dt)
+    N.check(N.typed("dsb200_rfft", dt == torch.float64)(_ptr(xc), _ptr(y), rows, Lin, fft_length, out_format, _dev(x), _stream(x)))
+    return y
+
+
+@rfft.register_fake
+def _(x, fft_length, out_format):
+    K = fft_length // 2 + 1
+    shape = (*x.shape[:-1], K, 2) if out_format == 0 else (*x.shape[:-1], K)
+    return x.new_empty(shape, dtype=_native_dtype(x))
+
+
+@torch.library.custom_op(f"{_NS}::spec", mutates_args=(), device_types="cuda")
+def spec(b: Optional[Tensor], a: Optional[Tensor], fft_length: int, eps: float, relative_floor: float,
+         out_format: int) -> Tensor:
+    """relative_floor is the LINEAR factor (<= 0 means none)."""
+    ref = b if b is not None else a
+    if ref is None:
+        raise ValueError("Either b or a must be specified.")
+    dt = _native_dtype(b, a)
+    bc, ac = _prep(b, dt), _prep(a, dt)
+    lead = ref.shape[:-1]
+    if bc is not None and ac is not None and bc.shape[:-1] != ac.shape[:-1]:
+        lead = torch.broadcast_shapes(bc.shape[:-1], ac.shape[:-1])
+        bc = bc.expand(*lead, bc.shape[-1]).contiguous()
+        ac = ac.expand(*lead, ac.shape[-1]).contiguous()
+    rows = 1
+    for s in lead:
+        rows *= s
+    K = fft_length // 2 + 1
+    y = torch.empty((*lead, K), device=ref.device, dtype=dt)
+    p = _spec_params(fft_length, out_format, eps, relative_floor)
+    N.check(N.typed("dsb200_spec", dt == torch.float64)(
+        _ptr(bc), 0 if bc is None else bc.shape[-1], _ptr(ac), 0 if ac is None else ac.shape[-1],
+        _ptr(y), rows, C.byref(p), _dev(ref), _stream(ref)))
+    return y
+
+
+@spec.register_fake
+def _(b, a, fft_length, eps, relative_floor, out_format):
+    ref = b if b is not None else a
+    lead = ref.shape[:-1]
+    if b is not None and a is not None:
+        lead = torch.broadcast_shapes(b.shape[:-1], a.shape[:-1])
+    return ref.new_empty((*lead, fft_length // 2 + 1), dtype=_native_dtype(b, a))
+
+
+@torch.library.custom_op(f"{_NS}::stft", mutates_args=(), device_types="cuda")
+def stft(x: Tensor, window: Tensor, frame_period: int, fft_length: int, center: bool, zmean: bool,
+         pad_mode: int, eps: float, relative_floor: float, out_format: int) -> Tensor:
+    """Fused frame+window+rFFT+formatter.  Complex output comes back as real [..., N, K, 2]."""
+    dt = _native_dtype(x, window)
+    xc, wc = _prep(x, dt), _prep(window, dt)
+    T = xc.shape[-1]
+    if T < 1:
+        raise ValueError("waveform length must be at least 1")
+    B = xc.numel() // T
+    L = wc.shape[-1]
+    n = num_frames(T, frame_period)
+    K = fft_length // 2 + 1
+    shape = (*xc.shape[:-1], n, K, 2) if out_format == 4 else (*xc.shape[:-1], n, K)
+    y = torch.empty(shape, device=x.device, dtype=dt)
+    p = N.StftParams(_frame_params(L, frame_period, center, zmean, pad_mode),
+                     _spec_params(fft_length, out_format, eps, relative_floor))
+    N.check(N.typed("dsb200_stft", dt == torch.float64)(_ptr(xc), _ptr(wc), _ptr(y), B, T, C.byref(p), _dev(x), _stream(x)))
+    return y
+
+
+@stft.register_fake
+def _(x, window, frame_period, fft_length, center, zmean, pad_mode, eps, relative_floor, out_format):
+    n, K = num_frames(x.shape[-1], frame_period), fft_length // 2 + 1
+    shape = (*x.shape[:-1], n, K, 2) if out_format == 4 else (*x.shape[:-1], n, K)
+    return x.new_empty(shape, dtype=_native_dtype(x, window))
+
+
+@torch.library.custom_op(f"{_NS}::acorr", mutates_args=(), device_types="cuda")
+def acorr(x: Tensor, acr_order: int, out_format: int) -> Tensor:
+    dt = _native_dtype(x)
+    xc = _prep(x, dt)
+    L = xc.shape[-1]
+    rows = xc.numel() // max(L, 1)
+    r = torch.empty((*xc.shape[:-1], acr_order + 1), device=x.device, dtype=dt)
+    N.check(N.typed("dsb200_acorr", dt == torch.float64)(_ptr(xc), _ptr(r), rows, L, acr_order, out_format, _dev(x), _stream(x)))
+    return r
+
+
+@acorr.register_fake
+def _(x, acr_order, out_format):
+    return x.new_empty((*x.shape[:-1], acr_order + 1), dtype=_native_dtype(x))
+
+
+@torch.library.custom_op(f"{_NS}::levdur", mutates_args=(), device_types="cuda")
+def levdur(r: Tensor, eps: float) -> Tensor:
+    dt = _native_dtype(r)
+    rc = _prep(r, dt)
+    D = rc.shape[-1]
+    rows = rc.numel() // max(D, 1)
+    a = torch.empty_like(rc)
+    N.check(N.typed("dsb200_levdur", dt == torch.float64)(_ptr(rc), _ptr(a), rows, D - 1, eps, _dev(r), _stream(r)))
+    return a
+
+
+@levdur.register_fake
+def _(r, eps):
+    return r.new_empty(r.shape, dtype=_native_dtype(r))
+
+
+@torch.library.custom_op(f"{_NS}::lpc", mutates_args=(), device_types="cuda")
+def lpc(x: Tensor, lpc_order: int, eps: float) -> Tensor:
+    dt = _native_dtype(x)
+    xc = _prep(x, dt)
+    L = xc.shape[-1]
+    rows = xc.numel() // max(L, 1)
+    a = torch.empty((*xc.shape[:-1], lpc_order + 1), device=x.device, dtype=dt)
+    N.check(N.typed("dsb200_lpc", dt == torch.float64)(_ptr(xc), _ptr(a), rows, L, lpc_order, eps, _dev(x), _stream(x)))
+    return a
+
+
+@lpc.register_fake
+def _(x, lpc_order, eps):
+    return x.new_empty((*x.shape[:-1], lpc_order + 1), dtype=_native_dtype(x))
+
+
+@torch.library.custom_op(f"{_NS}::lpc_wave", mutates_args=(), device_types="cuda")
+def lpc_wave(x: Tensor, window: Tensor, frame_period: int, center: bool, zmean: bool, pad_mode: int,
+             lpc_order: int, eps: float) -> Tensor:
+    dt = _native_dtype(x, window)
+    xc, wc = _prep(x, dt), _prep(window, dt)
+    T = xc.shape[-1]
+    B = xc.numel() // max(T, 1)
+    n = num_frames(T, frame_period)
+    a = torch.empty((*xc.shape[:-1], n, lpc_order + 1), device=x.device, dtype=dt)
+    p = _frame_params(wc.shape[-1], frame_period, center, zmean, pad_mode)
+    N.check(N.typed("dsb200_lpc_wave", dt == torch.float64)(_ptr(xc), _ptr(wc), _ptr(a), B, T, C.byref(p), lpc_order, eps, _dev(x), _stream(x)))
+    return a
+
+
+@lpc_wave.register_fake
+def _(x, window, frame_period, center, zmean, pad_mode, lpc_order, eps):
+    return x.new_empty((*x.shape[:-1], num_frames(x.shape[-1], frame_period), lpc_order + 1), dtype=_native_dtype(x, window))
+
+
+@torch.library.custom_op(f"{_NS}::rowmat", mutates_args=(), device_types="cuda")
+def rowmat(x: Tensor, W: Tensor) -> Tensor:
+    dt = _native_dtype(x, W)
+    xc, Wc = _prep(x, dt), _prep(W, dt)
+    Din, Dout = Wc.shape
+    rows = xc.numel() // max(Din, 1)
+    y = torch.empty((*xc.shape[:-1], Dout), device=x.device, dtype=dt)
+    N.check(N.typed("dsb200_rowmat", dt == torch.float64)(_ptr(xc), _ptr(Wc), _ptr(y), rows, Din, Dout, _dev(x), _stream(x)))
+    return y
+
+
+@rowmat.register_fake
+def _(x, W):
+    return x.new_empty((*x.shape[:-1], W.shape[1]), dtype=_native_dtype(x, W))
+
+
+@torch.library.custom_op(f"{_NS}::mcep", mutates_args=(), device_types="cuda")
+def mcep(x: Tensor, P0: Tensor, G: Tensor, Hm: Tensor, alpha_vector: Tensor, n_iter: int) -> Tensor:
+    dt = _native_dtype(x, alpha_vector)
+    xc = _prep(x, dt)
+    K = xc.shape[-1]
+    D = alpha_vector.shape[-1]
+    rows = xc.numel() // max(K, 1)
+    mc = torch.empty((*xc.shape[:-1], D), device=x.device, dtype=dt)
+    p = N.McepParams(2 * (K - 1), D - 1, n_iter, 0)
+    N.check(N.typed("dsb200_mcep", dt == torch.float64)(
+        _ptr(xc), _ptr(mc), rows, C.byref(p), _ptr(_prep(P0, dt)), _ptr(_prep(G, dt)), _ptr(_prep(Hm, dt)),
+        _ptr(_prep(alpha_vector, dt)), _dev(x), _stream(x)))
+    return mc
+
+
+@mcep.register_fake
+def _(x, P0, G, Hm, alpha_vector, n_iter):
+    return x.new_empty((*x.shape[:-1], alpha_vector.shape[-1]), dtype=_native_dtype(x, alpha_vector))
+
+
+@torch.library.custom_op(f"{_NS}::fbank", mutates_args=(), device_types="cuda")
+def fbank(x: Tensor, H: Tensor, col_begin: Optional[Tensor], col_end: Optional[Tensor], floor: float,
+          gamma: float, use_power: bool, want_energy: bool) -> tuple[Tensor, Tensor]:
+    dt = _native_dtype(x, H)
+    xc, Hc = _prep(x, dt), _prep(H, dt)
+    K, Cn = Hc.shape
+    rows = xc.numel() // max(K, 1)
+    y = torch.empty((*xc.shape[:-1], Cn), device=x.device, dtype=dt)
+    E = torch.empty((*xc.shape[:-1], 1) if want_energy else (0,), device=x.device, dtype=dt)
+    p = N.FbankParams(2 * (K - 1), Cn, int(use_power), int(want_energy), float(floor), float(gamma))
+    N.check(N.typed("dsb200_fbank", dt == torch.float64)(
+        _ptr(xc), _ptr(Hc), _ptr(col_begin), _ptr(col_end), _ptr(y), _ptr(E) if want_energy else None, rows,
+        C.byref(p), _dev(x), _stream(x)))
+    return y, E
+
+
+@fbank.register_fake
+def _(x, H, col_begin, col_end, floor, gamma, use_power, want_energy):
+    dt = _native_dtype(x, H)
+    return (x.new_empty((*x.shape[:-1], H.shape[1]), dtype=dt),
+            x.new_empty((*x.shape[:-1], 1) if want_energy else (0,), dtype=dt))
+
+
+def _mfcc_dim(M: int, out_format: int) -> int:
+    return M + (0, 1, 1, 2)[out_format]
+
+
+@torch.library.custom_op(f"{_NS}::mfcc", mutates_args=(), device_types="cuda")
+def mfcc(x: Tensor, H: Tensor, col_begin: Optional[Tensor], col_end: Optional[Tensor], W: Tensor,
+         lifter: Tensor, floor: float, gamma: float, out_format: int) -> Tensor:
+    dt = _native_dtype(x, H)
+    xc, Hc, Wc, lc = _prep(x, dt), _prep(H, dt), _prep(W, dt), _prep(lifter, dt)
+    K, Cn = Hc.shape
+    M = lc.shape[-1] - 1
+    rows = xc.numel() // max(K, 1)
+    y = torch.empty((*xc.shape[:-1], _mfcc_dim(M, out_format)), device=x.device, dtype=dt)
+    p = N.MfccParams(N.FbankParams(2 * (K - 1), Cn, 0, 0, float(floor), float(gamma)), M, out_format)
+    N.check(N.typed("dsb200_mfcc", dt == torch.float64)(
+        _ptr(xc), _ptr(Hc), _ptr(col_begin), _ptr(col_end), _ptr(Wc), _ptr(lc), _ptr(y), rows, C.byref(p),
+        _dev(x), _stream(x)))
+    return y
+
+
+@mfcc.register_fake
+def _(x, H, col_begin, col_end, W, lifter, floor, gamma, out_format):
+    return x.new_empty((*x.shape[:-1], _mfcc_dim(lifter.shape[-1] - 1, out_format)), dtype=_native_dtype(x, H))
+
+
+@torch.library.custom_op(f"{_NS}::mfcc_wave", mutates_args=(), device_types="cuda")
+def mfcc_wave(x: Tensor, window: Tensor, H: Tensor, col_begin: Optional[Tensor], col_end: Optional[Tensor],
+              W: Tensor, lifter: Tensor, frame_period: int, fft_length: int, center: bool, zmean: bool,
+              pad_mode: int, eps: float, floor: float, gamma: float, out_format: int) -> Tensor:
+    dt = _native_dtype(x, window, H)
+    xc, wc, Hc, Wc, lc = (_prep(t, dt) for t in (x, window, H, W, lifter))
+    T = xc.shape[-1]
+    B = xc.numel() // max(T, 1)
+    n = num_frames(T, frame_period)
+    K, Cn = Hc.shape
+    M = lc.shape[-1] - 1
+    y = torch.empty((*xc.shape[:-1], n, _mfcc_dim(M, out_format)), device=x.device, dtype=dt)
+    sp = N.StftParams(_frame_params(wc.shape[-1], frame_period, center, zmean, pad_mode),
+                      _spec_params(fft_length, 3, eps, None))
+    mp = N.MfccParams(N.FbankParams(fft_length, Cn, 0, 0, float(floor), float(gamma)), M, out_format)
+    N.check(N.typed("dsb200_mfcc_wave", dt == torch.float64)(
+        _ptr(xc), _ptr(wc), _ptr(Hc), _ptr(col_begin), _ptr(col_end), _ptr(Wc), _ptr(lc), _ptr(y), B, T,
+        C.byref(sp), C.byref(mp), _dev(x), _stream(x)))
+    return y
+
+
+@mfcc_wave.register_fake
+def _(x, window, H, col_begin, col_end, W, lifter, frame_period, fft_length, center, zmean, pad_mode, eps,
+      floor, gamma, out_format):
+    return x.new_empty((*x.shape[:-1], num_frames(x.shape[-1], frame_period),
+                        _mfcc_dim(lifter.shape[-1] - 1, out_format)), dtype=_native_dtype(x, window, H))
+
+
+# ------------------------------------------------------------------------- host-buffer pipeline
+class HostStftPipeline:
+    """Pinned host -> device -> fused STFT -> pinned host, chunked and overlapped (C ABI object)."""
+
+    def __init__(self, window: Tensor, T: int, frame_period: int, fft_length: int, *, chunk_utterances: int = 32,
+                 center: bool = True, zmean: bool = False, pad_mode: int = 0, eps: float = 1e-9,
+                 relative_floor: Optional[float] = None, out_format: int = 3):
+        if not window.is_cuda:
+            raise RuntimeError("the window table must live on the CUDA device")
+        self.window = window.contiguous()
+        self.is_f64 = window.dtype == torch.float64
+        self.T, self.N, self.K = T, num_frames(T, frame_period), fft_length // 2 + 1
+        self.out_format = out_format
+        self._p = N.StftParams(_frame_params(window.shape[-1], frame_period, center, zmean, pad_mode),
+                               _spec_params(fft_length, out_format, eps, relative_floor))
+        self._h = C.c_void_p()
+        N.check(N.load().dsb200_pipeline_create(C.byref(self._h), _dev(window), chunk_utterances, T,
+                                                C.byref(self._p), int(self.is_f64)))
+
+    def out_shape(self, batch: int):
+        return (batch, self.N, self.K, 2) if self.out_format == 4 else (batch, self.N, self.K)
+
+    def __call__(self, x_host: Tensor, y_host: Optional[Tensor] = None) -> Tensor:
+        dt = torch.float64 if self.is_f64 else torch.float32
+        if x_host.is_cuda or x_host.dtype != dt or not x_host.is_contiguous() or x_host.dim() != 2 or x_host.shape[1] != self.T:
+            raise ValueError("x_host must be a contiguous CPU tensor of shape [batch, T] in the pipeline dtype")
+        B = x_host.shape[0]
+        if y_host is None:
+            y_host = torch.empty(self.out_shape(B), dtype=dt, pin_memory=True)
+        N.check(N.load().dsb200_pipeline_stft_host(self._h, C.c_void_p(x_host.data_ptr()), _ptr(self.window),
+                                                   C.c_void_p(y_host.data_ptr()), B))
+        return y_host
+
+    def close(self):
+        if self._h:
+            N.load().dsb200_pipeline_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

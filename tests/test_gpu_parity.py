@@ -1,0 +1,250 @@
+"""GPU parity: the CUDA path (through functional API -> torch.ops -> C ABI) against the committed
+golden vectors of the reference and against the numpy oracle.
+
+Tolerances are the reference's own (tests/utils.py:66-72 there): float32 rtol 1e-4 / atol 1e-6,
+float64 rtol 1e-5 / atol 1e-8; Frame without zmean is bit-exact.  For the conditioning-dominated ops
+(levdur / lpc / mcep) in float32 the criterion is "within 4x the reference's own float32-vs-float64
+error on that row" (helpers.assert_close_conditioned).
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+ILL = {"levdur", "lpc", "mcep"}
+TD = {"f32": torch.float32, "f64": torch.float64}
+
+
+def dev():
+    return torch.device("cuda", 0)
+
+
+def to_dev(a, prec):
+    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev(), TD[prec])
+
+
+def to_np(t):
+    return t.detach().cpu().numpy()
+
+
+def check_outputs(name, op, params, prec, got, outs):
+    got = got if isinstance(got, tuple) else (got,)
+    assert len(got) == len(outs)
+    for g, w in zip(got, outs):
+        g = to_np(g)
+        if op == "frame" and not params.get("zmean"):
+            assert np.array_equal(g, w, equal_nan=True), f"{name}: frame must be bit-exact"
+            continue
+        if prec == "f32" and op in ILL:
+            w64 = H.load_case(name, "f64")[3][0]
+            H.assert_close_conditioned(g, w, w64, what=f"{name}[f32]")
+            continue
+        loose = prec == "f32" and params.get("zmean")
+        H.assert_close(g, w, prec, what=f"{name}[{prec}]", scale_atol=True,
+                       rtol_mul=10.0 if loose else 1.0, atol_mul=10.0 if loose else 1.0)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("name", H.case_names())
+def test_functional_matches_reference(name, prec):
+    import diffsptk_b200.functional as F
+    op, params, ins, outs = H.load_case(name, prec)
+    with torch.no_grad():
+        got = getattr(F, op)(*[to_dev(a, prec) for a in ins], **params)
+    check_outputs(name, op, params, prec, got, outs)
+
+
+def build_module(op, params, ins, prec):
+    import diffsptk_b200 as B
+    dt, d = TD[prec], dev()
+    x = ins[0] if ins[0] is not None else ins[1]
+    n = x.shape[-1]
+    p = dict(params)
+    if op == "frame":
+        return B.Frame(p.pop("frame_length"), p.pop("frame_period"), **p)
+    if op == "window":
+        return B.Window(n, p.pop("out_length"), **p, device=d, dtype=dt)
+    if op == "fftr":
+        if p.get("fft_length") is None:
+            p["fft_length"] = n
+        return B.RealValuedFastFourierTransform(**p, device=d, dtype=dt)
+    if op == "spec":
+        return B.Spectrum(p.pop("fft_length"), **p)
+    if op == "stft":
+        fl, fp, nfft = p.pop("frame_length", 400), p.pop("frame_period", 80), p.pop("fft_length", 512)
+        return B.STFT(fl, fp, nfft, **p, device=d, dtype=dt)
+    if op == "acorr":
+        return B.Autocorrelation(n, **p)
+    if op == "levdur":
+        return B.LevinsonDurbin(n - 1, **p, device=d, dtype=dt)
+    if op == "lpc":
+        return B.LPC(n, **p, device=d, dtype=dt)
+    if op == "freqt":
+        return B.FrequencyTransform(n - 1, **p, device=d, dtype=dt)
+    if op == "mcep":
+        return B.MelCepstralAnalysis(fft_length=2 * n - 2, **p, device=d, dtype=dt)
+    if op == "fbank":
+        return B.FBANK(fft_length=2 * n - 2, **p, device=d, dtype=dt)
+    if op == "mfcc":
+        return B.MFCC(fft_length=2 * n - 2, **p, device=d, dtype=dt)
+    if op == "dct":
+        return B.DCT(n, **p, device=d, dtype=dt)
+    raise KeyError(op)
+
+
+MODULE_CASES = [n for n in H.case_names() if not n.startswith(("window_", "frame_ramp"))] + \
+               [n for n in H.case_names(["window"]) if n.endswith(("_8_10", "_10_None"))][::7]
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("name", MODULE_CASES)
+def test_module_matches_reference(name, prec):
+    op, params, ins, outs = H.load_case(name, prec)
+    mod = build_module(op, params, ins, prec).to(dev())
+    with torch.no_grad():
+        got = mod(*[to_dev(a, prec) for a in ins])
+    check_outputs(name, op, params, prec, got, outs)
+
+
+# ------------------------------------------------------------------ oracle at BASELINE parameters
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_stft_baseline_against_oracle_all_formats(prec):
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(11)
+    x = rng.standard_normal((4, 16000)).astype(np.float32 if prec == "f32" else np.float64)
+    xd = torch.from_numpy(x).to(dev())
+    for fmt in ("power", "magnitude", "db", "log-magnitude", "complex"):
+        want = O.stft(x.astype(np.float64), out_format=fmt)
+        got = to_np(F.stft(xd, out_format=fmt))
+        H.assert_close(got, want, prec, what=f"stft {fmt} {prec}", scale_atol=True)
+
+
+def test_full_size_batch_sampled_against_oracle():
+    """BASELINE.json config 2 at full size (256 x 10 s): every utterance is computed on the GPU, a
+    sample of utterances is recomputed by the oracle; plus size-independent properties."""
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    g = torch.Generator(device=dev()).manual_seed(1234)
+    x = torch.randn(256, 160000, generator=g, device=dev())
+    P = F.stft(x)
+    assert P.shape == (256, 2000, 257) and P.dtype == torch.float32
+    assert bool(torch.isfinite(P).all()) and float(P.min()) > 0
+    for b in (0, 1, 77, 255):
+        want = O.stft(x[b].cpu().numpy().astype(np.float64))
+        H.assert_close(to_np(P[b]), want, "f32", what=f"utterance {b}", scale_atol=True)
+    # Parseval per frame: sum_k c_k |X_k|^2 = n * sum_j (w_j x_j)^2, c_0 = c_{n/2} = 1 else 2
+    fr = F.window(F.frame(x[:8]), 512)
+    energy = (fr.double() ** 2).sum(-1) * 512
+    c = torch.full((257,), 2.0, device=dev(), dtype=torch.float64)
+    c[0] = c[-1] = 1.0
+    lhs = ((P[:8].double() - 1e-9) * c).sum(-1)
+    assert torch.allclose(lhs, energy, rtol=1e-4, atol=1e-6)
+    # shifting the waveform by one hop shifts the frames by one (interior frames)
+    Ps = F.stft(torch.roll(x[:4], -80, dims=-1))
+    assert torch.equal(Ps[:, 5:1990], P[:4, 6:1991])
+    # complex STFT is linear
+    a, b2 = x[:2], x[2:4]
+    lin = F.stft(2.0 * a - 0.5 * b2, out_format="complex")
+    ref = 2.0 * F.stft(a, out_format="complex") - 0.5 * F.stft(b2, out_format="complex")
+    assert torch.allclose(torch.view_as_real(lin), torch.view_as_real(ref), rtol=1e-4, atol=2e-5)
+
+
+def test_fused_pipelines_equal_their_cascades():
+    import diffsptk_b200 as B
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((3, 8000))
+    for prec in ("f32", "f64"):
+        xd = to_dev(x, prec)
+        got = to_np(F.lpc_from_waveform(xd, lpc_order=24))
+        fr = O.window(O.frame(x), None)
+        ref64 = O.lpc(fr, 24, eps=1e-5 if prec == "f32" else 0.0)
+        if prec == "f32":
+            ref32 = O.lpc(fr.astype(np.float32), 24)
+            H.assert_close_conditioned(got, ref32, ref64, what="lpc_from_waveform f32")
+        else:
+            H.assert_close(got, ref64, prec, what="lpc_from_waveform f64", scale_atol=True)
+        want = O.mfcc(O.stft(x), 13, 40, 16000, lifter=22, out_format="ycE")
+        got = to_np(F.mfcc_from_waveform(xd, lifter=22, out_format="ycE"))
+        H.assert_close(got, want, prec, what=f"mfcc_from_waveform {prec}", scale_atol=True)
+    seq = torch.nn.Sequential(B.Frame(400, 80), B.Window(400), B.LPC(400, 24)).to(dev())
+    fused = B.fuse(seq)
+    assert isinstance(fused, B.fused.FusedLPC)
+    xd = to_dev(x, "f32")
+    assert torch.allclose(fused(xd), seq(xd), rtol=1e-3, atol=1e-5)
+    seq = torch.nn.Sequential(B.STFT(400, 80, 512), B.MFCC(fft_length=512, mfcc_order=13, n_channel=40,
+                                                           sample_rate=16000)).to(dev())
+    fused = B.fuse(seq)
+    assert isinstance(fused, B.fused.FusedMFCC)
+    assert torch.allclose(fused(xd), seq(xd), rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------ edge cases
+def test_edge_cases():
+    import diffsptk_b200 as B
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    d = dev()
+    # empty batch, rank-3 leading dims, T = 1
+    assert F.stft(torch.zeros(0, 1000, device=d)).shape == (0, 13, 257)
+    assert F.frame(torch.zeros(0, 1000, device=d)).shape == (0, 13, 400)
+    x = torch.randn(2, 3, 1000, device=d)
+    assert F.stft(x).shape == (2, 3, 13, 257)
+    assert torch.equal(F.stft(x)[1, 2], F.stft(x[1, 2]))
+    one = torch.tensor([0.5], device=d)
+    H.assert_close(to_np(F.stft(one)), O.stft(np.array([0.5])), "f32", scale_atol=True)
+    # silence: power == eps exactly; LPC of silence with float32 eps -> zeros
+    z = torch.zeros(1, 800, device=d)
+    assert torch.equal(F.stft(z), torch.full((1, 10, 257), 1e-9, device=d))
+    assert torch.equal(F.lpc(F.window(F.frame(z)), 24), torch.zeros(1, 10, 25, device=d))
+    # non-contiguous and integer / half inputs promote like x * window
+    xt = torch.randn(1000, 2, device=d).T
+    assert torch.equal(F.stft(xt), F.stft(xt.contiguous()))
+    xi = (torch.randn(2, 1000, device=d) * 1000).to(torch.int16)
+    assert F.stft(xi).dtype == torch.float32
+    assert torch.allclose(F.stft(xi), F.stft(xi.float()))
+    assert F.stft(torch.randn(2, 1000, device=d, dtype=torch.float16)).dtype == torch.float32
+    m32 = B.STFT(400, 80, 512).to(d)
+    assert m32(torch.randn(2, 1000, device=d, dtype=torch.float64)).dtype == torch.float64
+    # frame_length > fft_length truncates each windowed frame (window.py:190-192)
+    xx = np.random.default_rng(2).standard_normal((2, 600))
+    got = to_np(F.stft(to_dev(xx, "f64"), frame_length=40, frame_period=10, fft_length=32))
+    H.assert_close(got, O.stft(xx, frame_length=40, frame_period=10, fft_length=32), "f64", scale_atol=True)
+    # non power-of-two even FFT length
+    got = to_np(F.stft(to_dev(xx, "f64"), frame_length=40, frame_period=10, fft_length=48, out_format="complex"))
+    H.assert_close(got, O.stft(xx, frame_length=40, frame_period=10, fft_length=48, out_format="complex"), "f64",
+                   scale_atol=True)
+    with pytest.raises(ValueError):
+        F.stft(torch.randn(100, device=d), fft_length=511)
+    with pytest.raises((ValueError, RuntimeError)):
+        F.frame(torch.randn(2, 100, device=d), mode="reflect")  # pad 200 >= T (torch raises here too)
+    with pytest.raises(NotImplementedError):
+        F.stft(torch.randn(1000, device=d, requires_grad=True))
+    # a side stream is honoured
+    s = torch.cuda.Stream(device=d)
+    xs = torch.randn(4, 8000, device=d)
+    ref = F.stft(xs)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s):
+        out = F.stft(xs)
+    s.synchronize()
+    assert torch.equal(out, ref)
+
+
+def test_host_pipeline_equals_device_path():
+    import diffsptk_b200.functional as F
+    from diffsptk_b200 import ops, tables
+    d = dev()
+    xh = torch.randn(10, 16000).pin_memory()
+    w = tables.make_window(400, device=d, dtype=torch.float32)
+    pipe = ops.HostStftPipeline(w, 16000, 80, 512, chunk_utterances=3)
+    yh = pipe(xh)
+    want = F.stft(xh.to(d)).cpu()
+    assert torch.equal(yh, want)
+    pipe.close()
