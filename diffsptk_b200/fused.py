@@ -41,7 +41,8 @@ def mfcc_from_waveform(x: Tensor, *, frame_length: int = 400, frame_period: int 
                        gamma: float = 0, scale: str = "htk", erb_factor: float | None = None,
                        out_format: str | int = "y", window_table: Tensor | None = None,
                        H: Tensor | None = None, W: Tensor | None = None,
-                       liftering_vector: Tensor | None = None) -> Tensor:
+                       liftering_vector: Tensor | None = None, H_begin: Tensor | None = None,
+                       H_end: Tensor | None = None) -> Tensor:
     """``(..., T) -> (..., N, D)``: STFT power (``eps``, no relative floor) -> fbank -> DCT -> lifter."""
     dt = x.dtype if x.dtype.is_floating_point else None
     dev = x.device
@@ -55,7 +56,7 @@ def mfcc_from_waveform(x: Tensor, *, frame_length: int = 400, frame_period: int 
         liftering_vector = tables.make_lifter(mfcc_order, lifter, dev, dt)
     fmt = mfcc_format_id(out_format)
     ops._no_grad_check(x, window_table, H)
-    cb, ce = support_of(H)
+    cb, ce = support_of(H, H_begin, H_end)
     try:
         return ops.mfcc_wave(x, window_table, H, cb, ce, W, liftering_vector, frame_period, fft_length, center,
                              zmean, pad_mode_id(mode), eps, floor, gamma, fmt)
@@ -92,7 +93,8 @@ class FusedMFCC(nn.Module):
         return mfcc_from_waveform(
             x, frame_period=s.frame_period, fft_length=s.fft_length, center=s.center, zmean=s.zmean,
             mode=modes[s.pad_mode], eps=s.eps, floor=m.floor, gamma=m.gamma, out_format=m.out_format,
-            window_table=s.window.window, H=m.fbank.H, W=m.dct.W, liftering_vector=m.liftering_vector)
+            window_table=s.window.window, H=m.fbank.H, W=m.dct.W, liftering_vector=m.liftering_vector,
+            H_begin=getattr(m.fbank, "H_begin", None), H_end=getattr(m.fbank, "H_end", None))
 
 
 def fuse(seq: nn.Sequential) -> nn.Module:

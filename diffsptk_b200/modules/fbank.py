@@ -30,21 +30,14 @@ def fbank_check(fft_length, n_channel, sample_rate, f_min, f_max, floor, gamma, 
         raise ValueError("erb_factor must be positive.")
 
 
-def support_of(H: torch.Tensor):
-    """Column support of a *fixed* filter bank (None, None for a trainable one: it may change)."""
-    if isinstance(H, torch.nn.Parameter) and H.requires_grad:
+def support_of(H: torch.Tensor, begin=None, end=None):
+    """Column support to hand to the kernel: the precomputed one for a fixed filter bank, none (dense
+    walk) for a trainable one, computed on the fly when the caller brought its own matrix."""
+    if isinstance(H, torch.nn.Parameter):
         return None, None
-    key = (H.data_ptr(), H._version, tuple(H.shape), str(H.device))
-    hit = _SUPPORT_CACHE.get(key)
-    if hit is None:
-        if len(_SUPPORT_CACHE) > 64:
-            _SUPPORT_CACHE.clear()
-        hit = tables.column_support(H)
-        _SUPPORT_CACHE[key] = hit
-    return hit
-
-
-_SUPPORT_CACHE: dict = {}
+    if begin is not None and end is not None:
+        return begin, end
+    return tables.column_support(H)
 
 
 class MelFilterBankAnalysis(BaseFunctionalModule):
@@ -63,8 +56,12 @@ class MelFilterBankAnalysis(BaseFunctionalModule):
                  dtype: torch.dtype | None = None) -> None:
         super().__init__()
         self.in_dim = fft_length // 2 + 1
-        self._register_precomputed(self._precompute(**filter_values(locals(), drop_keys=["learnable"])),
-                                   learnable=learnable)
+        pre = self._precompute(**filter_values(locals(), drop_keys=["learnable"]))
+        support = {k: pre.tensors.pop(k) for k in ("H_begin", "H_end")}
+        self._register_precomputed(pre, learnable=learnable)
+        if not learnable:  # a trainable H may grow new non-zeros: the kernel then walks it densely
+            for k, v in support.items():
+                self.register_buffer(k, v, persistent=False)
 
     def forward(self, x: torch.Tensor):
         check_size(x.size(-1), self.in_dim, "dimension of spectrum")
@@ -96,14 +93,15 @@ class MelFilterBankAnalysis(BaseFunctionalModule):
             dtype = None
         H = tables.make_fbank_matrix(fft_length, n_channel, sample_rate, f_min, f_max, scale, erb_factor,
                                      device, dtype)
+        begin, end = tables.column_support(H)
         return Precomputed(values=dict(floor=floor, gamma=gamma, use_power=use_power, out_format=fmt),
-                           tensors={"H": H})
+                           tensors={"H": H, "H_begin": begin, "H_end": end})
 
     @staticmethod
     def _forward(x: torch.Tensor, *, floor: float, gamma: float, use_power: bool, out_format: int,
-                 H: torch.Tensor):
+                 H: torch.Tensor, H_begin: torch.Tensor | None = None, H_end: torch.Tensor | None = None):
         ops._no_grad_check(x, H)
-        cb, ce = support_of(H)
+        cb, ce = support_of(H, H_begin, H_end)
         y, E = ops.fbank(x, H, cb, ce, floor, gamma, use_power, out_format != 0)
         if out_format == 0:
             return y

@@ -71,8 +71,9 @@ class MelFrequencyCepstralCoefficientsAnalysis(BaseFunctionalModule):
             H = tables.make_fbank_matrix(fft_length, n_channel, sample_rate, f_min, f_max, scale, erb_factor,
                                          device, dtype)
             W = tables.make_dct_matrix(n_channel, 2, device, dtype)
+            begin, end = tables.column_support(H)
             return Precomputed(values=values, tensors={"liftering_vector": liftering_vector, "H_table": H,
-                                                       "W_table": W})
+                                                       "W_table": W, "H_begin": begin, "H_end": end})
         fbank = get_layer(True, MelFilterBankAnalysis,
                           dict(fft_length=fft_length, n_channel=n_channel, sample_rate=sample_rate, f_min=f_min,
                                f_max=f_max, floor=floor, gamma=gamma, scale=scale, erb_factor=erb_factor,
@@ -86,11 +87,14 @@ class MelFrequencyCepstralCoefficientsAnalysis(BaseFunctionalModule):
     @staticmethod
     def _forward(x: torch.Tensor, *, floor: float, gamma: float, out_format: int,
                  liftering_vector: torch.Tensor, fbank=None, dct=None, H_table: torch.Tensor | None = None,
-                 W_table: torch.Tensor | None = None) -> torch.Tensor:
+                 W_table: torch.Tensor | None = None, H_begin: torch.Tensor | None = None,
+                 H_end: torch.Tensor | None = None) -> torch.Tensor:
         H = H_table if H_table is not None else fbank.H
+        if H_table is None:
+            H_begin, H_end = getattr(fbank, "H_begin", None), getattr(fbank, "H_end", None)
         W = W_table if W_table is not None else dct.W
         if x.size(-1) != H.size(0):
             raise ValueError(f"Unexpected dimension of spectrum (input {x.size(-1)} vs target {H.size(0)}).")
         ops._no_grad_check(x, H)
-        cb, ce = support_of(H)
+        cb, ce = support_of(H, H_begin, H_end)
         return ops.mfcc(x, H, cb, ce, W, liftering_vector, floor, gamma, out_format)

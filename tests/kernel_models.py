@@ -1,0 +1,99 @@
+"""numpy models of the data flow of the specialised CUDA kernels (same index arithmetic, lane by
+lane).  They let the CPU test-suite check the *algorithms* -- decomposition, twiddles, exchange
+patterns, lane-0 special cases -- against the oracle before the CUDA code ever runs.
+
+stft512 model (diffsptk_b200/csrc/stft512.cu): a 512-point real FFT as a 256-point complex FFT
+(z[m] = x[2m] + i x[2m+1]) factored 16 x 16 across the 16 lanes of a half-warp:
+
+  pass 1   lane m1 holds z[m1 + 16 j], j = 0..15, and does a radix-16 FFT over j -> index k2
+  twiddle  C[m1][k2] *= W256^(m1 k2)
+  exch. 1  transpose through shared memory: lane k2 receives C[0..15][k2]
+  pass 2   radix-16 FFT over m1 -> k1;  lane k2 holds Z[16 k1 + k2]
+  exch. 2  lane l swaps registers 8..15 with lane (16 - l) % 16 (lane 0 and 8 with themselves)
+  split    X[k], X[256-k] from Z[k], Z[256-k];  lane 0 also owns the bins 0, 128, 256
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+
+def w(n, k):
+    return np.exp(-2j * np.pi * k / n)
+
+
+def radix4(x0, x1, x2, x3):
+    t0, t1, t2, t3 = x0 + x2, x0 - x2, x1 + x3, x1 - x3
+    return t0 + t2, t1 - 1j * t3, t0 - t2, t1 + 1j * t3
+
+
+def fft16(a):
+    """Natural-order 16-point DFT as 4 x 4 (j = 4 s + c, k = r + 4 t), as in the kernel."""
+    b = [[None] * 4 for _ in range(4)]
+    for c in range(4):
+        y = radix4(a[c], a[c + 4], a[c + 8], a[c + 12])
+        for r in range(4):
+            b[c][r] = y[r] * w(16, c * r)
+    out = [None] * 16
+    for r in range(4):
+        y = radix4(b[0][r], b[1][r], b[2][r], b[3][r])
+        for t in range(4):
+            out[r + 4 * t] = y[t]
+    return out
+
+
+def stft512_frame_model(frame512):
+    """512 windowed (zero-padded) real samples -> 257 complex bins, following the kernel's lanes."""
+    x = np.asarray(frame512, dtype=np.float64)
+    z = x[0::2] + 1j * x[1::2]
+    # pass 1 + twiddle, per lane m1
+    C = np.zeros((16, 16), dtype=np.complex128)
+    for m1 in range(16):
+        A = fft16([z[m1 + 16 * j] for j in range(16)])
+        for k2 in range(16):
+            C[m1][k2] = A[k2] * w(256, m1 * k2)
+    # exchange 1 + pass 2, per lane k2: reg[k1] = Z[16 k1 + k2]
+    reg = np.zeros((16, 16), dtype=np.complex128)
+    for k2 in range(16):
+        reg[k2] = fft16([C[m1][k2] for m1 in range(16)])
+    X = np.zeros(257, dtype=np.complex128)
+
+    def butterfly(a, b, k):
+        """a = Z[k], b = Z[256-k] -> X[k], X[256-k] (k in 0..128)."""
+        E = 0.5 * (a + np.conj(b))
+        O = -0.5j * (a - np.conj(b))
+        T = w(512, k) * O
+        return E + T, np.conj(E - T)
+
+    for l in range(16):
+        partner = (16 - l) % 16
+        send = [reg[partner][8 + j] for j in range(8)]  # what lane l receives: partner's regs 8..15
+        if l == 0:
+            # lane 0 pre-permutes what it sends to itself: (reg9..reg15, reg0)
+            send = [reg[0][9 + j] for j in range(7)] + [reg[0][0]]
+        for k1 in range(8):
+            k = 16 * k1 + l
+            xa, xb = butterfly(reg[l][k1], send[7 - k1], k)
+            X[k] = xa
+            X[256 - k] = xb
+        if l == 0:  # the one extra butterfly: bin 128 pairs with itself
+            xa, _ = butterfly(reg[0][8], reg[0][8], 128)
+            X[128] = xa
+    return X
+
+
+def lpc_wave_model(frame, M, eps):
+    """Windowed frame -> [K, a_1..a_M] with time-domain lag sums and the Levinson recursion."""
+    x = np.asarray(frame, dtype=np.float64)
+    L = len(x)
+    r = np.array([np.dot(x[:L - k], x[k:]) for k in range(M + 1)])
+    a = np.zeros(M + 1)
+    E = r[0] + eps
+    for i in range(1, M + 1):
+        k = -(r[i] + np.dot(a[1:i], r[i - 1:0:-1])) / E
+        a[1:i] = a[1:i] + k * a[i - 1:0:-1]
+        a[i] = k
+        E *= 1 - k * k
+    out = a.copy()
+    out[0] = np.sqrt(r[0] + np.dot(r[1:], a[1:]))
+    return out

@@ -40,7 +40,10 @@ def test_protocol_and_buffers():
     names = {n for n, _ in B.MelCepstralAnalysis(fft_length=64, cep_order=8, alpha=0.3, n_iter=1).named_buffers()}
     assert {"alpha_vector", "freqt.A", "ifreqt.A", "rfreqt.A"} <= names
     names = {n for n, _ in B.MFCC(fft_length=64, mfcc_order=4, n_channel=8, sample_rate=8000).named_buffers()}
-    assert names == {"liftering_vector", "fbank.H", "dct.W"}
+    assert {"liftering_vector", "fbank.H", "dct.W"} <= names <= {"liftering_vector", "fbank.H", "dct.W",
+                                                                "fbank.H_begin", "fbank.H_end"}
+    lf = B.FBANK(fft_length=64, n_channel=8, sample_rate=8000, learnable=True)
+    assert [n for n, _ in lf.named_parameters()] == ["H"] and not list(lf.named_buffers())
     assert B.STFT(400, 80, 512).state_dict() == {}  # non-persistent buffers, as in the reference
     m = B.STFT(400, 80, 512, learnable=["window"])
     assert [n for n, _ in m.named_parameters()] == ["window.window"]
