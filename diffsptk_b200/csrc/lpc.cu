@@ -104,42 +104,45 @@ int launch_acorr(AcorrArgs<T>& A, int device, cudaStream_t stream) {
 //   rho = r, rho0 = r0 + eps;  E = rho0
 //   for i = 1..M:  k = -(rho_i + sum_{j<i} a_j rho_{i-j}) / E;  a_j += k a_{i-j};  a_i = k;  E *= 1 - k^2
 //   K = sqrt(r0 + sum_j r_j a_j)          (un-regularised r0, levdur.py:124)
-// In-place safe: a row is read completely before it is written.
+// The recursion state is float64 for both element types: on speech-like (ill-conditioned) frames a
+// float32 recursion loses ~4x more than the reference's pivoted float32 LU does, float64 state keeps
+// the result at the accuracy of the float32 autocorrelation itself (DFMA runs at half FP32 rate on
+// B200 and this kernel is ~5 % of the LPC path).  In-place safe: a row is read before it is written.
 template <typename T>
-__global__ void levdur_kernel(const T* r, T* out, int64_t rows, int M, T eps) {
+__global__ void levdur_kernel(const T* r, T* out, int64_t rows, int M, double eps) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tpb = blockDim.x, ld = tpb + 1, D = M + 1;
-  T* rs = reinterpret_cast<T*>(smem_raw);  // [D][ld]
-  T* as = rs + static_cast<size_t>(D) * ld;  // [D][ld]
-  T* ts = as + static_cast<size_t>(D) * ld;  // [D][ld]
+  double* rs = reinterpret_cast<double*>(smem_raw);  // [D][ld]
+  double* as = rs + static_cast<size_t>(D) * ld;     // [D][ld]
+  double* ts = as + static_cast<size_t>(D) * ld;     // [D][ld]
   for (int64_t base = static_cast<int64_t>(blockIdx.x) * tpb; base < rows; base += static_cast<int64_t>(gridDim.x) * tpb) {
     const int nrow = static_cast<int>(rows - base < tpb ? rows - base : tpb);
     for (int idx = threadIdx.x; idx < nrow * D; idx += tpb) {
       const int rl = idx / D, j = idx - rl * D;
-      rs[j * ld + rl] = r[base * D + idx];
+      rs[j * ld + rl] = static_cast<double>(r[base * D + idx]);
     }
     __syncthreads();
     const int t = threadIdx.x;
     if (t < nrow) {
-      const T r0 = rs[t];
-      T E = r0 + eps;
+      const double r0 = rs[t];
+      double E = r0 + eps;
       for (int i = 1; i <= M; ++i) {
-        T acc = rs[i * ld + t];
-        for (int j = 1; j < i; ++j) acc = dfma(as[j * ld + t], rs[(i - j) * ld + t], acc);
-        const T k = -acc / E;
-        for (int j = 1; j < i; ++j) ts[j * ld + t] = dfma(k, as[(i - j) * ld + t], as[j * ld + t]);
+        double acc = rs[i * ld + t];
+        for (int j = 1; j < i; ++j) acc = fma(as[j * ld + t], rs[(i - j) * ld + t], acc);
+        const double k = -acc / E;
+        for (int j = 1; j < i; ++j) ts[j * ld + t] = fma(k, as[(i - j) * ld + t], as[j * ld + t]);
         for (int j = 1; j < i; ++j) as[j * ld + t] = ts[j * ld + t];
         as[i * ld + t] = k;
-        E *= (static_cast<T>(1) - k * k);
+        E *= (1.0 - k * k);
       }
-      T g = r0;
-      for (int j = 1; j <= M; ++j) g = dfma(rs[j * ld + t], as[j * ld + t], g);
-      as[t] = dsqrt(g);
+      double g = r0;
+      for (int j = 1; j <= M; ++j) g = fma(rs[j * ld + t], as[j * ld + t], g);
+      as[t] = sqrt(g);
     }
     __syncthreads();
     for (int idx = threadIdx.x; idx < nrow * D; idx += tpb) {
       const int rl = idx / D, j = idx - rl * D;
-      out[base * D + idx] = as[j * ld + rl];
+      out[base * D + idx] = static_cast<T>(as[j * ld + rl]);
     }
     __syncthreads();
   }
@@ -151,13 +154,13 @@ int launch_levdur(const T* r, T* out, int64_t rows, int M, double eps, int devic
   const size_t cap = static_cast<size_t>(max_dynamic_smem(device));
   const size_t D = static_cast<size_t>(M) + 1;
   int tpb = 128;
-  auto bytes = [&](int t) { return 3 * D * (t + 1) * sizeof(T); };
+  auto bytes = [&](int t) { return 3 * D * (t + 1) * sizeof(double); };
   while (tpb > 32 && bytes(tpb) > std::min<size_t>(cap, 96 * 1024)) tpb -= 32;
   if (bytes(tpb) > cap) return fail(DSB200_E_UNSUPPORTED, "lpc_order=%d is too large for the shared-memory Levinson kernel", M);
   DSB_CUDA(cudaFuncSetAttribute(levdur_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cap)));
   const int64_t need = (rows + tpb - 1) / tpb;
   const int blocks = static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(sm_count(device)) * 8));
-  levdur_kernel<T><<<blocks, tpb, bytes(tpb), stream>>>(r, out, rows, M, static_cast<T>(eps));
+  levdur_kernel<T><<<blocks, tpb, bytes(tpb), stream>>>(r, out, rows, M, eps);
   return after_launch("levdur_kernel");
 }
 

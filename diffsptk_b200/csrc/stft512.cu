@@ -3,36 +3,42 @@
 // This is the headline kernel of BASELINE.json (fl=400, fp=80, n_fft=512): one pass over HBM
 // (each waveform sample read once, each output written once), everything else on chip.
 //
-// Mapping (see tests/kernel_models.py for a lane-by-lane numpy model of the same data flow):
-//   * A persistent CTA walks tiles of F = 2 * (half-warps per CTA) consecutive frames of one
-//     utterance.  The contiguous sample span of a tile is staged in shared memory by ONE bulk
-//     async copy (cp.async.bulk -> UBLKCP, completion on an mbarrier, double buffered); tiles that
-//     touch the padded ends of an utterance (or are not 16-byte aligned) are staged by guarded
-//     loads that implement the reference's pad modes (frame.py:130-137).
+// Mapping (tests/kernel_models.py holds a lane-by-lane numpy model of the same data flow):
+//   * Persistent CTAs, one per SM.  Every WARP runs its own software pipeline over "quads" of four
+//     consecutive frames of one utterance -- there is no CTA-wide barrier in the main loop:
+//       - the contiguous sample span of a quad is staged in shared memory by ONE bulk async copy
+//         (cp.async.bulk -> UBLKCP) completing on a warp-private mbarrier, double buffered; the
+//         part of the span that falls outside the utterance is zero-filled (constant padding,
+//         frame.py:134); other pad modes / unaligned waveforms use guarded loads for those quads;
+//       - the four finished output rows (4 x 257 floats, contiguous in HBM) are staged in shared
+//         memory and leave with ONE bulk async store (UBLKCP) per quad.
 //   * Each half-warp (16 lanes) transforms a PAIR of frames at once: every arithmetic value is a
-//     float2 holding (frame A, frame B), so butterflies issue as packed FADD2 / FMUL2 / FFMA2 --
-//     the FP32 pipe is the binding resource of this kernel (ubench: 128 lanes/clk/SM for scalar
-//     and packed alike) and packed issue frees the slots the LDS/STS/SHFL/STG traffic needs.
+//     float2 = (frame A, frame B), so butterflies issue as packed FADD2 / FMUL2 / FFMA2 with
+//     scalar-broadcast twiddles.  The FP32 pipe is the binding resource (tools/ubench: 128 results
+//     per clock per SM, scalar or packed); packed issue frees the slots LDS/STS/SHFL need.
 //   * 512-point real FFT = 256-point complex FFT of z[m] = x[2m] + i x[2m+1], factored 16 x 16:
-//     radix-16 in registers (pruned: samples >= frame_length are zero), twiddle, transpose through
-//     padded shared memory, radix-16 in registers, then the real-input split.  The split needs
-//     Z[k] and Z[256-k], which live in lanes l and 16-l: they swap 8 registers by shuffle.
-//   * |X|^2 + eps (or another spectrum format) is formed in registers and stored straight to HBM;
-//     a half-warp writes 64 contiguous bytes per instruction.
+//     radix-16 in registers (pruned: samples >= frame_length are structural zeros), W256 twiddles,
+//     16 x 16 transpose through padded shared memory (conflict-free 64-bit accesses), radix-16,
+//     then the real-input split.  The split needs Z[k] and Z[256-k], which live in lanes l and
+//     16-l: they swap 8 registers by shuffle (lane 0 pairs bins with itself).
 //
-// Envelope: float32, fft_length == 512, frame_length <= 512, even frame_period, no zmean, no
-// relative floor.  Anything else returns DSB200_E_UNSUPPORTED and the generic kernel runs.
+// Envelope: float32, fft_length == 512, frame_length <= 512, even frame_period, no zmean, no relative
+// floor (bulk copies additionally need 16-byte aligned spans, else guarded loads are used).  Anything else returns DSB200_E_UNSUPPORTED and the
+// generic kernel (spectral.cu) runs.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
 namespace dsb200 {
 namespace {
 
-constexpr int kThreads = 384;           // 12 warps = 24 half-warps -> 48 frames per tile
-constexpr int kHalfWarps = kThreads / 16;
-constexpr int kTileFrames = 2 * kHalfWarps;
-constexpr int kXchStride = 17;           // float4 units per row of the transpose buffer (16 + 1 pad)
+constexpr int kWarps = 12;
+constexpr int kThreads = kWarps * 32;
+constexpr int kXRow = 17;                              // float2 units per transpose row (16 + 1 pad)
+constexpr int kPlane = 16 * kXRow;                     // float2 units per plane
+constexpr int kXchBytesPerWarp = 2 * 2 * kPlane * 8;   // 2 half-warps x (re, im) planes = 8704 B
+constexpr int kOutFloats = 4 * 257;                    // one quad of real-valued output rows
 
 struct C2 {  // one complex value for each of the two frames of a pair
   float2 re, im;
@@ -46,9 +52,8 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __
 
 __device__ __forceinline__ C2 cadd(C2 a, C2 b) { return {add2(a.re, b.re), add2(a.im, b.im)}; }
 __device__ __forceinline__ C2 csub(C2 a, C2 b) { return {sub2(a.re, b.re), sub2(a.im, b.im)}; }
-// a - i b  and  a + i b
-__device__ __forceinline__ C2 csub_i(C2 a, C2 b) { return {add2(a.re, b.im), sub2(a.im, b.re)}; }
-__device__ __forceinline__ C2 cadd_i(C2 a, C2 b) { return {sub2(a.re, b.im), add2(a.im, b.re)}; }
+__device__ __forceinline__ C2 csub_i(C2 a, C2 b) { return {add2(a.re, b.im), sub2(a.im, b.re)}; }  // a - i b
+__device__ __forceinline__ C2 cadd_i(C2 a, C2 b) { return {sub2(a.re, b.im), add2(a.im, b.re)}; }  // a + i b
 __device__ __forceinline__ C2 cmul_s(C2 a, float wr, float wi) {
   C2 r;
   r.re = fma2s(a.im, -wi, mul2s(a.re, wr));
@@ -79,8 +84,11 @@ __device__ __forceinline__ void radix4(C2& x0, C2& x1, C2& x2, C2& x3) {
   }
 }
 
-// In-place natural-order 16-point DFT of a[0..15]; inputs a[j], j >= NJ, are structurally zero.
-// j = 4 s + c, k = r + 4 t:  W16^(jk) = W4^(s r) W16^(c r) W4^(c t).
+// 16-point DFT of a[0..15] (inputs a[j], j >= NJ, structurally zero).  With j = 4 s + c and
+// k = r + 4 t:  W16^(jk) = W4^(s r) W16^(c r) W4^(c t).  The result is left in the "digit-swapped"
+// register order a[4 r + t] = A[r + 4 t]; callers index through dig().
+__host__ __device__ constexpr int dig(int k) { return 4 * (k & 3) + (k >> 2); }
+
 template <int NJ>
 __device__ __forceinline__ void fft16(C2 (&a)[16]) {
   radix4<(12 >= NJ)>(a[0], a[4], a[8], a[12]);
@@ -117,19 +125,10 @@ __device__ __forceinline__ void fft16(C2 (&a)[16]) {
     a[11].im = mul2s(add2(v.re, v.im), -kR);
   }
   a[15] = cmul_s(a[15], -kC8, kS8);                     // c=3 r=3 : W16^9
-  // second stage over c for every r: inputs a[0+4r], a[1+4r], a[2+4r], a[3+4r] -> outputs k = r + 4 t
   radix4<false>(a[0], a[1], a[2], a[3]);      // r = 0 -> k = 0, 4, 8, 12
   radix4<false>(a[4], a[5], a[6], a[7]);      // r = 1 -> k = 1, 5, 9, 13
   radix4<false>(a[8], a[9], a[10], a[11]);    // r = 2 -> k = 2, 6, 10, 14
   radix4<false>(a[12], a[13], a[14], a[15]);  // r = 3 -> k = 3, 7, 11, 15
-  // a[4 r + t] holds A[r + 4 t]: transpose the 4 x 4 register block to natural order
-  C2 t;
-  t = a[1]; a[1] = a[4]; a[4] = t;
-  t = a[2]; a[2] = a[8]; a[8] = t;
-  t = a[3]; a[3] = a[12]; a[12] = t;
-  t = a[6]; a[6] = a[9]; a[9] = t;
-  t = a[7]; a[7] = a[13]; a[13] = t;
-  t = a[11]; a[11] = a[14]; a[14] = t;
 }
 
 struct Args {
@@ -137,12 +136,15 @@ struct Args {
   const float* window;  // [L]
   const float* tw512;   // W512^k interleaved (re, im), 512 entries
   float* y;
-  int64_t T;
-  int64_t n_frames;     // frames per utterance
-  int64_t n_tiles;      // batch * tiles_per_utt
-  int tiles_per_utt;
+  int T;                // samples per utterance
+  int n_frames;         // frames per utterance
+  int quads_per_utt;    // ceil(n_frames / 4)
+  int n_quads;          // batch * quads_per_utt
   int L, P, left, pad_mode;
-  int tile_floats;      // floats staged per tile (multiple of 4)
+  int span;             // floats staged per quad: 3 P + 32 NJ, rounded up to 4
+  int in_floats;        // floats per input buffer (>= span, multiple of 4)
+  int bulk_in;          // waveform layout allows bulk copies (alignment)
+  int bulk_out;         // output layout allows bulk stores
   float eps;
 };
 
@@ -168,6 +170,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <int FMT>
 __device__ __forceinline__ float fmt1(float s) {
@@ -177,191 +185,228 @@ __device__ __forceinline__ float fmt1(float s) {
   return s;
 }
 
-// Store one bin of both frames of the pair.
-template <int FMT>
-__device__ __forceinline__ void store_bin(float* yA, float* yB, bool vA, bool vB, int k, float2 re, float2 im, float eps) {
+// One bin of both frames of the pair: to the shared staging rows (real formats, STAGED) or to HBM.
+template <int FMT, bool STAGED>
+__device__ __forceinline__ void put_bin(float* rowA, float* rowB, bool vB, int k, float2 re, float2 im, float eps) {
   if (FMT == DSB200_SPEC_COMPLEX) {
-    if (vA) reinterpret_cast<float2*>(yA)[k] = make_float2(re.x, im.x);
-    if (vB) reinterpret_cast<float2*>(yB)[k] = make_float2(re.y, im.y);
+    reinterpret_cast<float2*>(rowA)[k] = make_float2(re.x, im.x);
+    if (vB) reinterpret_cast<float2*>(rowB)[k] = make_float2(re.y, im.y);
   } else {
     const float2 s = fma2(re, re, fma2(im, im, make_float2(eps, eps)));
-    if (vA) yA[k] = fmt1<FMT>(s.x);
-    if (vB) yB[k] = fmt1<FMT>(s.y);
+    rowA[k] = fmt1<FMT>(s.x);
+    if (STAGED || vB) rowB[k] = fmt1<FMT>(s.y);
   }
 }
 
 template <int NJ, bool MASK_ALL, int FMT>
 __global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw);            // [2]
-  float* win = reinterpret_cast<float*>(smem_raw + 16);              // [512], zero padded
-  float* tile0 = win + 512;                                          // [2][tile_floats]
-  float4* xch = reinterpret_cast<float4*>(tile0 + 2 * A.tile_floats) + (threadIdx.x >> 4) * (16 * kXchStride);
-
   const int tid = threadIdx.x;
-  const int l = tid & 15;          // lane within the half-warp
-  const int hw = tid >> 4;         // half-warp = frame pair within the tile
-  const int partner = (tid & 16) | ((16 - l) & 15);  // lane (within the warp) that holds Z[256 - k]
-  const unsigned hmask = 0xFFFFu << (tid & 16);      // this half-warp (the two halves may diverge on a partial tile)
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int l = lane & 15;   // lane within the half-warp
+  const int h = lane >> 4;   // half-warp within the warp = frame pair within the quad
+  const int partner = (lane & 16) | ((16 - l) & 15);  // lane that holds Z[256 - k]
+
+  // shared-memory carve-up: [mbar 2/warp][window 512][per warp: in0 | in1 | exchange/out-staging]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw) + 2 * warp;
+  float* win = reinterpret_cast<float*>(smem_raw + 16 * kWarps);
+  float2* htw = reinterpret_cast<float2*>(win + 512);  // [128]
+  unsigned char* wbase = smem_raw + 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) +
+                         static_cast<size_t>(warp) * (2 * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
+  float* in0 = reinterpret_cast<float*>(wbase);
+  float2* xch = reinterpret_cast<float2*>(wbase + 2 * static_cast<size_t>(A.in_floats) * 4);
+  float* ostage = reinterpret_cast<float*>(xch);            // aliases the exchange planes (see loop)
+  float2* xr = xch + h * (2 * kPlane);
+  float2* xi = xr + kPlane;
 
   for (int i = tid; i < 512; i += kThreads) win[i] = i < A.L ? A.window[i] : 0.0f;
-  if (tid == 0) {
+  if (lane == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // per-lane twiddles: W256^(l k2) for the inter-pass rotation, W512^(16 k1 + l) / 2 for the split
   const float2* tw = reinterpret_cast<const float2*>(A.tw512);
-  float twr[16], twi[16], hwr[8], hwi[8];
+  float twr[16], twi[16];
 #pragma unroll
   for (int k2 = 1; k2 < 16; ++k2) {
     const float2 v = tw[2 * l * k2];
     twr[k2] = v.x;
     twi[k2] = v.y;
   }
-#pragma unroll
-  for (int k1 = 0; k1 < 8; ++k1) {
-    const float2 v = tw[16 * k1 + l];
-    hwr[k1] = 0.5f * v.x;
-    hwi[k1] = 0.5f * v.y;
+  for (int i = tid; i < 128; i += kThreads) {  // half split-twiddles W512^k / 2, k = 16 k1 + l < 128
+    const float2 v = tw[i];
+    htw[i] = make_float2(0.5f * v.x, 0.5f * v.y);
   }
-  __syncthreads();
+  __syncthreads();  // the only CTA-wide barrier: window table + mbarrier init
 
-  // ---- tile staging ---------------------------------------------------------------------
-  const bool x_aligned = (reinterpret_cast<uintptr_t>(A.x) & 15) == 0;
-  auto tile_geom = [&](int64_t t, int64_t& b, int& n0, int64_t& s0, bool& bulk) {
-    b = t / A.tiles_per_utt;
-    n0 = static_cast<int>(t - b * A.tiles_per_utt) * kTileFrames;
-    s0 = static_cast<int64_t>(n0) * A.P - A.left;
-    bulk = x_aligned && s0 >= 0 && s0 + A.tile_floats <= A.T && (((b * A.T + s0) & 3) == 0);
-  };
-  auto stage = [&](int64_t t, int buf) {  // called by all threads
-    int64_t b, s0;
-    int n0;
-    bool bulk;
-    tile_geom(t, b, n0, s0, bulk);
-    float* dst = tile0 + buf * A.tile_floats;
-    const float* xb = A.x + b * A.T;
-    if (bulk) {
-      if (tid == 0) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_expect_tx(&mbar[buf], static_cast<uint32_t>(A.tile_floats) * 4u);
-        bulk_g2s(dst, xb + s0, static_cast<uint32_t>(A.tile_floats) * 4u, &mbar[buf]);
+  const int n_warps = gridDim.x * kWarps;
+  int q = blockIdx.x * kWarps + warp;   // consecutive warps take consecutive quads (L2 locality)
+  int b = q / A.quads_per_utt;
+  int g = q - b * A.quads_per_utt;
+  const int db = n_warps / A.quads_per_utt, dg = n_warps - db * A.quads_per_utt;
+
+  // Stage the sample span of quad (bq, gq) into `dst`.  Returns true when a bulk copy is in flight.
+  auto stage = [&](int bq, int gq, float* dst, uint64_t* bar) -> bool {
+    const int s0 = 4 * gq * A.P - A.left;  // first sample of the span (may be negative)
+    const float* xb = A.x + static_cast<int64_t>(bq) * A.T;
+    const int lo = s0 < 0 ? 0 : s0;
+    const int hi = (s0 + A.span) > A.T ? A.T : (s0 + A.span);
+    const bool interior = (lo == s0) && (hi == s0 + A.span);
+    if (A.bulk_in && (interior || A.pad_mode == DSB200_PAD_CONSTANT) && hi > lo) {
+      // zero the out-of-utterance head/tail (constant padding), bulk-copy the rest
+      for (int i = lane; i < lo - s0; i += 32) dst[i] = 0.0f;
+      for (int i = hi - s0 + lane; i < A.span; i += 32) dst[i] = 0.0f;
+      if (lane == 0) {
+        fence_async_smem();
+        const uint32_t bytes = static_cast<uint32_t>(hi - lo) * 4u;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(dst + (lo - s0), xb + lo, bytes, bar);
       }
-    } else {
-      for (int i = tid; i < A.tile_floats; i += kThreads) {
-        const int64_t q = pad_index(s0 + i, A.T, A.pad_mode);
-        dst[i] = q < 0 ? 0.0f : xb[q];
-      }
+      return true;
     }
-    return bulk;
+    for (int i = lane; i < A.span; i += 32) {
+      const int64_t p = pad_index(static_cast<int64_t>(s0) + i, A.T, A.pad_mode);
+      dst[i] = p < 0 ? 0.0f : xb[p];
+    }
+    return false;
   };
 
-  uint32_t phase[2] = {0u, 0u};
-  int64_t t = blockIdx.x;
+  uint32_t phase0 = 0u, phase1 = 0u;
   bool cur_bulk = false;
-  if (t < A.n_tiles) cur_bulk = stage(t, 0);
-  __syncthreads();
+  if (q < A.n_quads) cur_bulk = stage(b, g, in0, &mbar[0]);
+  bool store_pending = false;
 
-  for (int it = 0; t < A.n_tiles; ++it, t += gridDim.x) {
+  for (int it = 0; q < A.n_quads; ++it) {
     const int buf = it & 1;
-    const int64_t tn = t + gridDim.x;
+    // next quad of this warp
+    const int qn = q + n_warps;
+    int bn = b + db, gn = g + dg;
+    if (gn >= A.quads_per_utt) { gn -= A.quads_per_utt; ++bn; }
     bool next_bulk = false;
-    if (tn < A.n_tiles) next_bulk = stage(tn, buf ^ 1);
+    if (qn < A.n_quads) next_bulk = stage(bn, gn, in0 + (buf ^ 1) * A.in_floats, &mbar[buf ^ 1]);
     if (cur_bulk) {
-      mbar_wait(&mbar[buf], phase[buf]);
-      phase[buf] ^= 1u;
+      if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1u; }
+      else          { mbar_wait(&mbar[1], phase1); phase1 ^= 1u; }
     }
-    int64_t b, s0;
-    int n0;
-    bool dummy;
-    tile_geom(t, b, n0, s0, dummy);
-    const float* tile = tile0 + buf * A.tile_floats;
+    __syncwarp();  // zero-fill / guarded stores of the other lanes
+    const float* span = in0 + buf * A.in_floats;
 
-    const int fA = n0 + 2 * hw;
-    if (fA < A.n_frames) {  // half-warp uniform
-      const bool vA = true, vB = (fA + 1) < A.n_frames;
-      const float* pa = tile + (2 * hw) * A.P + 2 * l;
-      const float* pb = pa + A.P;
+    const int fA = 4 * g + 2 * h;
+    const int rows = (A.n_frames - 4 * g) < 4 ? (A.n_frames - 4 * g) : 4;   // valid frames in the quad
+    const bool vA = fA < A.n_frames, vB = (fA + 1) < A.n_frames;
+    const float* pa = span + (2 * h) * A.P + 2 * l;
+    const float* pb = pa + A.P;
 
-      C2 a[16];
+    C2 a[16];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        if (j < NJ) {
-          float2 xa = *reinterpret_cast<const float2*>(pa + 32 * j);
-          float2 xb2 = *reinterpret_cast<const float2*>(pb + 32 * j);
-          const float2 wv = *reinterpret_cast<const float2*>(win + 2 * l + 32 * j);
-          if (MASK_ALL || j == NJ - 1) {  // never let samples past the frame end in (0 * inf = nan)
-            const int p0 = 2 * l + 32 * j;
-            if (p0 >= A.L) { xa.x = 0.0f; xb2.x = 0.0f; }
-            if (p0 + 1 >= A.L) { xa.y = 0.0f; xb2.y = 0.0f; }
-          }
-          a[j].re = make_float2(xa.x * wv.x, xb2.x * wv.x);
-          a[j].im = make_float2(xa.y * wv.y, xb2.y * wv.y);
-        } else {
-          a[j].re = make_float2(0.0f, 0.0f);
-          a[j].im = make_float2(0.0f, 0.0f);
+    for (int j = 0; j < 16; ++j) {
+      if (j < NJ) {
+        float2 xa = *reinterpret_cast<const float2*>(pa + 32 * j);
+        float2 xb2 = *reinterpret_cast<const float2*>(pb + 32 * j);
+        const float2 wv = *reinterpret_cast<const float2*>(win + 2 * l + 32 * j);
+        if (MASK_ALL || j == NJ - 1) {  // never let samples past the frame end in (0 * inf = nan)
+          const int p0 = 2 * l + 32 * j;
+          if (p0 >= A.L) { xa.x = 0.0f; xb2.x = 0.0f; }
+          if (p0 + 1 >= A.L) { xa.y = 0.0f; xb2.y = 0.0f; }
         }
+        a[j].re = make_float2(xa.x * wv.x, xb2.x * wv.x);
+        a[j].im = make_float2(xa.y * wv.y, xb2.y * wv.y);
+      } else {
+        a[j].re = make_float2(0.0f, 0.0f);
+        a[j].im = make_float2(0.0f, 0.0f);
       }
+    }
 
-      fft16<NJ>(a);  // over j -> k2
+    fft16<NJ>(a);  // over j -> k2, result in digit-swapped order
 #pragma unroll
-      for (int k2 = 1; k2 < 16; ++k2) a[k2] = cmul_s(a[k2], twr[k2], twi[k2]);
+    for (int k2 = 1; k2 < 16; ++k2) a[dig(k2)] = cmul_s(a[dig(k2)], twr[k2], twi[k2]);
 
-      // transpose through shared memory: lane m1 writes column m1, lane k2 reads row k2
+    // the previous quad's bulk store reads the staging rows that alias the exchange planes
+    if (store_pending) {
+      if (lane == 0) bulk_wait_read();
+      store_pending = false;
+    }
+    __syncwarp();
+    // transpose through shared memory: lane m1 writes column m1, lane k2 reads row k2
 #pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2)
-        xch[k2 * kXchStride + l] = make_float4(a[k2].re.x, a[k2].re.y, a[k2].im.x, a[k2].im.y);
-      __syncwarp(hmask);
+    for (int k2 = 0; k2 < 16; ++k2) {
+      xr[k2 * kXRow + l] = a[dig(k2)].re;
+      xi[k2 * kXRow + l] = a[dig(k2)].im;
+    }
+    __syncwarp();
 #pragma unroll
-      for (int m1 = 0; m1 < 16; ++m1) {
-        const float4 v = xch[l * kXchStride + m1];
-        a[m1].re = make_float2(v.x, v.y);
-        a[m1].im = make_float2(v.z, v.w);
-      }
-      __syncwarp(hmask);
+    for (int m1 = 0; m1 < 16; ++m1) {
+      a[m1].re = xr[l * kXRow + m1];
+      a[m1].im = xi[l * kXRow + m1];
+    }
+    __syncwarp();
 
-      fft16<16>(a);  // over m1 -> k1 : a[k1] = Z[16 k1 + l]
+    fft16<16>(a);  // over m1 -> k1 : a[dig(k1)] = Z[16 k1 + l]
 
-      // swap the upper registers with the lane that holds the mirrored bins
-      C2 r[8];
+    // swap the upper registers with the lane that holds the mirrored bins
+    C2 r[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        C2 s = a[8 + j];
-        if (l == 0) s = (j < 7) ? a[9 + j] : a[0];  // lane 0 pairs k1 with 16 - k1 (and bin 0 with itself)
-        r[j].re.x = __shfl_sync(hmask, s.re.x, partner);
-        r[j].re.y = __shfl_sync(hmask, s.re.y, partner);
-        r[j].im.x = __shfl_sync(hmask, s.im.x, partner);
-        r[j].im.y = __shfl_sync(hmask, s.im.y, partner);
-      }
+    for (int j = 0; j < 8; ++j) {
+      C2 s = a[dig(8 + j)];
+      if (l == 0) s = (j < 7) ? a[dig(9 + j)] : a[dig(0)];  // lane 0 pairs k1 with 16 - k1 (and bin 0 with itself)
+      r[j].re.x = __shfl_sync(0xffffffffu, s.re.x, partner);
+      r[j].re.y = __shfl_sync(0xffffffffu, s.re.y, partner);
+      r[j].im.x = __shfl_sync(0xffffffffu, s.im.x, partner);
+      r[j].im.y = __shfl_sync(0xffffffffu, s.im.y, partner);
+    }
 
-      const int64_t rowA = b * A.n_frames + fA;
-      const int64_t stride = (FMT == DSB200_SPEC_COMPLEX) ? 514 : 257;
-      float* yA = A.y + rowA * stride;
-      float* yB = yA + stride;
+    const bool staged = (FMT != DSB200_SPEC_COMPLEX) && A.bulk_out && rows == 4 &&
+                        (((static_cast<int64_t>(b) * A.n_frames + 4 * g) & 3) == 0);
+    const int64_t row0 = static_cast<int64_t>(b) * A.n_frames + 4 * g;
+    constexpr int kStride = (FMT == DSB200_SPEC_COMPLEX) ? 514 : 257;
+    float* rowA;
+    float* rowB;
+    if (staged) {
+      rowA = ostage + (2 * h) * 257;
+      rowB = rowA + 257;
+    } else {
+      rowA = A.y + (row0 + 2 * h) * kStride;
+      rowB = rowA + kStride;
+    }
+
+    auto split = [&](auto staged_tag) {
+      constexpr bool ST = decltype(staged_tag)::value;
 #pragma unroll
       for (int k1 = 0; k1 < 8; ++k1) {
-        // a = Z[k], m = Z[256 - k], k = 16 k1 + l
-        const C2 z = a[k1], m = r[7 - k1];
+        // z = Z[k], m = Z[256 - k], k = 16 k1 + l
+        const C2 z = a[dig(k1)], m = r[7 - k1];
         const float2 sr = add2(z.re, m.re), dr = sub2(z.re, m.re);
         const float2 si = add2(z.im, m.im), di = sub2(z.im, m.im);
-        // T = (W/2) * (si, -dr)
-        const float2 tr = fma2s(dr, hwi[k1], mul2s(si, hwr[k1]));
-        const float2 ti = fma2s(dr, -hwr[k1], mul2s(si, hwi[k1]));
-        const float2 xr = fma2s(sr, 0.5f, tr), xi = fma2s(di, 0.5f, ti);  // X[k]      = E + T
-        const float2 mr = fma2s(sr, 0.5f, make_float2(-tr.x, -tr.y));      // X[256-k]  = conj(E - T)
+        const float2 hw = htw[16 * k1 + l];                          // W512^k / 2
+        const float2 tr = fma2s(dr, hw.y, mul2s(si, hw.x));          // T = (W/2) (si, -dr)
+        const float2 ti = fma2s(dr, -hw.x, mul2s(si, hw.y));
+        const float2 xr_ = fma2s(sr, 0.5f, tr), xi_ = fma2s(di, 0.5f, ti);   // X[k]     = E + T
+        const float2 mr = fma2s(sr, 0.5f, make_float2(-tr.x, -tr.y));         // X[256-k] = conj(E - T)
         const float2 mi = fma2s(di, -0.5f, ti);
         const int k = 16 * k1 + l;
-        store_bin<FMT>(yA, yB, vA, vB, k, xr, xi, A.eps);
-        store_bin<FMT>(yA, yB, vA, vB, 256 - k, mr, mi, A.eps);
+        put_bin<FMT, ST>(rowA, rowB, vB, k, xr_, xi_, A.eps);
+        put_bin<FMT, ST>(rowA, rowB, vB, 256 - k, mr, mi, A.eps);
       }
-      if (l == 0) {  // bin 128 pairs with itself: X[128] = conj(Z[128])
-        store_bin<FMT>(yA, yB, vA, vB, 128, a[8].re, make_float2(-a[8].im.x, -a[8].im.y), A.eps);
-      }
+      if (l == 0)  // bin 128 pairs with itself: X[128] = conj(Z[128])
+        put_bin<FMT, ST>(rowA, rowB, vB, 128, a[dig(8)].re, make_float2(-a[dig(8)].im.x, -a[dig(8)].im.y), A.eps);
+    };
+
+    if (staged) {
+      split(std::true_type{});
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_s2g(A.y + row0 * 257, ostage, kOutFloats * 4u);
+      store_pending = true;
+    } else if (vA) {
+      split(std::false_type{});
     }
-    __syncthreads();  // tile buffer `buf` may be overwritten by the staging of iteration it + 1
+
+    q = qn; b = bn; g = gn;
     cur_bulk = next_bulk;
   }
+  if (store_pending && lane == 0) bulk_wait_read();
 }
 
 template <int NJ, bool MASK_ALL>
@@ -392,17 +437,19 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
                 const dsb200_stft_params* p, int device, cudaStream_t stream) {
   const dsb200_frame_params& f = p->frame;
   const dsb200_spec_params& s = p->spec;
-  if (s.fft_length != 512 || f.frame_length > 512 || (f.frame_period & 1) || f.zmean || s.has_relative_floor)
+  const int left = f.center ? f.frame_length / 2 : 0;
+  if (s.fft_length != 512 || f.frame_length > 512 || (f.frame_period & 1) || f.zmean || s.has_relative_floor ||
+      T_len > (1 << 30))
     return DSB200_E_UNSUPPORTED;
   const int64_t N = dsb200_num_frames(T_len, f.frame_period);
-  const int nj_exact = (f.frame_length + 31) / 32;
-  const bool fast13 = nj_exact == 13;
+  const int64_t Q = (N + 3) / 4;
+  if (batch * Q > (1LL << 30) || batch * N * 257 > (1LL << 40)) return DSB200_E_UNSUPPORTED;
+  const bool fast13 = (f.frame_length + 31) / 32 == 13;
   const int NJ = fast13 ? 13 : 16;
-  // floats staged per tile: last frame starts at (F-1) P and the loader touches 32 NJ samples of it
-  int64_t tile_floats = static_cast<int64_t>(kTileFrames - 1) * f.frame_period + 32 * NJ;
-  tile_floats = (tile_floats + 3) & ~static_cast<int64_t>(3);
-  const size_t smem = 16 + 512 * sizeof(float) + 2 * static_cast<size_t>(tile_floats) * sizeof(float) +
-                      static_cast<size_t>(kHalfWarps) * 16 * kXchStride * sizeof(float4);
+  const int span = (3 * f.frame_period + 32 * NJ + 3) & ~3;
+  const int in_floats = span;
+  const size_t smem = 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) +
+                      static_cast<size_t>(kWarps) * (2 * static_cast<size_t>(in_floats) * 4 + kXchBytesPerWarp);
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
   const void* tw = twiddle_table(device, 512, false, stream);
   if (tw == nullptr) return fail(DSB200_E_CUDA, "could not build the twiddle table for fft_length=512");
@@ -412,17 +459,23 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
   A.window = window;
   A.tw512 = static_cast<const float*>(tw);
   A.y = y;
-  A.T = T_len;
-  A.n_frames = N;
-  A.tiles_per_utt = static_cast<int>((N + kTileFrames - 1) / kTileFrames);
-  A.n_tiles = batch * A.tiles_per_utt;
+  A.T = static_cast<int>(T_len);
+  A.n_frames = static_cast<int>(N);
+  A.quads_per_utt = static_cast<int>(Q);
+  A.n_quads = static_cast<int>(batch * Q);
   A.L = f.frame_length;
   A.P = f.frame_period;
-  A.left = f.center ? f.frame_length / 2 : 0;
+  A.left = left;
   A.pad_mode = f.pad_mode;
-  A.tile_floats = static_cast<int>(tile_floats);
+  A.span = span;
+  A.in_floats = in_floats;
+  // bulk copies need 16-byte aligned global addresses and sizes: every span start (4 g P - left) and
+  // every utterance start (b T) must be a multiple of 4 floats.
+  A.bulk_in = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (T_len % 4 == 0) && (left % 4 == 0) &&
+              (f.frame_period % 4 == 0);
+  A.bulk_out = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   A.eps = static_cast<float>(s.eps);
-  const int blocks = static_cast<int>(std::min<int64_t>(A.n_tiles, sm_count(device)));
+  const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));
   if (fast13) return launch_fmt<13, false>(A, s.out_format, blocks, smem, stream);
   return launch_fmt<16, true>(A, s.out_format, blocks, smem, stream);
 }
