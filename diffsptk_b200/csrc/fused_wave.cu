@@ -1,10 +1,248 @@
-// Fused waveform -> {LPC, MFCC} fast paths.  Placeholder: defers to the generic kernels.
-#include "common.cuh"
+// Fused waveform -> LPC kernel (fp32, sm_100a): Frame -> Window -> autocorrelation -> Levinson-Durbin
+// in one pass over HBM (BASELINE.json config 3: fl=400, fp=80, M=24; 320 B read + 100 B written per frame).
+//
+// Reference cascade being replaced: diffsptk/modules/frame.py:120-141, window.py:185-193 (out_length
+// None), acorr.py:110-120, levdur.py:113-127 (README.md:198-201 pipeline).
+//
+// Mapping: persistent CTAs; every warp runs its own pipeline over "units" of 32 consecutive frames of
+// one utterance (no CTA barrier in the loop):
+//   * the unit's contiguous sample span is staged in shared memory by one bulk async copy (UBLKCP) on a
+//     warp-private mbarrier; the next unit's copy is issued before the Levinson phase, which no longer
+//     reads the span, so the copy overlaps it;
+//   * 8 sub-steps of 4 frames: each half-warp takes a PAIR of frames (float2 = (frame A, frame B),
+//     packed FFMA2); lane l owns samples [25 l, 25 l + 25) plus a 24-sample halo in registers and
+//     accumulates all 25 lags (625 FFMA2, no memory traffic); the 16 partial sums per lag are reduced
+//     through shared memory; the autocorrelations of the 32 frames collect in a 32 x 25 tile;
+//   * Levinson-Durbin for the 32 frames runs with one frame per lane, float64 state in registers
+//     (reciprocals by MUFU.RCP + two Newton steps), and the 32 x (M+1) result tile leaves with one bulk
+//     async store.
+// The FP32 pipe bounds this kernel (9.7 k multiply-adds per frame = 76 clk/frame/SM), not HBM.
+//
+// Envelope: float32, frame_length <= 400, lpc_order <= 24, even frame_period, no zmean.
+#include <algorithm>
+
+#include "bulk.cuh"
+
 namespace dsb200 {
-int lpc_wave_fast_try(const float*, const float*, float*, int64_t, int64_t, const dsb200_frame_params*, int32_t, double,
-                      int, cudaStream_t) {
-  return DSB200_E_UNSUPPORTED;
+namespace {
+
+constexpr int kLWarps = 12;
+constexpr int kLThreads = kLWarps * 32;
+constexpr int kUnit = 32;     // frames per warp unit (one Levinson frame per lane)
+constexpr int kHalfUnit = 16; // frames staged at a time
+constexpr int kCh = 25;       // samples per lane (16 lanes x 25 = 400 >= frame_length)
+constexpr int kLag = 25;      // lags 0..24
+constexpr int kHalo = kLag - 1;
+
+struct LArgs {
+  const float* x;
+  const float* window;  // [L]
+  float* y;             // [batch, n_frames, M + 1]
+  int T, n_frames, units_per_utt, n_units;
+  int L, P, left, pad_mode, M;
+  int span;             // floats staged per half unit: 15 P + 400 + 24, rounded up to 4
+  int bulk_in, bulk_out;
+  double eps;
+};
+
+__global__ void __launch_bounds__(kLThreads, 1) lpc_wave_kernel(const LArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int l = lane & 15, h = lane >> 4;
+  const int D = A.M + 1;
+
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
+  float* win = reinterpret_cast<float*>(smem_raw + 8 * kLWarps);  // [448], zero padded
+  const size_t per_warp = static_cast<size_t>(A.span) * 4 + 2 * 16 * kLag * 8 + kUnit * kLag * 4;
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(win + 448) + warp * per_warp;
+  float* span = reinterpret_cast<float*>(wbase);
+  float2* part = reinterpret_cast<float2*>(wbase + static_cast<size_t>(A.span) * 4) + h * (16 * kLag);  // [16][25]
+  float* rbuf = reinterpret_cast<float*>(wbase + static_cast<size_t>(A.span) * 4 + 2 * 16 * kLag * 8);  // [32][25]
+
+  for (int i = tid; i < 448; i += kLThreads) win[i] = i < A.L ? A.window[i] : 0.0f;
+  if (lane == 0) {
+    mbar_init(mbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();  // the only CTA-wide barrier
+
+  const int n_warps = gridDim.x * kLWarps;
+  int u = blockIdx.x * kLWarps + warp;
+  int b = u / A.units_per_utt, g = u - b * A.units_per_utt;
+  const int db = n_warps / A.units_per_utt, dg = n_warps - db * A.units_per_utt;
+  uint32_t phase = 0u;
+  auto stage_half = [&](int bq, int gq, int half) {
+    return stage_span(A.x + static_cast<int64_t>(bq) * A.T, A.T, (kUnit * gq + kHalfUnit * half) * A.P - A.left,
+                      A.span, A.pad_mode, A.bulk_in != 0, span, mbar, lane);
+  };
+  bool cur_bulk = false;
+  if (u < A.n_units) cur_bulk = stage_half(b, g, 0);
+  bool store_pending = false;
+
+  while (u < A.n_units) {
+    const int f0 = kUnit * g;                       // first frame of the unit
+    const int nvalid = (A.n_frames - f0) < kUnit ? (A.n_frames - f0) : kUnit;
+    const int un = u + n_warps;
+    int bn = b + db, gn = g + dg;
+    if (gn >= A.units_per_utt) { gn -= A.units_per_utt; ++bn; }
+
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      if (cur_bulk) {
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+      }
+      __syncwarp();
+      if (half == 0 && store_pending) {             // rbuf doubles as the output staging tile
+        if (lane == 0) bulk_wait_read();
+        store_pending = false;
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int sub = 0; sub < kHalfUnit / 4; ++sub) {
+        // frame pair of this half-warp: (fa, fa + 2).  The two half-warps start one frame apart, which
+        // shifts their shared-memory banks by P mod 32 (= 16 at P = 80): 32-lane loads are conflict-free.
+        const int fa = 4 * sub + h;                 // relative to the staged half unit
+        const float* pa = span + fa * A.P + kCh * l;
+        const float* pb = pa + 2 * A.P;
+        const float* pw = win + kCh * l;
+        auto ld = [&](int i) {                      // windowed sample pair i of this lane's chunk (+ halo)
+          const bool in = (kCh * l + i) < A.L;      // samples past the frame end are structural zeros
+          const float xa = in ? pa[i] : 0.0f, xb = in ? pb[i] : 0.0f, w = pw[i];
+          return make_float2(xa * w, xb * w);
+        };
+        float2 x2[kCh + kHalo];
+        float2 acc[kLag];
+#pragma unroll
+        for (int k = 0; k < kLag; ++k) acc[k] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int i = 0; i < kLag; ++i) x2[i] = ld(i);
+#pragma unroll
+        for (int i = 0; i < kCh; ++i) {             // x2[i .. i+24] live: a 25-deep sliding register window
+          if (i + kLag < kCh + kHalo) x2[i + kLag] = ld(i + kLag);
+#pragma unroll
+          for (int k = 0; k < kLag; ++k) acc[k] = __ffma2_rn(x2[i], x2[i + k], acc[k]);
+        }
+        // reduce the 16 per-lane partial sums of every lag through shared memory
+#pragma unroll
+        for (int k = 0; k < kLag; ++k) part[l * kLag + k] = acc[k];
+        __syncwarp();
+        float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          s0 = __fadd2_rn(s0, part[j * kLag + l]);
+          if (l < kLag - 16) s1 = __fadd2_rn(s1, part[j * kLag + 16 + l]);
+        }
+        const int fu = kHalfUnit * half + fa;       // frame within the unit
+        rbuf[fu * kLag + l] = s0.x;
+        rbuf[(fu + 2) * kLag + l] = s0.y;
+        if (l < kLag - 16) {
+          rbuf[fu * kLag + 16 + l] = s1.x;
+          rbuf[(fu + 2) * kLag + 16 + l] = s1.y;
+        }
+        __syncwarp();
+      }
+      // the staged samples are dead: fetch the second half, or the next unit's first half (that copy
+      // overlaps the Levinson phase below)
+      if (half == 0) cur_bulk = stage_half(b, g, 1);
+      else cur_bulk = (un < A.n_units) ? stage_half(bn, gn, 0) : false;
+    }
+
+    // Levinson-Durbin, one frame per lane, float64 state (see lpc.cu for the recursion)
+    double r[kLag], a[kLag];
+#pragma unroll
+    for (int k = 0; k < kLag; ++k) r[k] = static_cast<double>(rbuf[lane * kLag + k]);
+    double E = r[0] + A.eps;
+#pragma unroll
+    for (int i = 1; i < kLag; ++i) {
+      if (i <= A.M) {
+        double acc = r[i];
+#pragma unroll
+        for (int j = 1; j < i; ++j) acc = fma(a[j], r[i - j], acc);
+        // k = -acc / E with a Newton-refined reciprocal (exact division outside the float range)
+        double inv = static_cast<double>(__frcp_rn(static_cast<float>(E)));
+        inv = fma(inv, fma(-E, inv, 1.0), inv);
+        inv = fma(inv, fma(-E, inv, 1.0), inv);
+        const bool tame = fabs(E) > 1e-30 && fabs(E) < 1e30;
+        const double kk = tame ? (-acc * inv) : (-acc / E);
+#pragma unroll
+        for (int j = 1; 2 * j <= i; ++j) {  // a_j <- a_j + k a_{i-j}, updated in symmetric pairs
+          const double lo = a[j], hi = a[i - j];
+          a[j] = fma(kk, hi, lo);
+          if (2 * j != i) a[i - j] = fma(kk, lo, hi);
+        }
+        a[i] = kk;
+        E *= fma(-kk, kk, 1.0);
+      }
+    }
+    double gain = r[0];
+#pragma unroll
+    for (int j = 1; j < kLag; ++j)
+      if (j <= A.M) gain = fma(r[j], a[j], gain);
+    a[0] = sqrt(gain);
+
+    const int64_t row0 = static_cast<int64_t>(b) * A.n_frames + f0;
+    const bool staged = A.bulk_out && nvalid == kUnit && (((row0 * D) & 3) == 0);
+    __syncwarp();  // every lane has read its rbuf row
+    if (staged) {
+      float* o = rbuf + lane * D;                   // dense [32][D] tile (D <= 25 fits in the row storage)
+#pragma unroll
+      for (int k = 0; k < kLag; ++k)
+        if (k < D) o[k] = static_cast<float>(a[k]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_s2g(A.y + row0 * D, rbuf, static_cast<uint32_t>(kUnit * D) * 4u);
+      store_pending = true;
+    } else if (lane < nvalid) {
+      float* o = A.y + (row0 + lane) * D;
+#pragma unroll
+      for (int k = 0; k < kLag; ++k)
+        if (k < D) o[k] = static_cast<float>(a[k]);
+    }
+    u = un; b = bn; g = gn;
+  }
+  if (store_pending && lane == 0) bulk_wait_read();
 }
+
+}  // namespace
+
+int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
+                      const dsb200_frame_params* fp, int32_t M, double eps, int device, cudaStream_t stream) {
+  if (fp->frame_length > 16 * kCh || M >= kLag || (fp->frame_period & 1) || fp->zmean || T_len > (1 << 30))
+    return DSB200_E_UNSUPPORTED;
+  const int64_t N = dsb200_num_frames(T_len, fp->frame_period);
+  const int64_t U = (N + kUnit - 1) / kUnit;
+  if (batch * U > (1LL << 30)) return DSB200_E_UNSUPPORTED;
+  const int left = fp->center ? fp->frame_length / 2 : 0;
+  const int span = ((kHalfUnit - 1) * fp->frame_period + 16 * kCh + kHalo + 3) & ~3;
+  const size_t per_warp = static_cast<size_t>(span) * 4 + 2 * 16 * kLag * 8 + kUnit * kLag * 4;
+  const size_t smem = 8 * kLWarps + 448 * sizeof(float) + kLWarps * per_warp;
+  if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
+
+  LArgs A{};
+  A.x = x;
+  A.window = window;
+  A.y = y;
+  A.T = static_cast<int>(T_len);
+  A.n_frames = static_cast<int>(N);
+  A.units_per_utt = static_cast<int>(U);
+  A.n_units = static_cast<int>(batch * U);
+  A.L = fp->frame_length;
+  A.P = fp->frame_period;
+  A.left = left;
+  A.pad_mode = fp->pad_mode;
+  A.M = M;
+  A.span = span;
+  A.bulk_in = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (T_len % 4 == 0) && (left % 4 == 0) &&
+              ((kHalfUnit * fp->frame_period) % 4 == 0);
+  A.bulk_out = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  A.eps = eps;
+  DSB_CUDA(cudaFuncSetAttribute(lpc_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int blocks = static_cast<int>(std::min<int64_t>((A.n_units + kLWarps - 1) / kLWarps, sm_count(device)));
+  lpc_wave_kernel<<<blocks, kLThreads, smem, stream>>>(A);
+  return after_launch("lpc_wave_kernel");
+}
+
 }  // namespace dsb200
 
 extern "C" {

@@ -60,16 +60,19 @@ __global__ void __launch_bounds__(256) acorr_kernel(AcorrArgs<T> A) {
     T r0 = 0;
     for (int k0 = 0; k0 <= A.M; k0 += 32) {
       const int k = k0 + lane;
-      T acc0 = 0, acc1 = 0;
+      // float64 accumulators for both element types: the LPC systems built from these sums are
+      // ill-conditioned on speech, and a 400-term float32 chain costs ~10x the reference's FFT route
+      // in accuracy; this generic kernel is not the throughput path (see fused_wave.cu).
+      double acc0 = 0, acc1 = 0;
       if (k <= A.M) {
         int n = 0;
         for (; n + 1 < A.L; n += 2) {
-          acc0 = dfma(xs[n], xs[n + k], acc0);
-          acc1 = dfma(xs[n + 1], xs[n + 1 + k], acc1);
+          acc0 = fma(static_cast<double>(xs[n]), static_cast<double>(xs[n + k]), acc0);
+          acc1 = fma(static_cast<double>(xs[n + 1]), static_cast<double>(xs[n + 1 + k]), acc1);
         }
-        if (n < A.L) acc0 = dfma(xs[n], xs[n + k], acc0);
+        if (n < A.L) acc0 = fma(static_cast<double>(xs[n]), static_cast<double>(xs[n + k]), acc0);
       }
-      T v = acc0 + acc1;
+      T v = static_cast<T>(acc0 + acc1);
       if (k0 == 0) r0 = __shfl_sync(0xffffffffu, v, 0);
       if (k <= A.M) {
         switch (A.out_format) {

@@ -26,9 +26,10 @@
 // floor (bulk copies additionally need 16-byte aligned spans, else guarded loads are used).  Anything else returns DSB200_E_UNSUPPORTED and the
 // generic kernel (spectral.cu) runs.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
-#include "common.cuh"
+#include "bulk.cuh"
 
 namespace dsb200 {
 namespace {
@@ -39,6 +40,7 @@ constexpr int kXRow = 17;                              // float2 units per trans
 constexpr int kPlane = 16 * kXRow;                     // float2 units per plane
 constexpr int kXchBytesPerWarp = 2 * 2 * kPlane * 8;   // 2 half-warps x (re, im) planes = 8704 B
 constexpr int kOutFloats = 4 * 257;                    // one quad of real-valued output rows
+constexpr int kDefaultBulkStore = 1;                   // see stft512_try (DSB200_STFT_STORE)
 
 struct C2 {  // one complex value for each of the two frames of a pair
   float2 re, im;
@@ -148,35 +150,6 @@ struct Args {
   float eps;
 };
 
-// ---- mbarrier / bulk-copy helpers (PTX) -----------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "WAIT_LOOP:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra DONE;\n\t"
-      "bra WAIT_LOOP;\n\t"
-      "DONE:\n\t}"
-      ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
 template <int FMT>
 __device__ __forceinline__ float fmt1(float s) {
   if (FMT == DSB200_SPEC_DB) return 10.0f * log10f(s);
@@ -224,7 +197,7 @@ __global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
   if (lane == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   // per-lane twiddles: W256^(l k2) for the inter-pass rotation, W512^(16 k1 + l) / 2 for the split
   const float2* tw = reinterpret_cast<const float2*>(A.tw512);
@@ -247,30 +220,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
   int g = q - b * A.quads_per_utt;
   const int db = n_warps / A.quads_per_utt, dg = n_warps - db * A.quads_per_utt;
 
-  // Stage the sample span of quad (bq, gq) into `dst`.  Returns true when a bulk copy is in flight.
   auto stage = [&](int bq, int gq, float* dst, uint64_t* bar) -> bool {
-    const int s0 = 4 * gq * A.P - A.left;  // first sample of the span (may be negative)
-    const float* xb = A.x + static_cast<int64_t>(bq) * A.T;
-    const int lo = s0 < 0 ? 0 : s0;
-    const int hi = (s0 + A.span) > A.T ? A.T : (s0 + A.span);
-    const bool interior = (lo == s0) && (hi == s0 + A.span);
-    if (A.bulk_in && (interior || A.pad_mode == DSB200_PAD_CONSTANT) && hi > lo) {
-      // zero the out-of-utterance head/tail (constant padding), bulk-copy the rest
-      for (int i = lane; i < lo - s0; i += 32) dst[i] = 0.0f;
-      for (int i = hi - s0 + lane; i < A.span; i += 32) dst[i] = 0.0f;
-      if (lane == 0) {
-        fence_async_smem();
-        const uint32_t bytes = static_cast<uint32_t>(hi - lo) * 4u;
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(dst + (lo - s0), xb + lo, bytes, bar);
-      }
-      return true;
-    }
-    for (int i = lane; i < A.span; i += 32) {
-      const int64_t p = pad_index(static_cast<int64_t>(s0) + i, A.T, A.pad_mode);
-      dst[i] = p < 0 ? 0.0f : xb[p];
-    }
-    return false;
+    return stage_span(A.x + static_cast<int64_t>(bq) * A.T, A.T, 4 * gq * A.P - A.left, A.span, A.pad_mode,
+                      A.bulk_in != 0, dst, bar, lane);
   };
 
   uint32_t phase0 = 0u, phase1 = 0u;
@@ -473,7 +425,15 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
   // every utterance start (b T) must be a multiple of 4 floats.
   A.bulk_in = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (T_len % 4 == 0) && (left % 4 == 0) &&
               (f.frame_period % 4 == 0);
-  A.bulk_out = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  // Output path: rows staged in shared memory + one bulk store per quad, or plain per-lane stores.
+  // DSB200_STFT_STORE=direct|bulk overrides the default (tuning knob, read once).
+  static const int store_mode = [] {
+    const char* e = getenv("DSB200_STFT_STORE");
+    if (e != nullptr && e[0] == 'd') return 0;
+    if (e != nullptr && e[0] == 'b') return 1;
+    return kDefaultBulkStore;
+  }();
+  A.bulk_out = store_mode && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   A.eps = static_cast<float>(s.eps);
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));
   if (fast13) return launch_fmt<13, false>(A, s.out_format, blocks, smem, stream);

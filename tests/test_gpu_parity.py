@@ -248,3 +248,42 @@ def test_host_pipeline_equals_device_path():
     want = F.stft(xh.to(d)).cpu()
     assert torch.equal(yh, want)
     pipe.close()
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((3, 8000), dict()),                                   # bulk staging, one partial unit
+    ((2, 8002), dict()),                                   # T % 4 != 0 -> guarded loads
+    ((2, 5000), dict(mode="reflect")),                     # non-constant padding on the edge units
+    ((2, 5000), dict(center=False, lpc_order=12)),         # M < 24
+    ((2, 4000), dict(frame_length=320, frame_period=160, lpc_order=16, window="hamming", norm="none")),
+    ((1, 700), dict(frame_length=400, frame_period=80)),   # shorter than one unit
+])
+def test_lpc_wave_fast_kernel_against_oracle(shape, kw):
+    """The fused waveform->LPC kernel (fl <= 400, M <= 24) against the oracle cascade."""
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(42)
+    x = rng.standard_normal(shape)
+    fl, fp = kw.get("frame_length", 400), kw.get("frame_period", 80)
+    M = kw.get("lpc_order", 24)
+    fr = O.frame(x, fl, fp, kw.get("center", True), False, kw.get("mode", "constant"))
+    fr = O.window(fr, None, window=kw.get("window", "blackman"), norm=kw.get("norm", "power"))
+    ref64 = O.lpc(fr, M, eps=1e-5)
+    ref32 = O.lpc(fr.astype(np.float32), M)
+    got = to_np(F.lpc_from_waveform(to_dev(x, "f32"), **{"lpc_order": M, **kw}))
+    H.assert_close_conditioned(got, ref32, ref64, what=f"lpc_wave {shape} {kw}")
+
+
+def test_lpc_wave_full_size_sampled():
+    """BASELINE.json config 3 at full size (1024 x 5 s, M=24), sampled utterances against the oracle."""
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    g = torch.Generator(device=dev()).manual_seed(7)
+    x = torch.randn(1024, 80000, generator=g, device=dev())
+    a = F.lpc_from_waveform(x, lpc_order=24)
+    assert a.shape == (1024, 1000, 25) and bool(torch.isfinite(a).all())
+    for b in (0, 513, 1023):
+        xb = x[b].cpu().numpy().astype(np.float64)
+        fr = O.window(O.frame(xb), None)
+        H.assert_close_conditioned(to_np(a[b]), O.lpc(fr.astype(np.float32), 24), O.lpc(fr, 24, eps=1e-5),
+                                   what=f"utterance {b}")
