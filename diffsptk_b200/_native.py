@@ -12,7 +12,7 @@ import os
 import threading
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "lib", "libdiffsptk_b200.so")
+LIB_PATH = os.path.join(_PKG, "lib", os.environ.get("DSB200_LIB_NAME", "libdiffsptk_b200.so"))
 
 OK, E_BAD_PARAM, E_UNSUPPORTED, E_ALIGN, E_CUDA = 0, -1, -2, -3, -4
 

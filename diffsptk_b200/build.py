@@ -17,8 +17,8 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 OUT_DIR = os.path.join(PKG, "lib")
-OBJ_DIR = os.path.join(ROOT, "build", "obj")
-LIB_PATH = os.path.join(OUT_DIR, "libdiffsptk_b200.so")
+OBJ_DIR = os.path.join(ROOT, "build", "obj_" + os.environ.get("DSB200_LIB_NAME", "default"))
+LIB_PATH = os.path.join(OUT_DIR, os.environ.get("DSB200_LIB_NAME", "libdiffsptk_b200.so"))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -27,6 +27,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "-I", os.path.join(ROOT, "include"),
     "-I", CSRC,
+    *os.environ.get("DSB200_EXTRA_NVCC_FLAGS", "").split(),
 ]
 
 
@@ -54,7 +55,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     srcs = sources()
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     deps.append(os.path.join(ROOT, "include", "diffsptk_b200.h"))
-    stamp = os.path.join(OUT_DIR, ".build_digest")
+    stamp = os.path.join(OUT_DIR, ".build_digest_" + os.path.basename(LIB_PATH))
     digest = _digest(deps)
     if not force and os.path.exists(LIB_PATH) and os.path.exists(stamp) and open(stamp).read() == digest:
         return LIB_PATH

@@ -245,13 +245,41 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
 
 }  // namespace dsb200
 
+namespace dsb200 {
+int mfcc_wave_try(const float* x, const float* window, const float* H, const int32_t* cb, const int32_t* ce,
+                  const float* W, const float* lifter, float* y, int64_t batch, int64_t T_len,
+                  const dsb200_stft_params* sp, const dsb200_mfcc_params* mp, int device, cudaStream_t stream);
+}
+
 extern "C" {
-int dsb200_mfcc_wave_f32(const void*, const void*, const void*, const int32_t*, const int32_t*, const void*, const void*,
-                         void*, int64_t, int64_t, const dsb200_stft_params*, const dsb200_mfcc_params*, int, void*) {
-  return dsb200::fail(DSB200_E_UNSUPPORTED, "fused waveform->MFCC kernel not available for this configuration");
+int dsb200_mfcc_wave_f32(const void* x, const void* window, const void* H, const int32_t* cb, const int32_t* ce,
+                         const void* W, const void* lifter, void* y, int64_t batch, int64_t T,
+                         const dsb200_stft_params* sp, const dsb200_mfcc_params* mp, int device, void* stream) {
+  using namespace dsb200;
+  DSB_REQUIRE(sp != nullptr && mp != nullptr, "params are NULL");
+  DSB_REQUIRE(sp->frame.frame_length > 0, "frame_length must be positive.");
+  DSB_REQUIRE(sp->frame.frame_period > 0, "frame_period must be positive.");
+  DSB_REQUIRE(sp->spec.fft_length > 1 && sp->spec.fft_length % 2 == 0, "fft_length must be positive even.");
+  DSB_REQUIRE(sp->spec.eps >= 0, "eps must be non-negative.");
+  DSB_REQUIRE(mp->fbank.n_channel > 0, "n_channel must be positive.");
+  DSB_REQUIRE(mp->fbank.floor > 0, "floor must be positive.");
+  DSB_REQUIRE(mp->mfcc_order >= 0 && mp->mfcc_order < mp->fbank.n_channel, "mfcc_order must be less than n_channel.");
+  DSB_REQUIRE(mp->out_format >= DSB200_MFCC_Y && mp->out_format <= DSB200_MFCC_YCE, "out_format %d is not supported.", mp->out_format);
+  DSB_REQUIRE(T >= 1 && batch >= 0, "bad batch / waveform length");
+  if (batch == 0) return DSB200_OK;
+  DSB_REQUIRE(x && window && H && W && lifter && y, "NULL data pointer");
+  DeviceScope ds(device);
+  DSB_CUDA(ds.err);
+  const int rc = mfcc_wave_try(static_cast<const float*>(x), static_cast<const float*>(window),
+                               static_cast<const float*>(H), cb, ce, static_cast<const float*>(W),
+                               static_cast<const float*>(lifter), static_cast<float*>(y), batch, T, sp, mp, device,
+                               static_cast<cudaStream_t>(stream));
+  if (rc == DSB200_E_UNSUPPORTED)
+    return fail(DSB200_E_UNSUPPORTED, "fused waveform->MFCC kernel not available for this configuration");
+  return rc;
 }
 int dsb200_mfcc_wave_f64(const void*, const void*, const void*, const int32_t*, const int32_t*, const void*, const void*,
                          void*, int64_t, int64_t, const dsb200_stft_params*, const dsb200_mfcc_params*, int, void*) {
-  return dsb200::fail(DSB200_E_UNSUPPORTED, "fused waveform->MFCC kernel not available for this configuration");
+  return dsb200::fail(DSB200_E_UNSUPPORTED, "fused waveform->MFCC kernel is float32 only");
 }
 }

@@ -34,7 +34,10 @@
 namespace dsb200 {
 namespace {
 
-constexpr int kWarps = 12;
+#ifndef DSB_STFT_WARPS
+#define DSB_STFT_WARPS 12
+#endif
+constexpr int kWarps = DSB_STFT_WARPS;  // 12 -> 168 registers/thread, 16 -> 128 (register file is split per scheduler)
 constexpr int kThreads = kWarps * 32;
 constexpr int kXRow = 17;                              // float2 units per transpose row (16 + 1 pad)
 constexpr int kPlane = 16 * kXRow;                     // float2 units per plane
@@ -148,13 +151,28 @@ struct Args {
   int bulk_in;          // waveform layout allows bulk copies (alignment)
   int bulk_out;         // output layout allows bulk stores
   float eps;
+  // MFCC epilogue (FMT == kFmtMfcc): fbank.py:315-320, dct.py:135-137, mfcc.py:252-256
+  const float* mf_H;       // [257, C] filter bank
+  const int32_t* mf_cb;    // [C] first non-zero row of each filter
+  const int32_t* mf_ce;    // [C] one past the last non-zero row
+  const float* mf_W;       // [C, C] DCT-II basis
+  const float* mf_lifter;  // [M + 1]
+  int mf_C, mf_M, mf_format, mf_D;
+  float mf_floor, mf_gamma;
 };
+
+constexpr int kFmtMfcc = 5;  // internal: stage amplitudes, then filter bank + DCT + lifter on chip
 
 template <int FMT>
 __device__ __forceinline__ float fmt1(float s) {
   if (FMT == DSB200_SPEC_DB) return 10.0f * log10f(s);
   if (FMT == DSB200_SPEC_LOGMAG) return 0.5f * logf(s);
   if (FMT == DSB200_SPEC_MAGNITUDE) return sqrtf(s);
+  if (FMT == kFmtMfcc) {  // amplitude fed to the filter bank: one MUFU op, 2^-23 relative error
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    return r;
+  }
   return s;
 }
 
@@ -185,7 +203,13 @@ __global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw) + 2 * warp;
   float* win = reinterpret_cast<float*>(smem_raw + 16 * kWarps);
   float2* htw = reinterpret_cast<float2*>(win + 512);  // [128]
+  // MFCC tables (FMT == kFmtMfcc only): H [257 C] | W [C (M+1)] | lifter [M+1] | cb [C] | ce [C], padded to 16 B
+  float* mfH = reinterpret_cast<float*>(htw + 128);
+  const int mf_floats = (FMT == kFmtMfcc)
+                            ? ((257 * A.mf_C + A.mf_C * (A.mf_M + 1) + (A.mf_M + 1) + 2 * A.mf_C + 3) & ~3)
+                            : 0;
   unsigned char* wbase = smem_raw + 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) +
+                         static_cast<size_t>(mf_floats) * 4 +
                          static_cast<size_t>(warp) * (2 * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
   float* in0 = reinterpret_cast<float*>(wbase);
   float2* xch = reinterpret_cast<float2*>(wbase + 2 * static_cast<size_t>(A.in_floats) * 4);
@@ -211,6 +235,17 @@ __global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
   for (int i = tid; i < 128; i += kThreads) {  // half split-twiddles W512^k / 2, k = 16 k1 + l < 128
     const float2 v = tw[i];
     htw[i] = make_float2(0.5f * v.x, 0.5f * v.y);
+  }
+  float* mfW = mfH + 257 * A.mf_C;
+  float* mfL = mfW + A.mf_C * (A.mf_M + 1);
+  int* mfcb = reinterpret_cast<int*>(mfL + (A.mf_M + 1));
+  int* mfce = mfcb + A.mf_C;
+  if (FMT == kFmtMfcc) {
+    const int C = A.mf_C, M1 = A.mf_M + 1;
+    for (int i = tid; i < 257 * C; i += kThreads) mfH[i] = A.mf_H[i];
+    for (int i = tid; i < C * M1; i += kThreads) mfW[i] = A.mf_W[(i / M1) * C + (i % M1)];
+    for (int i = tid; i < M1; i += kThreads) mfL[i] = A.mf_lifter[i];
+    for (int i = tid; i < C; i += kThreads) { mfcb[i] = A.mf_cb[i]; mfce[i] = A.mf_ce[i]; }
   }
   __syncthreads();  // the only CTA-wide barrier: window table + mbarrier init
 
@@ -309,8 +344,9 @@ __global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
       r[j].im.y = __shfl_sync(0xffffffffu, s.im.y, partner);
     }
 
-    const bool staged = (FMT != DSB200_SPEC_COMPLEX) && A.bulk_out && rows == 4 &&
-                        (((static_cast<int64_t>(b) * A.n_frames + 4 * g) & 3) == 0);
+    const bool staged = (FMT == kFmtMfcc) ||
+                        ((FMT != DSB200_SPEC_COMPLEX) && A.bulk_out && rows == 4 &&
+                         (((static_cast<int64_t>(b) * A.n_frames + 4 * g) & 3) == 0));
     const int64_t row0 = static_cast<int64_t>(b) * A.n_frames + 4 * g;
     constexpr int kStride = (FMT == DSB200_SPEC_COMPLEX) ? 514 : 257;
     float* rowA;
@@ -345,7 +381,48 @@ __global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
         put_bin<FMT, ST>(rowA, rowB, vB, 128, a[dig(8)].re, make_float2(-a[dig(8)].im.x, -a[dig(8)].im.y), A.eps);
     };
 
-    if (staged) {
+    if (FMT == kFmtMfcc) {
+      // ---- MFCC epilogue on the four staged amplitude rows: 8 lanes per frame -------------------
+      split(std::true_type{});
+      __syncwarp();
+      const int C = A.mf_C, M = A.mf_M, M1 = M + 1;
+      const int f = lane >> 3, slot = lane & 7;
+      const float* amp = ostage + f * 257;
+      float* mel = ostage + kOutFloats + 4 + f * C;  // [4][C], inside this warp's exchange region
+      for (int c = slot; c < C; c += 8) {            // triangular filters: only their non-zero rows
+        float acc = 0.0f;
+        for (int k = mfcb[c]; k < mfce[c]; ++k) acc = fmaf(amp[k], mfH[k * C + c], acc);
+        acc = fmaxf(acc, A.mf_floor);
+        mel[c] = (A.mf_gamma == 0.0f) ? logf(acc) : (powf(acc, A.mf_gamma) - 1.0f) / A.mf_gamma;
+      }
+      float En = 0.0f;
+      const bool want_e = (A.mf_format == DSB200_MFCC_YE) || (A.mf_format == DSB200_MFCC_YCE);
+      if (want_e) {                                  // E = log((2 sum_{0<k<256} x_k + x_0 + x_256) / 512)
+        float e = 0.0f;
+        for (int k = slot; k < 257; k += 8) {
+          const float v = amp[k];
+          e = fmaf((k == 0 || k == 256) ? 1.0f : 2.0f, v * v, e);
+        }
+        e += __shfl_xor_sync(0xffffffffu, e, 1);
+        e += __shfl_xor_sync(0xffffffffu, e, 2);
+        e += __shfl_xor_sync(0xffffffffu, e, 4);
+        En = logf(e * (1.0f / 512.0f));
+      }
+      __syncwarp();
+      if (4 * g + f < A.n_frames) {
+        float* out = A.y + (row0 + f) * A.mf_D;
+        for (int m = slot; m < M1; m += 8) {         // DCT-II columns 0..M, lifter, pack y | yE | yc | ycE
+          float acc = 0.0f;
+          for (int c = 0; c < C; ++c) acc = fmaf(mel[c], mfW[c * M1 + m], acc);
+          acc *= mfL[m];
+          if (m > 0) out[m - 1] = acc;
+          else if (A.mf_format == DSB200_MFCC_YC || A.mf_format == DSB200_MFCC_YCE) out[M] = acc;
+        }
+        if (slot == 0 && A.mf_format == DSB200_MFCC_YE) out[M] = En;
+        if (slot == 0 && A.mf_format == DSB200_MFCC_YCE) out[M + 1] = En;
+      }
+      __syncwarp();
+    } else if (staged) {
       split(std::true_type{});
       fence_async_smem();
       __syncwarp();
@@ -385,8 +462,10 @@ int launch_fmt(const Args& A, int fmt, int blocks, size_t smem, cudaStream_t str
 
 }  // namespace
 
-int stft512_try(const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
-                const dsb200_stft_params* p, int device, cudaStream_t stream) {
+// Shared argument set-up of the spectrum and MFCC entry points.  Returns DSB200_E_UNSUPPORTED outside
+// the kernel's envelope (the callers then fall back to the generic kernels).
+static int setup_args(Args& A, const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
+                      const dsb200_stft_params* p, int device, cudaStream_t stream, int* NJ_out) {
   const dsb200_frame_params& f = p->frame;
   const dsb200_spec_params& s = p->spec;
   const int left = f.center ? f.frame_length / 2 : 0;
@@ -396,17 +475,10 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
   const int64_t N = dsb200_num_frames(T_len, f.frame_period);
   const int64_t Q = (N + 3) / 4;
   if (batch * Q > (1LL << 30) || batch * N * 257 > (1LL << 40)) return DSB200_E_UNSUPPORTED;
-  const bool fast13 = (f.frame_length + 31) / 32 == 13;
-  const int NJ = fast13 ? 13 : 16;
-  const int span = (3 * f.frame_period + 32 * NJ + 3) & ~3;
-  const int in_floats = span;
-  const size_t smem = 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) +
-                      static_cast<size_t>(kWarps) * (2 * static_cast<size_t>(in_floats) * 4 + kXchBytesPerWarp);
-  if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
+  const int NJ = ((f.frame_length + 31) / 32 == 13) ? 13 : 16;
+  *NJ_out = NJ;
   const void* tw = twiddle_table(device, 512, false, stream);
   if (tw == nullptr) return fail(DSB200_E_CUDA, "could not build the twiddle table for fft_length=512");
-
-  Args A{};
   A.x = x;
   A.window = window;
   A.tw512 = static_cast<const float*>(tw);
@@ -419,12 +491,28 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
   A.P = f.frame_period;
   A.left = left;
   A.pad_mode = f.pad_mode;
-  A.span = span;
-  A.in_floats = in_floats;
+  A.span = (3 * f.frame_period + 32 * NJ + 3) & ~3;
+  A.in_floats = A.span;
   // bulk copies need 16-byte aligned global addresses and sizes: every span start (4 g P - left) and
   // every utterance start (b T) must be a multiple of 4 floats.
   A.bulk_in = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (T_len % 4 == 0) && (left % 4 == 0) &&
               (f.frame_period % 4 == 0);
+  A.eps = static_cast<float>(s.eps);
+  return DSB200_OK;
+}
+
+static size_t smem_bytes(const Args& A, int mf_floats) {
+  return 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) + static_cast<size_t>(mf_floats) * 4 +
+         static_cast<size_t>(kWarps) * (2 * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
+}
+
+int stft512_try(const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
+                const dsb200_stft_params* p, int device, cudaStream_t stream) {
+  Args A{};
+  int NJ = 16;
+  if (int rc = setup_args(A, x, window, y, batch, T_len, p, device, stream, &NJ)) return rc;
+  const size_t smem = smem_bytes(A, 0);
+  if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
   // Output path: rows staged in shared memory + one bulk store per quad, or plain per-lane stores.
   // DSB200_STFT_STORE=direct|bulk overrides the default (tuning knob, read once).
   static const int store_mode = [] {
@@ -434,10 +522,48 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
     return kDefaultBulkStore;
   }();
   A.bulk_out = store_mode && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-  A.eps = static_cast<float>(s.eps);
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));
-  if (fast13) return launch_fmt<13, false>(A, s.out_format, blocks, smem, stream);
-  return launch_fmt<16, true>(A, s.out_format, blocks, smem, stream);
+  if (NJ == 13) return launch_fmt<13, false>(A, p->spec.out_format, blocks, smem, stream);
+  return launch_fmt<16, true>(A, p->spec.out_format, blocks, smem, stream);
+}
+
+// Fused waveform -> STFT power -> MFCC (stft.py:237-241 + mfcc.py:243-256) in the same kernel.
+int mfcc_wave_try(const float* x, const float* window, const float* H, const int32_t* cb, const int32_t* ce,
+                  const float* W, const float* lifter, float* y, int64_t batch, int64_t T_len,
+                  const dsb200_stft_params* sp, const dsb200_mfcc_params* mp, int device, cudaStream_t stream) {
+  if (sp->spec.out_format != DSB200_SPEC_POWER || cb == nullptr || ce == nullptr) return DSB200_E_UNSUPPORTED;
+  const int C = mp->fbank.n_channel, M = mp->mfcc_order;
+  if (C > 128 || M >= C || mp->fbank.fft_length != 512) return DSB200_E_UNSUPPORTED;
+  Args A{};
+  int NJ = 16;
+  if (int rc = setup_args(A, x, window, y, batch, T_len, sp, device, stream, &NJ)) return rc;
+  const int mf_floats = (257 * C + C * (M + 1) + (M + 1) + 2 * C + 3) & ~3;
+  const size_t smem = smem_bytes(A, mf_floats);
+  // the mel rows [4][C] live behind the staged amplitude rows inside the exchange region
+  if (smem > static_cast<size_t>(max_dynamic_smem(device)) || (kOutFloats + 4 + 4 * C) * 4 > kXchBytesPerWarp)
+    return DSB200_E_UNSUPPORTED;
+  A.mf_H = H;
+  A.mf_cb = cb;
+  A.mf_ce = ce;
+  A.mf_W = W;
+  A.mf_lifter = lifter;
+  A.mf_C = C;
+  A.mf_M = M;
+  A.mf_format = mp->out_format;
+  A.mf_D = M + (mp->out_format == DSB200_MFCC_Y ? 0 : (mp->out_format == DSB200_MFCC_YCE ? 2 : 1));
+  A.mf_floor = static_cast<float>(mp->fbank.floor);
+  A.mf_gamma = static_cast<float>(mp->fbank.gamma);
+  const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));
+  if (NJ == 13) {
+    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<13, false, kFmtMfcc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    stft512_kernel<13, false, kFmtMfcc><<<blocks, kThreads, smem, stream>>>(A);
+  } else {
+    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<16, true, kFmtMfcc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    stft512_kernel<16, true, kFmtMfcc><<<blocks, kThreads, smem, stream>>>(A);
+  }
+  return after_launch("stft512_kernel<mfcc>");
 }
 
 }  // namespace dsb200

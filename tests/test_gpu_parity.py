@@ -287,3 +287,28 @@ def test_lpc_wave_full_size_sampled():
         fr = O.window(O.frame(xb), None)
         H.assert_close_conditioned(to_np(a[b]), O.lpc(fr.astype(np.float32), 24), O.lpc(fr, 24, eps=1e-5),
                                    what=f"utterance {b}")
+
+
+@pytest.mark.parametrize("shape,kw", [
+    ((3, 8000), dict(out_format="y")),
+    ((2, 8002), dict(out_format="ycE", lifter=22)),                  # unaligned waveform, partial quad
+    ((2, 5000), dict(out_format="yE", mode="reflect")),
+    ((2, 4000), dict(out_format="yc", n_channel=24, mfcc_order=12, gamma=-0.5, floor=1e-3)),
+    ((1, 333), dict(out_format="ycE", frame_length=320, frame_period=160, scale="mel")),
+])
+def test_mfcc_wave_fused_kernel_against_oracle(shape, kw):
+    """waveform -> STFT power -> fbank -> DCT -> lifter in ONE kernel, against the oracle cascade."""
+    import diffsptk_b200.functional as F
+    from diffsptk_b200 import _native
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(shape)
+    st = {k: kw[k] for k in ("frame_length", "frame_period", "mode") if k in kw}
+    mf = dict(mfcc_order=kw.get("mfcc_order", 13), n_channel=kw.get("n_channel", 40), sample_rate=16000,
+              lifter=kw.get("lifter", 1), floor=kw.get("floor", 1e-5), gamma=kw.get("gamma", 0.0),
+              scale=kw.get("scale", "htk"), out_format=kw["out_format"])
+    want = O.mfcc(O.stft(x, **st), **mf)
+    n0 = _native.launch_count()
+    got = to_np(F.mfcc_from_waveform(to_dev(x, "f32"), **st, **mf))
+    assert _native.launch_count() - n0 == 1, "expected the single fused kernel"
+    H.assert_close(got, want, "f32", what=f"mfcc_wave {shape} {kw}", scale_atol=True, rtol_mul=2.0)
