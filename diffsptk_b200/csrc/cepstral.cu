@@ -9,6 +9,11 @@
 #include "common.cuh"
 
 namespace dsb200 {
+
+// Fast fp32 path for fft_length = 512, cep_order <= 24 (mcep_fast.cu); DSB200_E_UNSUPPORTED outside it.
+int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_params* p, const float* P0,
+                  const float* G, const float* Hm, const float* av, int device, cudaStream_t stream);
+
 namespace {
 
 
@@ -400,6 +405,13 @@ int mcep_impl(const void* x, void* mc, int64_t rows, const dsb200_mcep_params* p
   if (p->cep_order > 63) return fail(DSB200_E_UNSUPPORTED, "cep_order > 63 is not implemented in the fused mcep kernel");
   DeviceScope ds(device);
   DSB_CUDA(ds.err);
+  if (sizeof(T) == 4 && getenv("DSB200_MCEP_GENERIC") == nullptr) {
+    const int rc = mcep_fast_try(static_cast<const float*>(x), static_cast<float*>(mc), rows, p,
+                                 static_cast<const float*>(P0), static_cast<const float*>(G),
+                                 static_cast<const float*>(Hm), static_cast<const float*>(av), device,
+                                 static_cast<cudaStream_t>(stream));
+    if (rc != DSB200_E_UNSUPPORTED) return rc;
+  }
   McepArgs<T> A{};
   A.x = static_cast<const T*>(x);
   A.mc = static_cast<T*>(mc);

@@ -26,7 +26,7 @@
 namespace dsb200 {
 namespace {
 
-constexpr int kLWarps = 12;
+constexpr int kLWarps = 8;      // 2 warps per scheduler -> 255 registers/thread (25 lags x 2 frames + a 25-deep window)
 constexpr int kLThreads = kLWarps * 32;
 constexpr int kUnit = 32;     // frames per warp unit (one Levinson frame per lane)
 constexpr int kHalfUnit = 16; // frames staged at a time
@@ -45,11 +45,16 @@ struct LArgs {
   double eps;
 };
 
+// FULL: frame_length == 400 exactly -- every chunk sample is inside the frame, and only lane 15's halo
+// (samples 400..423) must be forced to zero; otherwise every load is compared with the per-lane limit.
+template <bool FULL>
 __global__ void __launch_bounds__(kLThreads, 1) lpc_wave_kernel(const LArgs A) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int l = lane & 15, h = lane >> 4;
   const int D = A.M + 1;
+  const bool last_lane = (l == 15);
+  const int lim = A.L - kCh * l;                  // valid samples counted from this lane's chunk start
 
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
   float* win = reinterpret_cast<float*>(smem_raw + 8 * kLWarps);  // [448], zero padded
@@ -107,8 +112,11 @@ __global__ void __launch_bounds__(kLThreads, 1) lpc_wave_kernel(const LArgs A) {
         const float* pb = pa + 2 * A.P;
         const float* pw = win + kCh * l;
         auto ld = [&](int i) {                      // windowed sample pair i of this lane's chunk (+ halo)
-          const bool in = (kCh * l + i) < A.L;      // samples past the frame end are structural zeros
-          const float xa = in ? pa[i] : 0.0f, xb = in ? pb[i] : 0.0f, w = pw[i];
+          // samples past the frame end are structural zeros (selected, never multiplied: 0 * inf = nan)
+          const bool out = FULL ? (last_lane && i >= kCh) : (i >= lim);
+          float xa = pa[i], xb = pb[i];
+          const float w = pw[i];
+          if (out) { xa = 0.0f; xb = 0.0f; }
           return make_float2(xa * w, xb * w);
         };
         float2 x2[kCh + kHalo];
@@ -237,9 +245,12 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
               ((kHalfUnit * fp->frame_period) % 4 == 0);
   A.bulk_out = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   A.eps = eps;
-  DSB_CUDA(cudaFuncSetAttribute(lpc_wave_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const bool full = fp->frame_length == 16 * kCh;
+  DSB_CUDA(cudaFuncSetAttribute(lpc_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  DSB_CUDA(cudaFuncSetAttribute(lpc_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_units + kLWarps - 1) / kLWarps, sm_count(device)));
-  lpc_wave_kernel<<<blocks, kLThreads, smem, stream>>>(A);
+  if (full) lpc_wave_kernel<true><<<blocks, kLThreads, smem, stream>>>(A);
+  else lpc_wave_kernel<false><<<blocks, kLThreads, smem, stream>>>(A);
   return after_launch("lpc_wave_kernel");
 }
 

@@ -1,0 +1,273 @@
+// Mel-cepstral analysis, fast path (fp32, sm_100a): fft_length = 512 (257 bins), cep_order <= 24.
+//
+// Reference: diffsptk/modules/mcep.py:189-224.  Per Newton step, with the FFT pairs folded into the
+// host-built tables (tables.make_mcep_tables):
+//     d  = mc @ G            [25 x 257]       e = exp(log x - 2 d)
+//     rt = e @ Hm            [257 x 49]       solve (Toeplitz(rt[:25]) + Hankel(rt)) g = rt[:25] - alpha;  mc += g
+// This is ~250 k FP32 multiply-adds per frame: the FP32 pipe bounds it at 1-2 % of the HBM roofline, so
+// the job of the mapping is to keep every operand of those multiply-adds on chip and reused:
+//   * a warp owns an OCTET of 8 frames; all arithmetic is packed float2 = (frame 2p, frame 2p+1);
+//   * lane l owns bins k = l + 32 t (t < 9) of all 8 frames in registers (log x, d / e): each table
+//     element fetched from shared memory feeds 8 multiply-adds (the generic kernel: 1);
+//   * the 49 (25) dot products over bins are reduced across the 32 lanes with a transposed butterfly
+//     (9 shuffles per output instead of 40);
+//   * the 25 x 25 Newton system is symmetric, so Gaussian elimination never needs another lane's ROW:
+//     the pivot row equals the pivot COLUMN, one entry per lane, published through shared memory in one
+//     parallel store; two frames' systems are eliminated per pass (packed), back substitution likewise.
+// The three tables (G, Hm, P0: 114 KB) stay resident in shared memory for the whole persistent CTA.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dsb200 {
+namespace {
+
+constexpr int kMW = 8;               // warps per CTA (2 per scheduler -> 255 registers per thread)
+constexpr int kMT = kMW * 32;
+constexpr int kKT = 9;               // bins per lane: k = lane + 32 t
+constexpr int kKS = 32 * kKT;        // 288: padded number of bins
+constexpr int kK = 257;
+constexpr int kDM = 25;              // max cepstral dimension (M + 1)
+constexpr int kJS = 49;              // row stride of Hm in shared memory (odd: conflict-free), = 2 * 24 + 1
+constexpr int kPS = 25;              // row stride of P0 in shared memory (odd)
+
+struct MArgs {
+  const float* x;    // [rows, 257] power spectrum
+  float* y;          // [rows, D]
+  const float* P0;   // [257, D]
+  const float* G;    // [D, 257]
+  const float* Hm;   // [257, J]
+  const float* av;   // [D]
+  int64_t rows;
+  int D, J, n_iter;
+};
+
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return f2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ float2 sel2(bool c, float2 a, float2 b) { return c ? a : b; }
+
+// Sum p[0..3] (frames (0,1), (2,3), (4,5), (6,7)) over the 32 lanes.  Returns, in EVERY lane, the total
+// of frame (lane >> 2); 9 shuffles (a plain butterfly would need 40).
+__device__ __forceinline__ float reduce8(const float2 (&p)[4], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  float2 k0 = sel2(h16, p[2], p[0]), k1 = sel2(h16, p[3], p[1]);
+  const float2 s0 = sel2(h16, p[0], p[2]), s1 = sel2(h16, p[1], p[3]);
+  k0 = __fadd2_rn(k0, shfl_xor2(s0, 16));
+  k1 = __fadd2_rn(k1, shfl_xor2(s1, 16));
+  float2 k = sel2(h8, k1, k0);
+  const float2 s = sel2(h8, k0, k1);
+  k = __fadd2_rn(k, shfl_xor2(s, 8));
+  float v = h4 ? k.y : k.x;
+  const float w = h4 ? k.x : k.y;
+  v += __shfl_xor_sync(0xffffffffu, w, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+__device__ __forceinline__ float fast_rcp(float x) {  // MUFU.RCP + one Newton step (~full fp32 accuracy)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return fmaf(r, fmaf(-x, r, 1.0f), r);
+}
+
+__global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = A.D, J = A.J;
+
+  float* Gs = reinterpret_cast<float*>(smem_raw);        // [kDM][kKS]   G[m][k]
+  float* Hs = Gs + kDM * kKS;                            // [kKS][kJS]   Hm[k][j]
+  float* Ps = Hs + kKS * kJS;                            // [kKS][kPS]   P0[k][m]
+  float* avs = Ps + kKS * kPS;                           // [32]
+  float* wbase = avs + 32 + warp * (kDM * 8 + 4 * kJS * 2 + 64 + 64 + 8);
+  float* mcs = wbase;                                    // [kDM][8]   mc[m][frame]
+  float2* rts = reinterpret_cast<float2*>(mcs + kDM * 8);   // [4][kJS]  rt[pair][j] = (frame 2p, frame 2p+1)
+  float2* col = rts + 4 * kJS;                           // [32]  pivot column (= pivot row, by symmetry)
+  float2* xs = col + 32;                                 // [32]  solution broadcast
+  float2* pb = xs + 32;                                  // [1]   pivot right-hand side (+ pad)
+
+  // tables -> shared memory (zero padded to 288 bins so that the tail lanes contribute nothing)
+  for (int i = tid; i < kDM * kKS; i += kMT) {
+    const int m = i / kKS, k = i - m * kKS;
+    Gs[i] = (m < D && k < kK) ? A.G[m * kK + k] : 0.0f;
+  }
+  for (int i = tid; i < kKS * kJS; i += kMT) {
+    const int k = i / kJS, j = i - k * kJS;
+    Hs[i] = (k < kK && j < J) ? A.Hm[k * J + j] : 0.0f;
+  }
+  for (int i = tid; i < kKS * kPS; i += kMT) {
+    const int k = i / kPS, m = i - k * kPS;
+    Ps[i] = (k < kK && m < D) ? A.P0[k * D + m] : 0.0f;
+  }
+  if (tid < 32) avs[tid] = tid < D ? A.av[tid] : 0.0f;
+  __syncthreads();
+
+  const int64_t n_oct = (A.rows + 7) / 8;
+  for (int64_t oct = static_cast<int64_t>(blockIdx.x) * kMW + warp; oct < n_oct;
+       oct += static_cast<int64_t>(gridDim.x) * kMW) {
+    const int64_t r0 = oct * 8;
+    const int nf = static_cast<int>(A.rows - r0 < 8 ? A.rows - r0 : 8);
+
+    // ---- log spectrum of the 8 frames: lx[t][p] = (log x[2p][k_t], log x[2p+1][k_t]) ------------
+    float2 lx[kKT][4];
+#pragma unroll
+    for (int t = 0; t < kKT; ++t) {
+      const int k = lane + 32 * t;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float a = (k < kK && 2 * p < nf) ? A.x[(r0 + 2 * p) * kK + k] : 1.0f;
+        const float b = (k < kK && 2 * p + 1 < nf) ? A.x[(r0 + 2 * p + 1) * kK + k] : 1.0f;
+        lx[t][p] = f2(logf(a), logf(b));
+      }
+    }
+    // ---- initial estimate mc = log x @ P0 (mcep.py:203-207 folded) ------------------------------
+    for (int m = 0; m < D; ++m) {
+      float2 p4[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
+#pragma unroll
+      for (int t = 0; t < kKT; ++t) {
+        const float c = Ps[(lane + 32 * t) * kPS + m];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) p4[p] = __ffma2_rn(lx[t][p], f2(c, c), p4[p]);
+      }
+      const float v = reduce8(p4, lane);
+      if ((lane & 3) == 0) mcs[m * 8 + (lane >> 2)] = v;
+    }
+    __syncwarp();
+
+    for (int it = 0; it < A.n_iter; ++it) {
+      // ---- d = mc @ G ; e = exp(log x - 2 d) ---------------------------------------------------
+      float2 e[kKT][4];
+#pragma unroll
+      for (int t = 0; t < kKT; ++t)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) e[t][p] = f2(0, 0);
+      for (int m = 0; m < D; ++m) {
+        const float4 ma = *reinterpret_cast<const float4*>(mcs + m * 8);
+        const float4 mb = *reinterpret_cast<const float4*>(mcs + m * 8 + 4);
+        const float2 mc2[4] = {f2(ma.x, ma.y), f2(ma.z, ma.w), f2(mb.x, mb.y), f2(mb.z, mb.w)};
+#pragma unroll
+        for (int t = 0; t < kKT; ++t) {
+          const float gk = Gs[m * kKS + lane + 32 * t];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) e[t][p] = __ffma2_rn(mc2[p], f2(gk, gk), e[t][p]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < kKT; ++t)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const float2 a = __ffma2_rn(e[t][p], f2(-2.0f, -2.0f), lx[t][p]);
+          e[t][p] = f2(__expf(a.x), __expf(a.y));
+        }
+      // ---- rt = e @ Hm, reduced over the lanes -------------------------------------------------
+      for (int j = 0; j < J; ++j) {
+        float2 p4[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
+#pragma unroll
+        for (int t = 0; t < kKT; ++t) {
+          const float hk = Hs[(lane + 32 * t) * kJS + j];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) p4[p] = __ffma2_rn(e[t][p], f2(hk, hk), p4[p]);
+        }
+        const float v = reduce8(p4, lane);
+        if ((lane & 3) == 0) reinterpret_cast<float*>(rts)[((lane >> 3) * kJS + j) * 2 + ((lane >> 2) & 1)] = v;
+      }
+      __syncwarp();
+
+      // ---- Newton systems, two frames per pass ---------------------------------------------------
+#pragma unroll 1
+      for (int p = 0; p < 4; ++p) {
+        const float2* rt = rts + p * kJS;
+        const int i = lane;                       // row owned by this lane (rows >= D are inert)
+        float2 a[kDM];
+        float2 b = f2(0, 0);
+        if (i < D) {
+#pragma unroll
+          for (int c = 0; c < kDM; ++c) {
+            const int d = i > c ? i - c : c - i;
+            a[c] = (c < D) ? __fadd2_rn(rt[d], rt[i + c]) : f2(0, 0);
+          }
+          const float alpha_i = avs[i];
+          b = __fadd2_rn(rt[i], f2(-alpha_i, -alpha_i));
+        } else {
+#pragma unroll
+          for (int c = 0; c < kDM; ++c) a[c] = f2(c == 0 ? 1.0f : 0.0f, c == 0 ? 1.0f : 0.0f);
+        }
+        // elimination: the sub-matrix stays symmetric, so pivot row entry c == column entry of lane c
+#pragma unroll
+        for (int pv = 0; pv < kDM - 1; ++pv) {
+          if (pv < D - 1) {
+            col[lane] = a[pv];
+            if (lane == pv) pb[0] = b;
+            __syncwarp();
+            const float2 piv = col[pv];
+            const float2 bp = pb[0];
+            const bool act = (i > pv) && (i < D);
+            const float2 f = act ? f2(a[pv].x * fast_rcp(piv.x), a[pv].y * fast_rcp(piv.y)) : f2(0, 0);
+            const float2 nf2 = f2(-f.x, -f.y);
+#pragma unroll
+            for (int c = pv + 1; c < kDM; ++c) a[c] = __ffma2_rn(nf2, col[c], a[c]);
+            b = __ffma2_rn(nf2, bp, b);
+            __syncwarp();
+          }
+        }
+        // back substitution: x_c published by lane c, consumed by the rows above it
+        float2 acc = f2(0, 0);
+#pragma unroll
+        for (int c = kDM - 1; c >= 0; --c) {
+          if (c < D) {
+            if (lane == c) {
+              const float2 num = f2(b.x - acc.x, b.y - acc.y);
+              xs[c] = f2(num.x * fast_rcp(a[c].x), num.y * fast_rcp(a[c].y));
+            }
+            __syncwarp();
+            if (i < c) acc = __ffma2_rn(a[c], xs[c], acc);
+          }
+        }
+        __syncwarp();
+        if (i < D) {  // mc += g
+          float2* mp = reinterpret_cast<float2*>(mcs + i * 8 + 2 * p);
+          const float2 g = xs[i];
+          *mp = __fadd2_rn(*mp, g);
+        }
+        __syncwarp();
+      }
+    }
+    // ---- store the 8 x D block (contiguous in HBM) ----------------------------------------------
+    for (int idx = lane; idx < nf * D; idx += 32) {
+      const int f = idx / D, m = idx - f * D;
+      A.y[r0 * D + idx] = mcs[m * 8 + f];
+    }
+    __syncwarp();
+  }
+}
+
+}  // namespace
+
+int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_params* p, const float* P0,
+                  const float* G, const float* Hm, const float* av, int device, cudaStream_t stream) {
+  if (p->fft_length != 512 || p->cep_order > kDM - 1) return DSB200_E_UNSUPPORTED;
+  const size_t smem = (static_cast<size_t>(kDM) * kKS + kKS * kJS + kKS * kPS + 32 +
+                       static_cast<size_t>(kMW) * (kDM * 8 + 4 * kJS * 2 + 64 + 64 + 8)) * sizeof(float);
+  if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
+  MArgs A{};
+  A.x = x;
+  A.y = y;
+  A.P0 = P0;
+  A.G = G;
+  A.Hm = Hm;
+  A.av = av;
+  A.rows = rows;
+  A.D = p->cep_order + 1;
+  A.J = 2 * p->cep_order + 1;
+  A.n_iter = p->n_iter;
+  DSB_CUDA(cudaFuncSetAttribute(mcep_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t n_oct = (rows + 7) / 8;
+  const int blocks = static_cast<int>(std::min<int64_t>((n_oct + kMW - 1) / kMW, sm_count(device)));
+  mcep_fast_kernel<<<blocks, kMT, smem, stream>>>(A);
+  return after_launch("mcep_fast_kernel");
+}
+
+}  // namespace dsb200

@@ -34,11 +34,12 @@
 namespace dsb200 {
 namespace {
 
-#ifndef DSB_STFT_WARPS
-#define DSB_STFT_WARPS 12
-#endif
-constexpr int kWarps = DSB_STFT_WARPS;  // 12 -> 168 registers/thread, 16 -> 128 (register file is split per scheduler)
-constexpr int kThreads = kWarps * 32;
+// Warps per CTA (template parameter W of the kernel).  The register file is split per scheduler, so
+// 12 warps allow 168 registers/thread and 16 warps 128.  Measured on B200 (BASELINE config 2): the
+// spectrum kernel is latency-bound and gains 6 % from 16 warps; the MFCC epilogue needs the shared memory
+// of four warps for its tables and runs with 12.
+constexpr int kWarpsSpectrum = 16;
+constexpr int kWarpsMfcc = 12;
 constexpr int kXRow = 17;                              // float2 units per transpose row (16 + 1 pad)
 constexpr int kPlane = 16 * kXRow;                     // float2 units per plane
 constexpr int kXchBytesPerWarp = 2 * 2 * kPlane * 8;   // 2 half-warps x (re, im) planes = 8704 B
@@ -189,8 +190,9 @@ __device__ __forceinline__ void put_bin(float* rowA, float* rowB, bool vB, int k
   }
 }
 
-template <int NJ, bool MASK_ALL, int FMT>
-__global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
+template <int NJ, bool MASK_ALL, int FMT, int W>
+__global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
+  constexpr int kWarps = W, kThreads = W * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -438,13 +440,14 @@ __global__ void __launch_bounds__(kThreads, 1) stft512_kernel(const Args A) {
   if (store_pending && lane == 0) bulk_wait_read();
 }
 
-template <int NJ, bool MASK_ALL>
-int launch_fmt(const Args& A, int fmt, int blocks, size_t smem, cudaStream_t stream) {
+template <int NJ, bool MASK_ALL, int W>
+int launch_fmt(const Args& A, int fmt, size_t smem, int device, cudaStream_t stream) {
+  const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + W - 1) / W, sm_count(device)));
 #define DSB_LAUNCH(F)                                                                                      \
   case F: {                                                                                                \
-    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<NJ, MASK_ALL, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<NJ, MASK_ALL, F, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   static_cast<int>(smem)));                                                \
-    stft512_kernel<NJ, MASK_ALL, F><<<blocks, kThreads, smem, stream>>>(A);                                \
+    stft512_kernel<NJ, MASK_ALL, F, W><<<blocks, W * 32, smem, stream>>>(A);                               \
     break;                                                                                                 \
   }
   switch (fmt) {
@@ -501,7 +504,7 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
   return DSB200_OK;
 }
 
-static size_t smem_bytes(const Args& A, int mf_floats) {
+static size_t smem_bytes(const Args& A, int mf_floats, int kWarps) {
   return 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) + static_cast<size_t>(mf_floats) * 4 +
          static_cast<size_t>(kWarps) * (2 * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
 }
@@ -511,7 +514,9 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
   Args A{};
   int NJ = 16;
   if (int rc = setup_args(A, x, window, y, batch, T_len, p, device, stream, &NJ)) return rc;
-  const size_t smem = smem_bytes(A, 0);
+  // the BASELINE frame length gets the 16-warp build; other lengths stage longer spans and use 12 warps
+  const int kWarps = (NJ == 13) ? kWarpsSpectrum : kWarpsMfcc;
+  const size_t smem = smem_bytes(A, 0, kWarps);
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
   // Output path: rows staged in shared memory + one bulk store per quad, or plain per-lane stores.
   // DSB200_STFT_STORE=direct|bulk overrides the default (tuning knob, read once).
@@ -522,9 +527,8 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
     return kDefaultBulkStore;
   }();
   A.bulk_out = store_mode && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-  const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));
-  if (NJ == 13) return launch_fmt<13, false>(A, p->spec.out_format, blocks, smem, stream);
-  return launch_fmt<16, true>(A, p->spec.out_format, blocks, smem, stream);
+  if (NJ == 13) return launch_fmt<13, false, kWarpsSpectrum>(A, p->spec.out_format, smem, device, stream);
+  return launch_fmt<16, true, kWarpsMfcc>(A, p->spec.out_format, smem, device, stream);
 }
 
 // Fused waveform -> STFT power -> MFCC (stft.py:237-241 + mfcc.py:243-256) in the same kernel.
@@ -538,7 +542,8 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   int NJ = 16;
   if (int rc = setup_args(A, x, window, y, batch, T_len, sp, device, stream, &NJ)) return rc;
   const int mf_floats = (257 * C + C * (M + 1) + (M + 1) + 2 * C + 3) & ~3;
-  const size_t smem = smem_bytes(A, mf_floats);
+  constexpr int kWarps = kWarpsMfcc;
+  const size_t smem = smem_bytes(A, mf_floats, kWarps);
   // the mel rows [4][C] live behind the staged amplitude rows inside the exchange region
   if (smem > static_cast<size_t>(max_dynamic_smem(device)) || (kOutFloats + 4 + 4 * C) * 4 > kXchBytesPerWarp)
     return DSB200_E_UNSUPPORTED;
@@ -555,13 +560,13 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   A.mf_gamma = static_cast<float>(mp->fbank.gamma);
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));
   if (NJ == 13) {
-    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<13, false, kFmtMfcc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-    stft512_kernel<13, false, kFmtMfcc><<<blocks, kThreads, smem, stream>>>(A);
+    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<13, false, kFmtMfcc, kWarps>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    stft512_kernel<13, false, kFmtMfcc, kWarps><<<blocks, kWarps * 32, smem, stream>>>(A);
   } else {
-    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<16, true, kFmtMfcc>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
-    stft512_kernel<16, true, kFmtMfcc><<<blocks, kThreads, smem, stream>>>(A);
+    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<16, true, kFmtMfcc, kWarps>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    stft512_kernel<16, true, kFmtMfcc, kWarps><<<blocks, kWarps * 32, smem, stream>>>(A);
   }
   return after_launch("stft512_kernel<mfcc>");
 }
