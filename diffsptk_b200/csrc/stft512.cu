@@ -183,6 +183,9 @@ __device__ __forceinline__ void put_bin(float* rowA, float* rowB, bool vB, int k
   if (FMT == DSB200_SPEC_COMPLEX) {
     reinterpret_cast<float2*>(rowA)[k] = make_float2(re.x, im.x);
     if (vB) reinterpret_cast<float2*>(rowB)[k] = make_float2(re.y, im.y);
+  } else if (FMT == kFmtMfcc) {  // rowA = this pair's float2 row: (amplitude of frame A, of frame B)
+    const float2 s = fma2(re, re, fma2(im, im, make_float2(eps, eps)));
+    reinterpret_cast<float2*>(rowA)[k] = make_float2(fmt1<FMT>(s.x), fmt1<FMT>(s.y));
   } else {
     const float2 s = fma2(re, re, fma2(im, im, make_float2(eps, eps)));
     rowA[k] = fmt1<FMT>(s.x);
@@ -353,7 +356,10 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     constexpr int kStride = (FMT == DSB200_SPEC_COMPLEX) ? 514 : 257;
     float* rowA;
     float* rowB;
-    if (staged) {
+    if (FMT == kFmtMfcc) {
+      rowA = ostage + h * (2 * 257);   // float2 amp2[257] of this half-warp's frame pair
+      rowB = rowA;
+    } else if (staged) {
       rowA = ostage + (2 * h) * 257;
       rowB = rowA + 257;
     } else {
@@ -384,44 +390,58 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     };
 
     if (FMT == kFmtMfcc) {
-      // ---- MFCC epilogue on the four staged amplitude rows: 8 lanes per frame -------------------
+      // ---- MFCC epilogue: each half-warp owns a frame pair, all arithmetic packed (A, B) ---------
       split(std::true_type{});
       __syncwarp();
       const int C = A.mf_C, M = A.mf_M, M1 = M + 1;
-      const int f = lane >> 3, slot = lane & 7;
-      const float* amp = ostage + f * 257;
-      float* mel = ostage + kOutFloats + 4 + f * C;  // [4][C], inside this warp's exchange region
-      for (int c = slot; c < C; c += 8) {            // triangular filters: only their non-zero rows
-        float acc = 0.0f;
-        for (int k = mfcb[c]; k < mfce[c]; ++k) acc = fmaf(amp[k], mfH[k * C + c], acc);
-        acc = fmaxf(acc, A.mf_floor);
-        mel[c] = (A.mf_gamma == 0.0f) ? logf(acc) : (powf(acc, A.mf_gamma) - 1.0f) / A.mf_gamma;
+      const float2* amp2 = reinterpret_cast<const float2*>(ostage) + h * 257;
+      float2* mel2 = reinterpret_cast<float2*>(ostage + kOutFloats + 4) + h * C;   // [C] log filter-bank outputs
+      for (int c = l; c < C; c += 16) {              // triangular filters: only their non-zero rows
+        float2 acc = make_float2(0.0f, 0.0f);
+        for (int k = mfcb[c]; k < mfce[c]; ++k) acc = fma2s(amp2[k], mfH[k * C + c], acc);
+        acc.x = fmaxf(acc.x, A.mf_floor);
+        acc.y = fmaxf(acc.y, A.mf_floor);
+        if (A.mf_gamma == 0.0f) {
+          mel2[c] = make_float2(__logf(acc.x), __logf(acc.y));
+        } else {
+          const float ig = 1.0f / A.mf_gamma;
+          mel2[c] = make_float2((powf(acc.x, A.mf_gamma) - 1.0f) * ig, (powf(acc.y, A.mf_gamma) - 1.0f) * ig);
+        }
       }
-      float En = 0.0f;
+      float2 En = make_float2(0.0f, 0.0f);
       const bool want_e = (A.mf_format == DSB200_MFCC_YE) || (A.mf_format == DSB200_MFCC_YCE);
       if (want_e) {                                  // E = log((2 sum_{0<k<256} x_k + x_0 + x_256) / 512)
-        float e = 0.0f;
-        for (int k = slot; k < 257; k += 8) {
-          const float v = amp[k];
-          e = fmaf((k == 0 || k == 256) ? 1.0f : 2.0f, v * v, e);
+        float2 e = make_float2(0.0f, 0.0f);
+        for (int k = l; k < 257; k += 16) {
+          const float2 v = amp2[k];
+          const float wgt = (k == 0 || k == 256) ? 1.0f : 2.0f;
+          e = fma2(mul2s(v, wgt), v, e);
         }
-        e += __shfl_xor_sync(0xffffffffu, e, 1);
-        e += __shfl_xor_sync(0xffffffffu, e, 2);
-        e += __shfl_xor_sync(0xffffffffu, e, 4);
-        En = logf(e * (1.0f / 512.0f));
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+          e.x += __shfl_xor_sync(0xffffffffu, e.x, o);
+          e.y += __shfl_xor_sync(0xffffffffu, e.y, o);
+        }
+        En = make_float2(__logf(e.x * (1.0f / 512.0f)), __logf(e.y * (1.0f / 512.0f)));
       }
       __syncwarp();
-      if (4 * g + f < A.n_frames) {
-        float* out = A.y + (row0 + f) * A.mf_D;
-        for (int m = slot; m < M1; m += 8) {         // DCT-II columns 0..M, lifter, pack y | yE | yc | ycE
-          float acc = 0.0f;
-          for (int c = 0; c < C; ++c) acc = fmaf(mel[c], mfW[c * M1 + m], acc);
-          acc *= mfL[m];
-          if (m > 0) out[m - 1] = acc;
-          else if (A.mf_format == DSB200_MFCC_YC || A.mf_format == DSB200_MFCC_YCE) out[M] = acc;
+      float* outA = A.y + (row0 + 2 * h) * A.mf_D;
+      float* outB = outA + A.mf_D;
+      for (int m = l; m < M1; m += 16) {             // DCT-II columns 0..M, lifter, pack y | yE | yc | ycE
+        float2 acc = make_float2(0.0f, 0.0f);
+        for (int c = 0; c < C; ++c) acc = fma2s(mel2[c], mfW[c * M1 + m], acc);
+        acc = mul2s(acc, mfL[m]);
+        int pos = m - 1;
+        if (m == 0) pos = (A.mf_format == DSB200_MFCC_YC || A.mf_format == DSB200_MFCC_YCE) ? M : -1;
+        if (pos >= 0) {
+          if (vA) outA[pos] = acc.x;
+          if (vB) outB[pos] = acc.y;
         }
-        if (slot == 0 && A.mf_format == DSB200_MFCC_YE) out[M] = En;
-        if (slot == 0 && A.mf_format == DSB200_MFCC_YCE) out[M + 1] = En;
+      }
+      if (l == 0 && want_e) {
+        const int pos = (A.mf_format == DSB200_MFCC_YE) ? M : M + 1;
+        if (vA) outA[pos] = En.x;
+        if (vB) outB[pos] = En.y;
       }
       __syncwarp();
     } else if (staged) {
