@@ -16,6 +16,7 @@
 //     parallel store; two frames' systems are eliminated per pass (packed), back substitution likewise.
 // The three tables (G, Hm, P0: 114 KB) stay resident in shared memory for the whole persistent CTA.
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -41,6 +42,16 @@ struct MArgs {
   int64_t rows;
   int D, J, n_iter;
 };
+
+// Compile-time loop: the elimination below indexes register arrays with the loop variable, so it must be
+// expanded even when the body is too large for `#pragma unroll` heuristics.
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
 
 __device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
 __device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
@@ -82,12 +93,12 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
   float* Hs = Gs + kDM * kKS;                            // [kKS][kJS]   Hm[k][j]
   float* Ps = Hs + kKS * kJS;                            // [kKS][kPS]   P0[k][m]
   float* avs = Ps + kKS * kPS;                           // [32]
-  float* wbase = avs + 32 + warp * (kDM * 8 + 4 * kJS * 2 + 64 + 64 + 8);
+  float* wbase = avs + 32 + warp * (kDM * 8 + 4 * kJS * 2 + 128 + 128 + 8);
   float* mcs = wbase;                                    // [kDM][8]   mc[m][frame]
   float2* rts = reinterpret_cast<float2*>(mcs + kDM * 8);   // [4][kJS]  rt[pair][j] = (frame 2p, frame 2p+1)
-  float2* col = rts + 4 * kJS;                           // [32]  pivot column (= pivot row, by symmetry)
-  float2* xs = col + 32;                                 // [32]  solution broadcast
-  float2* pb = xs + 32;                                  // [1]   pivot right-hand side (+ pad)
+  float4* col = reinterpret_cast<float4*>(rts + 4 * kJS);   // [32]  pivot column (= pivot row, by symmetry) of two systems
+  float4* xs = col + 32;                                 // [32]  solution broadcast
+  float4* pb = xs + 32;                                  // [1]   pivot right-hand sides
 
   // tables -> shared memory (zero padded to 288 bins so that the tail lanes contribute nothing)
   for (int i = tid; i < kDM * kKS; i += kMT) {
@@ -176,61 +187,79 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
       }
       __syncwarp();
 
-      // ---- Newton systems, two frames per pass ---------------------------------------------------
+      // ---- Newton systems: two frame PAIRS (four frames) per pass for instruction-level parallelism ----
 #pragma unroll 1
-      for (int p = 0; p < 4; ++p) {
-        const float2* rt = rts + p * kJS;
+      for (int pp = 0; pp < 2; ++pp) {
+        const float2* rtA = rts + (2 * pp) * kJS;
+        const float2* rtB = rtA + kJS;
         const int i = lane;                       // row owned by this lane (rows >= D are inert)
-        float2 a[kDM];
-        float2 b = f2(0, 0);
+        float2 aA[kDM], aB[kDM];
+        float2 bA = f2(0, 0), bB = f2(0, 0);
         if (i < D) {
 #pragma unroll
           for (int c = 0; c < kDM; ++c) {
             const int d = i > c ? i - c : c - i;
-            a[c] = (c < D) ? __fadd2_rn(rt[d], rt[i + c]) : f2(0, 0);
+            aA[c] = (c < D) ? __fadd2_rn(rtA[d], rtA[i + c]) : f2(0, 0);
+            aB[c] = (c < D) ? __fadd2_rn(rtB[d], rtB[i + c]) : f2(0, 0);
           }
           const float alpha_i = avs[i];
-          b = __fadd2_rn(rt[i], f2(-alpha_i, -alpha_i));
+          bA = __fadd2_rn(rtA[i], f2(-alpha_i, -alpha_i));
+          bB = __fadd2_rn(rtB[i], f2(-alpha_i, -alpha_i));
         } else {
 #pragma unroll
-          for (int c = 0; c < kDM; ++c) a[c] = f2(c == 0 ? 1.0f : 0.0f, c == 0 ? 1.0f : 0.0f);
+          for (int c = 0; c < kDM; ++c) aA[c] = aB[c] = f2(c == 0 ? 1.0f : 0.0f, c == 0 ? 1.0f : 0.0f);
         }
-        // elimination: the sub-matrix stays symmetric, so pivot row entry c == column entry of lane c
-#pragma unroll
-        for (int pv = 0; pv < kDM - 1; ++pv) {
-          if (pv < D - 1) {
-            col[lane] = a[pv];
-            if (lane == pv) pb[0] = b;
+        // elimination: the sub-matrix stays symmetric, so pivot-row entry c == column entry held by lane c
+        float2 dA = f2(1, 1), dB = f2(1, 1);     // reciprocal of this lane's own pivot
+        static_for<0, kDM>([&](auto pv_c) {
+          constexpr int pv = decltype(pv_c)::value;
+          if (pv < D) {
+            col[lane] = make_float4(aA[pv].x, aA[pv].y, aB[pv].x, aB[pv].y);
+            if (lane == pv) pb[0] = make_float4(bA.x, bA.y, bB.x, bB.y);
             __syncwarp();
-            const float2 piv = col[pv];
-            const float2 bp = pb[0];
-            const bool act = (i > pv) && (i < D);
-            const float2 f = act ? f2(a[pv].x * fast_rcp(piv.x), a[pv].y * fast_rcp(piv.y)) : f2(0, 0);
-            const float2 nf2 = f2(-f.x, -f.y);
+            const float4 piv = col[pv];
+            const float2 rA = f2(fast_rcp(piv.x), fast_rcp(piv.y)), rB = f2(fast_rcp(piv.z), fast_rcp(piv.w));
+            if (lane == pv) { dA = rA; dB = rB; }
+            if (pv < D - 1) {
+              const float4 bp = pb[0];
+              const bool act = (i > pv) && (i < D);
+              const float2 fA = act ? __fmul2_rn(aA[pv], f2(-rA.x, -rA.y)) : f2(0, 0);   // -a_ip / a_pp
+              const float2 fB = act ? __fmul2_rn(aB[pv], f2(-rB.x, -rB.y)) : f2(0, 0);
 #pragma unroll
-            for (int c = pv + 1; c < kDM; ++c) a[c] = __ffma2_rn(nf2, col[c], a[c]);
-            b = __ffma2_rn(nf2, bp, b);
-            __syncwarp();
-          }
-        }
-        // back substitution: x_c published by lane c, consumed by the rows above it
-        float2 acc = f2(0, 0);
-#pragma unroll
-        for (int c = kDM - 1; c >= 0; --c) {
-          if (c < D) {
-            if (lane == c) {
-              const float2 num = f2(b.x - acc.x, b.y - acc.y);
-              xs[c] = f2(num.x * fast_rcp(a[c].x), num.y * fast_rcp(a[c].y));
+              for (int c = pv + 1; c < kDM; ++c) {
+                const float4 pc = col[c];
+                aA[c] = __ffma2_rn(fA, f2(pc.x, pc.y), aA[c]);
+                aB[c] = __ffma2_rn(fB, f2(pc.z, pc.w), aB[c]);
+              }
+              bA = __ffma2_rn(fA, f2(bp.x, bp.y), bA);
+              bB = __ffma2_rn(fB, f2(bp.z, bp.w), bB);
             }
             __syncwarp();
-            if (i < c) acc = __ffma2_rn(a[c], xs[c], acc);
           }
-        }
+        });
+        // back substitution: x_c published by lane c, consumed by the rows above it
+        float2 accA = f2(0, 0), accB = f2(0, 0);
+        static_for<0, kDM>([&](auto cc) {
+          constexpr int c = kDM - 1 - decltype(cc)::value;
+          if (c < D) {
+            const float2 xa = __fmul2_rn(__fadd2_rn(bA, f2(-accA.x, -accA.y)), dA);
+            const float2 xb = __fmul2_rn(__fadd2_rn(bB, f2(-accB.x, -accB.y)), dB);
+            if (lane == c) xs[c] = make_float4(xa.x, xa.y, xb.x, xb.y);
+            __syncwarp();
+            const float4 xc = xs[c];
+            if (i < c) {
+              accA = __ffma2_rn(aA[c], f2(xc.x, xc.y), accA);
+              accB = __ffma2_rn(aB[c], f2(xc.z, xc.w), accB);
+            }
+          }
+        });
         __syncwarp();
-        if (i < D) {  // mc += g
-          float2* mp = reinterpret_cast<float2*>(mcs + i * 8 + 2 * p);
-          const float2 g = xs[i];
-          *mp = __fadd2_rn(*mp, g);
+        if (i < D) {  // mc += g for frames 4 pp .. 4 pp + 3
+          float4* mp = reinterpret_cast<float4*>(mcs + i * 8 + 4 * pp);
+          const float4 g = xs[i];
+          float4 m = *mp;
+          m.x += g.x; m.y += g.y; m.z += g.z; m.w += g.w;
+          *mp = m;
         }
         __syncwarp();
       }
@@ -250,7 +279,7 @@ int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_para
                   const float* G, const float* Hm, const float* av, int device, cudaStream_t stream) {
   if (p->fft_length != 512 || p->cep_order > kDM - 1) return DSB200_E_UNSUPPORTED;
   const size_t smem = (static_cast<size_t>(kDM) * kKS + kKS * kJS + kKS * kPS + 32 +
-                       static_cast<size_t>(kMW) * (kDM * 8 + 4 * kJS * 2 + 64 + 64 + 8)) * sizeof(float);
+                       static_cast<size_t>(kMW) * (kDM * 8 + 4 * kJS * 2 + 128 + 128 + 8)) * sizeof(float);
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
   MArgs A{};
   A.x = x;
