@@ -257,7 +257,8 @@ def main():
     dev = torch.device("cuda", local)
     dist_on = world > 1
     if dist_on:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))
 
     cfg, B, T, rd, wr = WORKLOADS[args.workload]
     N = n_frames(T)
@@ -275,18 +276,18 @@ def main():
     l0 = _native.launch_count()
     total_ms, per = timed_steps(step, args.steps, args.warmup, dist_on)
     launches = _native.launch_count() - l0
-    if sampler:  # keep the GPU under the same load a little longer so that NVML sees it
-        t_end = time.perf_counter() + 0.4
-        with torch.no_grad():
-            while time.perf_counter() < t_end:
-                for i in range(8):
-                    step(i)
-                torch.cuda.synchronize()
-        clocks = sampler.stop()
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if dist_on:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
+    # Keep every GPU under the same load a little longer so that NVML sees it.  ALL ranks run the SAME
+    # number of extra steps (derived from the max-reduced time): a step may contain a collective.
+    n_extra = max(8, min(4000, int(400.0 / max(total_ms / args.steps, 1e-3))))
+    with torch.no_grad():
+        for i in range(n_extra):
+            step(i)
+        torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
     ms_per_step = total_ms / args.steps
     value = world * frames_per_step / (ms_per_step / 1e3)
 

@@ -397,8 +397,18 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       const float2* amp2 = reinterpret_cast<const float2*>(ostage) + h * 257;
       float2* mel2 = reinterpret_cast<float2*>(ostage + kOutFloats + 4) + h * C;   // [C] log filter-bank outputs
       for (int c = l; c < C; c += 16) {              // triangular filters: only their non-zero rows
-        float2 acc = make_float2(0.0f, 0.0f);
-        for (int k = mfcb[c]; k < mfce[c]; ++k) acc = fma2s(amp2[k], mfH[k * C + c], acc);
+        // four independent partial sums: the filters are short dependent chains otherwise
+        float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, s2 = s0, s3 = s0;
+        const int kb = mfcb[c], ke = mfce[c];
+        int k = kb;
+        for (; k + 3 < ke; k += 4) {
+          s0 = fma2s(amp2[k], mfH[k * C + c], s0);
+          s1 = fma2s(amp2[k + 1], mfH[(k + 1) * C + c], s1);
+          s2 = fma2s(amp2[k + 2], mfH[(k + 2) * C + c], s2);
+          s3 = fma2s(amp2[k + 3], mfH[(k + 3) * C + c], s3);
+        }
+        for (; k < ke; ++k) s0 = fma2s(amp2[k], mfH[k * C + c], s0);
+        float2 acc = add2(add2(s0, s1), add2(s2, s3));
         acc.x = fmaxf(acc.x, A.mf_floor);
         acc.y = fmaxf(acc.y, A.mf_floor);
         if (A.mf_gamma == 0.0f) {
@@ -428,9 +438,16 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       float* outA = A.y + (row0 + 2 * h) * A.mf_D;
       float* outB = outA + A.mf_D;
       for (int m = l; m < M1; m += 16) {             // DCT-II columns 0..M, lifter, pack y | yE | yc | ycE
-        float2 acc = make_float2(0.0f, 0.0f);
-        for (int c = 0; c < C; ++c) acc = fma2s(mel2[c], mfW[c * M1 + m], acc);
-        acc = mul2s(acc, mfL[m]);
+        float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, s2 = s0, s3 = s0;
+        int c = 0;
+        for (; c + 3 < C; c += 4) {
+          s0 = fma2s(mel2[c], mfW[c * M1 + m], s0);
+          s1 = fma2s(mel2[c + 1], mfW[(c + 1) * M1 + m], s1);
+          s2 = fma2s(mel2[c + 2], mfW[(c + 2) * M1 + m], s2);
+          s3 = fma2s(mel2[c + 3], mfW[(c + 3) * M1 + m], s3);
+        }
+        for (; c < C; ++c) s0 = fma2s(mel2[c], mfW[c * M1 + m], s0);
+        float2 acc = mul2s(add2(add2(s0, s1), add2(s2, s3)), mfL[m]);
         int pos = m - 1;
         if (m == 0) pos = (A.mf_format == DSB200_MFCC_YC || A.mf_format == DSB200_MFCC_YCE) ? M : -1;
         if (pos >= 0) {

@@ -57,3 +57,23 @@ def test_sass_is_sm100a(native_lib):
     if out.returncode != 0:
         pytest.skip("cuobjdump not available")
     assert "sm_100a" in out.stdout
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU fallback: without the built .so the package must raise, not degrade."""
+    from diffsptk_b200 import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "missing.so"))
+    with pytest.raises(RuntimeError, match="native library not found"):
+        _native.load()
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under diffsptk_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "diffsptk_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), f
+                assert "np_oracle" not in txt, f
