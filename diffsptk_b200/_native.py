@@ -64,6 +64,10 @@ _TYPED = {
     "dsb200_mcep": [_P, _P, _I64, C.POINTER(McepParams), _P, _P, _P, _P, _INT, _P],
     "dsb200_fbank": [_P, _P, _P, _P, _P, _P, _I64, C.POINTER(FbankParams), _INT, _P],
     "dsb200_mfcc": [_P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(MfccParams), _INT, _P],
+    "dsb200_stft_backward": [_P, _P, _P, _P, _P, _I64, _I64, C.POINTER(StftParams), _INT, _P],
+    "dsb200_rfft_backward": [_P, _P, _P, _I64, _I32, _I32, _I32, _INT, _P],
+    "dsb200_spec_backward": [_P, _I32, _P, _P, _I64, C.POINTER(SpecParams), _INT, _P],
+    "dsb200_frame_backward": [_P, _P, _I64, _I64, C.POINTER(FrameParams), _INT, _P],
     "dsb200_mfcc_wave": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, C.POINTER(StftParams),
                          C.POINTER(MfccParams), _INT, _P],
 }

@@ -11,7 +11,7 @@
 // fftr.py:136-151, spec.py:152-178, stft.py:237-241.
 #include <algorithm>
 
-#include "common.cuh"
+#include "rowfft.cuh"
 
 namespace dsb200 {
 namespace {
@@ -44,77 +44,12 @@ struct RowArgs {
 template <typename T>
 __device__ __forceinline__ cx_t<T> ld_tw(const cx_t<T>* tw, int k) { return tw[k]; }
 
-// Stockham autosort radix-2 FFT of Nc complex points held in shared memory by one warp.
-// tw[k] = exp(-2 pi i k / (2 Nc)).  Returns the buffer that holds the natural-order result.
-template <typename T>
-__device__ cx_t<T>* warp_fft_pow2(cx_t<T>* in, cx_t<T>* out, int Nc, const cx_t<T>* tw, int lane) {
-  const int half = Nc >> 1;
-  for (int Ns = 1; Ns < Nc; Ns <<= 1) {
-    const int tstride = Nc / Ns;
-    for (int j = lane; j < half; j += 32) {
-      const int k = j & (Ns - 1);
-      const cx_t<T> w = tw[k * tstride];
-      const cx_t<T> u = in[j];
-      const cx_t<T> v = cmul(in[j + half], w);
-      const int j0 = ((j - k) << 1) + k;
-      out[j0] = cadd(u, v);
-      out[j0 + Ns] = csub(u, v);
-    }
-    __syncwarp();
-    cx_t<T>* t = in; in = out; out = t;
-  }
-  return in;
-}
-
-// Direct DFT of `len` real samples (zero beyond) to bins 0..Nc, table-driven, one warp.
-template <typename T>
-__device__ void warp_dft_direct(const T* xin, int len, cx_t<T>* X, int n, int Nc, const cx_t<T>* tw, int lane) {
-  for (int k = lane; k <= Nc; k += 32) {
-    T re = 0, im = 0;
-    int idx = 0;
-    for (int j = 0; j < len; ++j) {
-      const cx_t<T> w = tw[idx];
-      re = dfma(xin[j], w.x, re);
-      im = dfma(xin[j], w.y, im);
-      idx += k;
-      if (idx >= n) idx -= n;
-    }
-    X[k] = mk<T>(re, im);
-  }
-  __syncwarp();
-}
-
-// Bin k of the length-n real FFT from the length-Nc complex FFT Z of the even/odd packing.
-template <typename T>
-__device__ __forceinline__ cx_t<T> real_split(const cx_t<T>* Z, int k, int Nc, const cx_t<T>* tw) {
-  const int k1 = (k == Nc) ? 0 : k;
-  const int k2 = (k == 0 || k == Nc) ? 0 : Nc - k;
-  const cx_t<T> zk = Z[k1];
-  cx_t<T> zc = Z[k2];
-  zc.y = -zc.y;
-  const T half = static_cast<T>(0.5);
-  const cx_t<T> E = mk<T>(half * (zk.x + zc.x), half * (zk.y + zc.y));
-  const cx_t<T> O = mk<T>(half * (zk.y - zc.y), -half * (zk.x - zc.x));
-  const cx_t<T> w = (k == Nc) ? mk<T>(static_cast<T>(-1), static_cast<T>(0)) : tw[k];
-  return cadd(E, cmul(w, O));
-}
-
-template <typename T>
-__device__ __forceinline__ T spec_format(T s, int fmt) {
-  switch (fmt) {
-    case DSB200_SPEC_DB: return static_cast<T>(10) * dlog10(s);
-    case DSB200_SPEC_LOGMAG: return static_cast<T>(0.5) * dlog(s);
-    case DSB200_SPEC_MAGNITUDE: return dsqrt(s);
-    default: return s;
-  }
-}
-
 // Transform the `len` real samples staged in buf0[0..n) (zero padded) and return a pointer to
 // the spectrum accessor state: for pow2, Z (length Nc, needs real_split); for direct, X itself.
 template <typename T>
 __device__ __forceinline__ const cx_t<T>* transform_row(const RowArgs<T>& A, cx_t<T>* buf0, cx_t<T>* buf1,
                                                         int len, const cx_t<T>* tw, int lane) {
-  if (A.pow2) return warp_fft_pow2<T>(buf0, buf1, A.Nc, tw, lane);
+  if (A.pow2) return warp_fft_pow2<T>(buf0, buf1, A.Nc, tw, lane, A.n);
   warp_dft_direct<T>(reinterpret_cast<const T*>(buf0), len, buf1, A.n, A.Nc, tw, lane);
   return buf1;
 }

@@ -54,7 +54,6 @@ class RealValuedFastFourierTransform(BaseFunctionalModule):
 
     @staticmethod
     def _forward(x: torch.Tensor, *, fft_length: int | None, out_format: int) -> torch.Tensor:
-        ops._no_grad_check(x)
         n = x.size(-1) if fft_length is None else fft_length
         if n % 2 == 1:
             raise ValueError("fft_length must be positive even.")

@@ -42,5 +42,4 @@ class Frame(BaseFunctionalModule):
     @staticmethod
     def _forward(x: torch.Tensor, *, frame_length: int, frame_period: int, center: bool, zmean: bool,
                  mode: str) -> torch.Tensor:
-        ops._no_grad_check(x)
         return ops.frame(x, frame_length, frame_period, center, zmean, pad_mode_id(mode))

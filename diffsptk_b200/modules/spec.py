@@ -64,5 +64,5 @@ class Spectrum(BaseFunctionalModule):
                  relative_floor: float | None, out_format: int) -> torch.Tensor:
         if b is None and a is None:
             raise ValueError("Either b or a must be specified.")
-        ops._no_grad_check(b, a)
+        ops._no_grad_check(a)  # only the numerator spectrum is differentiable
         return ops.spec(b, a, fft_length, eps, -1.0 if relative_floor is None else relative_floor, out_format)

@@ -90,7 +90,6 @@ class ShortTimeFourierTransform(BaseFunctionalModule):
                  pad_mode: int, eps: float, relative_floor: float | None, out_format: int, frame=None,
                  window=None, spec=None, window_table: torch.Tensor | None = None) -> torch.Tensor:
         table = window_table if window_table is not None else window.window
-        ops._no_grad_check(x, table)
         y = ops.stft(x, table, frame_period, fft_length, center, zmean, pad_mode, eps,
                      -1.0 if relative_floor is None else relative_floor, out_format)
         return torch.view_as_complex(y) if out_format == 4 else y

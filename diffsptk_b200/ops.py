@@ -59,8 +59,9 @@ def _dev(t: Tensor) -> int:
 def _no_grad_check(*ts):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
         raise NotImplementedError(
-            "diffsptk_b200 kernels are forward-only: wrap the call in torch.no_grad() or detach() "
-            "the inputs (autograd for the fused ops is listed under 'next' in DESIGN.md)."
+            "this diffsptk_b200 op is forward-only (the spectral ops frame / window / fftr / spec / stft / "
+            "freqt / dct are differentiable; the LPC and cepstral solvers are not yet): wrap the call in "
+            "torch.no_grad() or detach() the inputs."
         )
 
 
@@ -422,3 +423,188 @@ class HostStftPipeline:
             self.close()
         except Exception:
             pass
+
+
+# ------------------------------------------------------------------------------------- autograd
+# SURVEY.md section 8(f) rank 1.  The spectral half of the path (frame, window, fftr, spec (numerator),
+# stft, freqt, dct) is differentiable through native adjoint kernels; the LPC / cepstral solvers are
+# forward-only and raise instead of silently dropping gradients (modules call _no_grad_check).
+def _like_input(g: Tensor, x: Tensor) -> Tensor:
+    return g.reshape(x.shape).to(x.dtype) if x.dtype.is_floating_point else None
+
+
+@torch.library.custom_op(f"{_NS}::stft_backward", mutates_args=(), device_types="cuda")
+def stft_backward(x: Tensor, window: Tensor, gy: Tensor, frame_period: int, fft_length: int, center: bool,
+                  zmean: bool, pad_mode: int, eps: float, relative_floor: float, out_format: int,
+                  need_gw: bool) -> tuple[Tensor, Tensor]:
+    dt = _native_dtype(x, window)
+    xc, wc, gc = _prep(x, dt), _prep(window, dt), _prep(gy, dt)
+    T = xc.shape[-1]
+    B = xc.numel() // max(T, 1)
+    gx = torch.empty_like(xc)
+    gw = torch.empty(wc.shape if need_gw else (0,), device=x.device, dtype=dt)
+    p = N.StftParams(_frame_params(wc.shape[-1], frame_period, center, zmean, pad_mode),
+                     _spec_params(fft_length, out_format, eps, relative_floor))
+    N.check(N.typed("dsb200_stft_backward", dt == torch.float64)(
+        _ptr(xc), _ptr(wc), _ptr(gc), _ptr(gx), _ptr(gw) if need_gw else None, B, T, C.byref(p), _dev(x),
+        _stream(x)))
+    return gx, gw
+
+
+@stft_backward.register_fake
+def _(x, window, gy, frame_period, fft_length, center, zmean, pad_mode, eps, relative_floor, out_format, need_gw):
+    dt = _native_dtype(x, window)
+    return x.new_empty(x.shape, dtype=dt), x.new_empty(window.shape if need_gw else (0,), dtype=dt)
+
+
+def _stft_setup(ctx, inputs, output):
+    x, window, *rest = inputs
+    ctx.save_for_backward(x, window)
+    ctx.rest = rest
+
+
+def _stft_bwd(ctx, g):
+    x, window = ctx.saved_tensors
+    need_gw = ctx.needs_input_grad[1]
+    gx, gw = stft_backward(x, window, g, *ctx.rest, need_gw)
+    return (_like_input(gx, x), gw.to(window.dtype) if need_gw else None) + (None,) * len(ctx.rest)
+
+
+torch.library.register_autograd(f"{_NS}::stft", _stft_bwd, setup_context=_stft_setup)
+
+
+@torch.library.custom_op(f"{_NS}::frame_backward", mutates_args=(), device_types="cuda")
+def frame_backward(gy: Tensor, T: int, frame_period: int, center: bool, zmean: bool, pad_mode: int) -> Tensor:
+    dt = _native_dtype(gy)
+    gc = _prep(gy, dt)
+    L = gc.shape[-1]
+    lead = gc.shape[:-2]
+    B = 1
+    for s in lead:
+        B *= s
+    gx = torch.empty((*lead, T), device=gy.device, dtype=dt)
+    p = _frame_params(L, frame_period, center, zmean, pad_mode)
+    N.check(N.typed("dsb200_frame_backward", dt == torch.float64)(_ptr(gc), _ptr(gx), B, T, C.byref(p), _dev(gy),
+                                                                  _stream(gy)))
+    return gx
+
+
+@frame_backward.register_fake
+def _(gy, T, frame_period, center, zmean, pad_mode):
+    return gy.new_empty((*gy.shape[:-2], T), dtype=_native_dtype(gy))
+
+
+def _frame_setup(ctx, inputs, output):
+    x, frame_length, frame_period, center, zmean, pad_mode = inputs
+    ctx.x_meta = (x.shape, x.dtype)
+    ctx.args = (frame_period, center, zmean, pad_mode)
+
+
+def _frame_bwd(ctx, g):
+    shape, dtype = ctx.x_meta
+    gx = frame_backward(g, shape[-1], *ctx.args)
+    return (gx.reshape(shape).to(dtype) if dtype.is_floating_point else None, None, None, None, None, None)
+
+
+torch.library.register_autograd(f"{_NS}::frame", _frame_bwd, setup_context=_frame_setup)
+
+
+@torch.library.custom_op(f"{_NS}::rfft_backward", mutates_args=(), device_types="cuda")
+def rfft_backward(x: Tensor, gy: Tensor, fft_length: int, out_format: int) -> Tensor:
+    dt = _native_dtype(x)
+    xc, gc = _prep(x, dt), _prep(gy, dt)
+    Lin = xc.shape[-1]
+    rows = xc.numel() // max(Lin, 1)
+    gx = torch.empty_like(xc)
+    N.check(N.typed("dsb200_rfft_backward", dt == torch.float64)(_ptr(xc), _ptr(gc), _ptr(gx), rows, Lin, fft_length,
+                                                                 out_format, _dev(x), _stream(x)))
+    return gx
+
+
+@rfft_backward.register_fake
+def _(x, gy, fft_length, out_format):
+    return x.new_empty(x.shape, dtype=_native_dtype(x))
+
+
+def _rfft_setup(ctx, inputs, output):
+    x, fft_length, out_format = inputs
+    ctx.save_for_backward(x)
+    ctx.args = (fft_length, out_format)
+
+
+def _rfft_bwd(ctx, g):
+    (x,) = ctx.saved_tensors
+    return _like_input(rfft_backward(x, g, *ctx.args), x), None, None
+
+
+torch.library.register_autograd(f"{_NS}::rfft", _rfft_bwd, setup_context=_rfft_setup)
+
+
+@torch.library.custom_op(f"{_NS}::spec_backward", mutates_args=(), device_types="cuda")
+def spec_backward(b: Tensor, gy: Tensor, fft_length: int, eps: float, relative_floor: float, out_format: int) -> Tensor:
+    dt = _native_dtype(b)
+    bc, gc = _prep(b, dt), _prep(gy, dt)
+    Lb = bc.shape[-1]
+    rows = bc.numel() // max(Lb, 1)
+    gb = torch.empty_like(bc)
+    p = _spec_params(fft_length, out_format, eps, relative_floor)
+    N.check(N.typed("dsb200_spec_backward", dt == torch.float64)(_ptr(bc), Lb, _ptr(gc), _ptr(gb), rows, C.byref(p),
+                                                                 _dev(b), _stream(b)))
+    return gb
+
+
+@spec_backward.register_fake
+def _(b, gy, fft_length, eps, relative_floor, out_format):
+    return b.new_empty(b.shape, dtype=_native_dtype(b))
+
+
+def _spec_setup(ctx, inputs, output):
+    b, a, *rest = inputs
+    if a is not None:
+        raise NotImplementedError("gradients through the denominator spectrum (a) are not implemented")
+    ctx.save_for_backward(b)
+    ctx.rest = rest
+
+
+def _spec_bwd(ctx, g):
+    (b,) = ctx.saved_tensors
+    return (_like_input(spec_backward(b, g, *ctx.rest), b), None) + (None,) * len(ctx.rest)
+
+
+torch.library.register_autograd(f"{_NS}::spec", _spec_bwd, setup_context=_spec_setup)
+
+
+def _window_setup(ctx, inputs, output):
+    x, w, out_length = inputs
+    ctx.save_for_backward(x, w)
+
+
+def _window_bwd(ctx, g):
+    x, w = ctx.saved_tensors
+    L1 = x.shape[-1]
+    gs = g[..., :L1] if g.shape[-1] >= L1 else torch.nn.functional.pad(g, (0, L1 - g.shape[-1]))
+    gx = window(gs, w, L1) if ctx.needs_input_grad[0] else None  # g * w with the same kernel
+    gw = None
+    if ctx.needs_input_grad[1]:
+        gw = (gs.to(w.dtype) * x.to(w.dtype)).reshape(-1, L1).sum(0)
+    return (_like_input(gx, x) if gx is not None else None), gw, None
+
+
+torch.library.register_autograd(f"{_NS}::window", _window_bwd, setup_context=_window_setup)
+
+
+def _rowmat_setup(ctx, inputs, output):
+    x, W = inputs
+    ctx.save_for_backward(x, W)
+
+
+def _rowmat_bwd(ctx, g):
+    x, W = ctx.saved_tensors
+    gx = rowmat(g, W.t().contiguous()) if ctx.needs_input_grad[0] else None
+    gW = None
+    if ctx.needs_input_grad[1]:
+        gW = x.reshape(-1, x.shape[-1]).to(W.dtype).t() @ g.reshape(-1, g.shape[-1]).to(W.dtype)
+    return (_like_input(gx, x) if gx is not None else None), gW
+
+
+torch.library.register_autograd(f"{_NS}::rowmat", _rowmat_bwd, setup_context=_rowmat_setup)

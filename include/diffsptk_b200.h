@@ -198,6 +198,24 @@ DSB200_DECL2(dsb200_mfcc_wave, (const void* x, const void* window, const void* H
                                 int64_t batch, int64_t T, const dsb200_stft_params* sp,
                                 const dsb200_mfcc_params* mp, int device, void* stream))
 
+/* ---- backward (vector-Jacobian products; SURVEY.md section 8f rank 1: the reference is differentiable) ----
+ * The forward kernels are fused, so torch autograd cannot see inside them; these are their adjoints.  Nothing
+ * is saved by the forward pass: each row's spectrum is recomputed on chip.  gx / gw are overwritten. */
+
+/* d/dx and (optionally, gw != NULL) d/dwindow of dsb200_stft.  gy has the layout of the forward output. */
+DSB200_DECL2(dsb200_stft_backward, (const void* x, const void* window, const void* gy, void* gx, void* gw,
+                                    int64_t batch, int64_t T, const dsb200_stft_params* p, int device,
+                                    void* stream))
+/* d/dx of dsb200_rfft. */
+DSB200_DECL2(dsb200_rfft_backward, (const void* x, const void* gy, void* gx, int64_t rows, int32_t in_length,
+                                    int32_t fft_length, int32_t out_format, int device, void* stream))
+/* d/db of dsb200_spec (numerator-only spectra). */
+DSB200_DECL2(dsb200_spec_backward, (const void* b, int32_t b_length, const void* gy, void* gb, int64_t rows,
+                                    const dsb200_spec_params* p, int device, void* stream))
+/* d/dx of dsb200_frame: scatter-add of the frame gradients (adjoint of pad + unfold + mean removal). */
+DSB200_DECL2(dsb200_frame_backward, (const void* gy, void* gx, int64_t batch, int64_t T,
+                                     const dsb200_frame_params* p, int device, void* stream))
+
 /* ---- host-buffer pipeline (the end-to-end path: pinned host -> device -> kernel -> host) -------------
  * One object owns two device staging slots and three streams (H2D, compute, D2H) and runs
  * dsb200_stft on utterance chunks so that copies overlap compute.  x_host[batch,T], y_host[batch,N,K]
