@@ -31,6 +31,7 @@ constexpr int kK = 257;
 constexpr int kDM = 25;              // max cepstral dimension (M + 1)
 constexpr int kJS = 49;              // row stride of Hm in shared memory (odd: conflict-free), = 2 * 24 + 1
 constexpr int kPS = 25;              // row stride of P0 in shared memory (odd)
+constexpr int kWarpFloats = kDM * 8 + 4 * kJS * 2 + 256 + 256 + 8 + kKT * 4 * 32 * 2;   // per-warp scratch
 
 struct MArgs {
   const float* x;    // [rows, 257] power spectrum
@@ -93,12 +94,13 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
   float* Hs = Gs + kDM * kKS;                            // [kKS][kJS]   Hm[k][j]
   float* Ps = Hs + kKS * kJS;                            // [kKS][kPS]   P0[k][m]
   float* avs = Ps + kKS * kPS;                           // [32]
-  float* wbase = avs + 32 + warp * (kDM * 8 + 4 * kJS * 2 + 128 + 128 + 8);
+  float* wbase = avs + 32 + warp * kWarpFloats;
   float* mcs = wbase;                                    // [kDM][8]   mc[m][frame]
   float2* rts = reinterpret_cast<float2*>(mcs + kDM * 8);   // [4][kJS]  rt[pair][j] = (frame 2p, frame 2p+1)
-  float4* col = reinterpret_cast<float4*>(rts + 4 * kJS);   // [32]  pivot column (= pivot row, by symmetry) of two systems
-  float4* xs = col + 32;                                 // [32]  solution broadcast
-  float4* pb = xs + 32;                                  // [1]   pivot right-hand sides
+  float4* col = reinterpret_cast<float4*>(rts + 4 * kJS);   // [2][32] pivot column (= pivot row, by symmetry), 8 systems
+  float4* xs = col + 64;                                 // [2][32] solution broadcast
+  float4* pb = xs + 64;                                  // [2]     pivot right-hand sides
+  float2* lxs = reinterpret_cast<float2*>(pb + 2);       // [kKT][4][32] log spectrum (frame pair p, bin lane + 32 t)
 
   // tables -> shared memory (zero padded to 288 bins so that the tail lanes contribute nothing)
   for (int i = tid; i < kDM * kKS; i += kMT) {
@@ -123,7 +125,6 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
     const int nf = static_cast<int>(A.rows - r0 < 8 ? A.rows - r0 : 8);
 
     // ---- log spectrum of the 8 frames: lx[t][p] = (log x[2p][k_t], log x[2p+1][k_t]) ------------
-    float2 lx[kKT][4];
 #pragma unroll
     for (int t = 0; t < kKT; ++t) {
       const int k = lane + 32 * t;
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
       for (int p = 0; p < 4; ++p) {
         const float a = (k < kK && 2 * p < nf) ? A.x[(r0 + 2 * p) * kK + k] : 1.0f;
         const float b = (k < kK && 2 * p + 1 < nf) ? A.x[(r0 + 2 * p + 1) * kK + k] : 1.0f;
-        lx[t][p] = f2(logf(a), logf(b));
+        lxs[(t * 4 + p) * 32 + lane] = f2(logf(a), logf(b));
       }
     }
     // ---- initial estimate mc = log x @ P0 (mcep.py:203-207 folded) ------------------------------
@@ -141,7 +142,7 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
       for (int t = 0; t < kKT; ++t) {
         const float c = Ps[(lane + 32 * t) * kPS + m];
 #pragma unroll
-        for (int p = 0; p < 4; ++p) p4[p] = __ffma2_rn(lx[t][p], f2(c, c), p4[p]);
+        for (int p = 0; p < 4; ++p) p4[p] = __ffma2_rn(lxs[(t * 4 + p) * 32 + lane], f2(c, c), p4[p]);
       }
       const float v = reduce8(p4, lane);
       if ((lane & 3) == 0) mcs[m * 8 + (lane >> 2)] = v;
@@ -170,96 +171,136 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
       for (int t = 0; t < kKT; ++t)
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float2 a = __ffma2_rn(e[t][p], f2(-2.0f, -2.0f), lx[t][p]);
+          const float2 a = __ffma2_rn(e[t][p], f2(-2.0f, -2.0f), lxs[(t * 4 + p) * 32 + lane]);
           e[t][p] = f2(__expf(a.x), __expf(a.y));
         }
-      // ---- rt = e @ Hm, reduced over the lanes -------------------------------------------------
-      for (int j = 0; j < J; ++j) {
-        float2 p4[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
+      // ---- rt = e @ Hm, reduced over the lanes; four columns per round so that the shuffle chains of one
+      //      column overlap the multiply-adds of the next ---------------------------------------------------
+      auto rt_columns = [&](auto nc_c, int j0) {
+        constexpr int NC = decltype(nc_c)::value;
+        float2 acc[NC][4];
+#pragma unroll
+        for (int u = 0; u < NC; ++u)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) acc[u][p] = f2(0, 0);
 #pragma unroll
         for (int t = 0; t < kKT; ++t) {
-          const float hk = Hs[(lane + 32 * t) * kJS + j];
 #pragma unroll
-          for (int p = 0; p < 4; ++p) p4[p] = __ffma2_rn(e[t][p], f2(hk, hk), p4[p]);
+          for (int u = 0; u < NC; ++u) {
+            const float hk = Hs[(lane + 32 * t) * kJS + j0 + u];
+#pragma unroll
+            for (int p = 0; p < 4; ++p) acc[u][p] = __ffma2_rn(e[t][p], f2(hk, hk), acc[u][p]);
+          }
         }
-        const float v = reduce8(p4, lane);
-        if ((lane & 3) == 0) reinterpret_cast<float*>(rts)[((lane >> 3) * kJS + j) * 2 + ((lane >> 2) & 1)] = v;
+#pragma unroll
+        for (int u = 0; u < NC; ++u) {
+          const float v = reduce8(acc[u], lane);
+          if ((lane & 3) == 0)
+            reinterpret_cast<float*>(rts)[((lane >> 3) * kJS + j0 + u) * 2 + ((lane >> 2) & 1)] = v;
+        }
+      };
+      {
+        int j = 0;
+        for (; j + 4 <= J; j += 4) rt_columns(std::integral_constant<int, 4>{}, j);
+        for (; j < J; ++j) rt_columns(std::integral_constant<int, 1>{}, j);
       }
       __syncwarp();
 
-      // ---- Newton systems: two frame PAIRS (four frames) per pass for instruction-level parallelism ----
-#pragma unroll 1
-      for (int pp = 0; pp < 2; ++pp) {
-        const float2* rtA = rts + (2 * pp) * kJS;
-        const float2* rtB = rtA + kJS;
-        const int i = lane;                       // row owned by this lane (rows >= D are inert)
-        float2 aA[kDM], aB[kDM];
-        float2 bA = f2(0, 0), bB = f2(0, 0);
+      // ---- Newton systems of all 8 frames (4 packed pairs) in one pass: lane = row ---------------------
+      {
+        const int i = lane;
+        float2 a[4][kDM], b[4];
         if (i < D) {
-#pragma unroll
-          for (int c = 0; c < kDM; ++c) {
-            const int d = i > c ? i - c : c - i;
-            aA[c] = (c < D) ? __fadd2_rn(rtA[d], rtA[i + c]) : f2(0, 0);
-            aB[c] = (c < D) ? __fadd2_rn(rtB[d], rtB[i + c]) : f2(0, 0);
-          }
           const float alpha_i = avs[i];
-          bA = __fadd2_rn(rtA[i], f2(-alpha_i, -alpha_i));
-          bB = __fadd2_rn(rtB[i], f2(-alpha_i, -alpha_i));
-        } else {
 #pragma unroll
-          for (int c = 0; c < kDM; ++c) aA[c] = aB[c] = f2(c == 0 ? 1.0f : 0.0f, c == 0 ? 1.0f : 0.0f);
+          for (int q = 0; q < 4; ++q) {
+            const float2* rt = rts + q * kJS;
+#pragma unroll
+            for (int c = 0; c < kDM; ++c) {
+              const int d = i > c ? i - c : c - i;
+              a[q][c] = (c < D) ? __fadd2_rn(rt[d], rt[i + c]) : f2(0, 0);
+            }
+            b[q] = __fadd2_rn(rt[i], f2(-alpha_i, -alpha_i));
+          }
+        } else {
+          // Rows D..24 are identity rows with a zero right-hand side (lanes >= 25 are all-zero rows that are
+          // never pivots): the elimination can then run all 25 pivots unconditionally -- no run-time
+          // `pv < D` tests, which the compiler otherwise keeps as a bit mask of 50 predicates.
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int c = 0; c < kDM; ++c) a[q][c] = f2(c == i ? 1.0f : 0.0f, c == i ? 1.0f : 0.0f);
+            b[q] = f2(0, 0);
+          }
         }
-        // elimination: the sub-matrix stays symmetric, so pivot-row entry c == column entry held by lane c
-        float2 dA = f2(1, 1), dB = f2(1, 1);     // reciprocal of this lane's own pivot
+        // Elimination.  The sub-matrix stays symmetric, so pivot-row entry c == column entry held by lane c:
+        // one parallel store publishes the whole pivot row.
+        float2 dinv[4] = {f2(1, 1), f2(1, 1), f2(1, 1), f2(1, 1)};   // 1 / (this lane's own pivot)
         static_for<0, kDM>([&](auto pv_c) {
           constexpr int pv = decltype(pv_c)::value;
-          if (pv < D) {
-            col[lane] = make_float4(aA[pv].x, aA[pv].y, aB[pv].x, aB[pv].y);
-            if (lane == pv) pb[0] = make_float4(bA.x, bA.y, bB.x, bB.y);
-            __syncwarp();
-            const float4 piv = col[pv];
-            const float2 rA = f2(fast_rcp(piv.x), fast_rcp(piv.y)), rB = f2(fast_rcp(piv.z), fast_rcp(piv.w));
-            if (lane == pv) { dA = rA; dB = rB; }
-            if (pv < D - 1) {
-              const float4 bp = pb[0];
-              const bool act = (i > pv) && (i < D);
-              const float2 fA = act ? __fmul2_rn(aA[pv], f2(-rA.x, -rA.y)) : f2(0, 0);   // -a_ip / a_pp
-              const float2 fB = act ? __fmul2_rn(aB[pv], f2(-rB.x, -rB.y)) : f2(0, 0);
-#pragma unroll
-              for (int c = pv + 1; c < kDM; ++c) {
-                const float4 pc = col[c];
-                aA[c] = __ffma2_rn(fA, f2(pc.x, pc.y), aA[c]);
-                aB[c] = __ffma2_rn(fB, f2(pc.z, pc.w), aB[c]);
-              }
-              bA = __ffma2_rn(fA, f2(bp.x, bp.y), bA);
-              bB = __ffma2_rn(fB, f2(bp.z, bp.w), bB);
-            }
-            __syncwarp();
+          col[lane] = make_float4(a[0][pv].x, a[0][pv].y, a[1][pv].x, a[1][pv].y);
+          col[32 + lane] = make_float4(a[2][pv].x, a[2][pv].y, a[3][pv].x, a[3][pv].y);
+          if (lane == pv) {
+            pb[0] = make_float4(b[0].x, b[0].y, b[1].x, b[1].y);
+            pb[1] = make_float4(b[2].x, b[2].y, b[3].x, b[3].y);
           }
+          __syncwarp();
+          const float4 p01 = col[pv], p23 = col[32 + pv];
+          const float2 r[4] = {f2(fast_rcp(p01.x), fast_rcp(p01.y)), f2(fast_rcp(p01.z), fast_rcp(p01.w)),
+                               f2(fast_rcp(p23.x), fast_rcp(p23.y)), f2(fast_rcp(p23.z), fast_rcp(p23.w))};
+          const bool act = i > pv;                 // identity / zero rows hold a zero here: factor 0
+          float2 f[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            f[q] = act ? __fmul2_rn(a[q][pv], f2(-r[q].x, -r[q].y)) : f2(0, 0);   // -a_ip / a_pp
+            dinv[q] = sel2(lane == pv, r[q], dinv[q]);
+          }
+          if constexpr (pv < kDM - 1) {
+#pragma unroll
+            for (int c = pv + 1; c < kDM; ++c) {
+              const float4 c01 = col[c], c23 = col[32 + c];
+              a[0][c] = __ffma2_rn(f[0], f2(c01.x, c01.y), a[0][c]);
+              a[1][c] = __ffma2_rn(f[1], f2(c01.z, c01.w), a[1][c]);
+              a[2][c] = __ffma2_rn(f[2], f2(c23.x, c23.y), a[2][c]);
+              a[3][c] = __ffma2_rn(f[3], f2(c23.z, c23.w), a[3][c]);
+            }
+            const float4 b01 = pb[0], b23 = pb[1];
+            b[0] = __ffma2_rn(f[0], f2(b01.x, b01.y), b[0]);
+            b[1] = __ffma2_rn(f[1], f2(b01.z, b01.w), b[1]);
+            b[2] = __ffma2_rn(f[2], f2(b23.x, b23.y), b[2]);
+            b[3] = __ffma2_rn(f[3], f2(b23.z, b23.w), b[3]);
+          }
+          __syncwarp();
         });
-        // back substitution: x_c published by lane c, consumed by the rows above it
-        float2 accA = f2(0, 0), accB = f2(0, 0);
+        // Back substitution in place: x_c published by lane c, b -= U[., c] x_c in the rows above it
+        // (x_c = 0 for c >= D: identity rows with a zero right-hand side).
         static_for<0, kDM>([&](auto cc) {
           constexpr int c = kDM - 1 - decltype(cc)::value;
-          if (c < D) {
-            const float2 xa = __fmul2_rn(__fadd2_rn(bA, f2(-accA.x, -accA.y)), dA);
-            const float2 xb = __fmul2_rn(__fadd2_rn(bB, f2(-accB.x, -accB.y)), dB);
-            if (lane == c) xs[c] = make_float4(xa.x, xa.y, xb.x, xb.y);
-            __syncwarp();
-            const float4 xc = xs[c];
-            if (i < c) {
-              accA = __ffma2_rn(aA[c], f2(xc.x, xc.y), accA);
-              accB = __ffma2_rn(aB[c], f2(xc.z, xc.w), accB);
-            }
+          if (lane == c) {
+            float2 x[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) x[q] = __fmul2_rn(b[q], dinv[q]);
+            xs[c] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
+            xs[32 + c] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+          }
+          __syncwarp();
+          if (i < c) {
+            const float4 x01 = xs[c], x23 = xs[32 + c];
+            b[0] = __ffma2_rn(a[0][c], f2(-x01.x, -x01.y), b[0]);
+            b[1] = __ffma2_rn(a[1][c], f2(-x01.z, -x01.w), b[1]);
+            b[2] = __ffma2_rn(a[2][c], f2(-x23.x, -x23.y), b[2]);
+            b[3] = __ffma2_rn(a[3][c], f2(-x23.z, -x23.w), b[3]);
           }
         });
         __syncwarp();
-        if (i < D) {  // mc += g for frames 4 pp .. 4 pp + 3
-          float4* mp = reinterpret_cast<float4*>(mcs + i * 8 + 4 * pp);
-          const float4 g = xs[i];
-          float4 m = *mp;
-          m.x += g.x; m.y += g.y; m.z += g.z; m.w += g.w;
-          *mp = m;
+        if (i < D) {  // mc += g
+          float4* mp = reinterpret_cast<float4*>(mcs + i * 8);
+          const float4 g0 = xs[i], g1 = xs[32 + i];
+          float4 m0 = mp[0], m1 = mp[1];
+          m0.x += g0.x; m0.y += g0.y; m0.z += g0.z; m0.w += g0.w;
+          m1.x += g1.x; m1.y += g1.y; m1.z += g1.z; m1.w += g1.w;
+          mp[0] = m0;
+          mp[1] = m1;
         }
         __syncwarp();
       }
@@ -279,7 +320,7 @@ int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_para
                   const float* G, const float* Hm, const float* av, int device, cudaStream_t stream) {
   if (p->fft_length != 512 || p->cep_order > kDM - 1) return DSB200_E_UNSUPPORTED;
   const size_t smem = (static_cast<size_t>(kDM) * kKS + kKS * kJS + kKS * kPS + 32 +
-                       static_cast<size_t>(kMW) * (kDM * 8 + 4 * kJS * 2 + 128 + 128 + 8)) * sizeof(float);
+                       static_cast<size_t>(kMW) * kWarpFloats) * sizeof(float);
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
   MArgs A{};
   A.x = x;
