@@ -56,7 +56,8 @@ __global__ void __launch_bounds__(256) rowfft_bwd_kernel(BwdArgs<T> A) {
   C* tw = reinterpret_cast<C*>(smem_raw);  // full circle: n entries
   for (int i = threadIdx.x; i < n; i += blockDim.x) tw[i] = reinterpret_cast<const C*>(A.tw)[i];
   const int gw_len = (A.mode == BWD_STFT && A.gw != nullptr) ? A.L : 0;
-  const size_t per_warp = static_cast<size_t>(2 * n) * sizeof(C) + static_cast<size_t>(K + gw_len) * sizeof(T);
+  // K + gw_len rounded up to even: every warp's complex buffers stay aligned to sizeof(C)
+  const size_t per_warp = static_cast<size_t>(2 * n) * sizeof(C) + static_cast<size_t>((K + gw_len + 1) & ~1) * sizeof(T);
   unsigned char* wb = smem_raw + static_cast<size_t>(n) * sizeof(C) + warp * per_warp;
   C* buf0 = reinterpret_cast<C*>(wb);
   C* buf1 = buf0 + n;
@@ -242,7 +243,7 @@ int launch_bwd(BwdArgs<T>& A, int device, cudaStream_t stream) {
   const int K = A.Nc + 1;
   const int gw_len = (A.mode == BWD_STFT && A.gw != nullptr) ? A.L : 0;
   const size_t tw_bytes = static_cast<size_t>(A.n) * 2 * sizeof(T);
-  const size_t per_warp = static_cast<size_t>(2 * A.n) * 2 * sizeof(T) + static_cast<size_t>(K + gw_len) * sizeof(T);
+  const size_t per_warp = static_cast<size_t>(2 * A.n) * 2 * sizeof(T) + static_cast<size_t>((K + gw_len + 1) & ~1) * sizeof(T);
   const size_t cap = static_cast<size_t>(max_dynamic_smem(device));
   if (tw_bytes + per_warp > cap)
     return fail(DSB200_E_UNSUPPORTED, "fft_length=%d is too long for the backward kernel's shared memory", A.n);

@@ -147,7 +147,7 @@ struct Args {
   int quads_per_utt;    // ceil(n_frames / 4)
   int n_quads;          // batch * quads_per_utt
   int L, P, left, pad_mode;
-  int span;             // floats staged per quad: 3 P + 32 NJ, rounded up to 4
+  int span;             // floats staged per quad: 3 P + L, rounded up to 4
   int in_floats;        // floats per input buffer (>= span, multiple of 4)
   int bulk_in;          // waveform layout allows bulk copies (alignment)
   int bulk_out;         // output layout allows bulk stores
@@ -163,6 +163,13 @@ struct Args {
 };
 
 constexpr int kFmtMfcc = 5;  // internal: stage amplitudes, then filter bank + DCT + lifter on chip
+constexpr int kSegLen = 8;     // bins per filter-bank segment
+constexpr int kMaxSeg = 128;   // segments the fast filter-bank path can hold (40 mel filters at 512 bins: ~85)
+constexpr int kAmpPitch = 264; // float2 units per staged amplitude row: 257 bins + zero padding for segment tails
+
+__host__ __device__ constexpr int mf_table_floats(int C, int M) {
+  return (C * (M + 1) + (M + 1) + 2 * C + kMaxSeg + (C + 1) + kSegLen * kMaxSeg + 4 + 3) & ~3;
+}
 
 template <int FMT>
 __device__ __forceinline__ float fmt1(float s) {
@@ -208,11 +215,9 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw) + 2 * warp;
   float* win = reinterpret_cast<float*>(smem_raw + 16 * kWarps);
   float2* htw = reinterpret_cast<float2*>(win + 512);  // [128]
-  // MFCC tables (FMT == kFmtMfcc only): H [257 C] | W [C (M+1)] | lifter [M+1] | cb [C] | ce [C], padded to 16 B
-  float* mfH = reinterpret_cast<float*>(htw + 128);
-  const int mf_floats = (FMT == kFmtMfcc)
-                            ? ((257 * A.mf_C + A.mf_C * (A.mf_M + 1) + (A.mf_M + 1) + 2 * A.mf_C + 3) & ~3)
-                            : 0;
+  // MFCC tables (FMT == kFmtMfcc only), see mf_table_floats(): W^T | lifter | cb | ce | seg_k0 | chs | wT | info
+  float* mfW = reinterpret_cast<float*>(htw + 128);
+  const int mf_floats = (FMT == kFmtMfcc) ? mf_table_floats(A.mf_C, A.mf_M) : 0;
   unsigned char* wbase = smem_raw + 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) +
                          static_cast<size_t>(mf_floats) * 4 +
                          static_cast<size_t>(warp) * (2 * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
@@ -241,18 +246,47 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     const float2 v = tw[i];
     htw[i] = make_float2(0.5f * v.x, 0.5f * v.y);
   }
-  float* mfW = mfH + 257 * A.mf_C;
   float* mfL = mfW + A.mf_C * (A.mf_M + 1);
   int* mfcb = reinterpret_cast<int*>(mfL + (A.mf_M + 1));
   int* mfce = mfcb + A.mf_C;
+  int* seg_k0 = mfce + A.mf_C;            // [kMaxSeg] first bin of each segment (segments of a channel are adjacent)
+  int* chs = seg_k0 + kMaxSeg;            // [C + 1]   first segment of each channel
+  float* wT = reinterpret_cast<float*>(chs + A.mf_C + 1);   // [kSegLen][kMaxSeg] segment weights, zero padded
+  int* mf_info = reinterpret_cast<int*>(wT + kSegLen * kMaxSeg);   // [0] number of segments, 0 = dense fallback
   if (FMT == kFmtMfcc) {
     const int C = A.mf_C, M1 = A.mf_M + 1;
-    for (int i = tid; i < 257 * C; i += kThreads) mfH[i] = A.mf_H[i];
     for (int i = tid; i < C * M1; i += kThreads) mfW[i] = A.mf_W[(i / M1) * C + (i % M1)];
     for (int i = tid; i < M1; i += kThreads) mfL[i] = A.mf_lifter[i];
     for (int i = tid; i < C; i += kThreads) { mfcb[i] = A.mf_cb[i]; mfce[i] = A.mf_ce[i]; }
+    for (int i = tid; i < kSegLen * kMaxSeg; i += kThreads) wT[i] = 0.0f;
+    __syncthreads();
+    // Cut every filter's support [cb, ce) into segments of <= kSegLen bins: 32 lanes then work on 32 segments
+    // of all four frames at once instead of walking one whole filter per lane (the mel filters differ 10x in
+    // length).  Filter banks whose segments do not fit (dense / learnable) use the slow general loop.
+    if (tid == 0) {
+      int n = 0;
+      bool fits = true;
+      for (int c = 0; c < C; ++c) {
+        chs[c] = n;
+        for (int k = mfcb[c]; k < mfce[c]; k += kSegLen) {
+          if (n < kMaxSeg) seg_k0[n] = k;
+          else fits = false;
+          ++n;
+        }
+      }
+      chs[C] = n;
+      mf_info[0] = fits ? n : 0;
+    }
+    __syncthreads();
+    const int ns = mf_info[0];
+    for (int c = warp; c < C && ns > 0; c += kWarps)
+      for (int sg = chs[c]; sg < chs[c + 1]; ++sg) {
+        const int k = seg_k0[sg] + lane;
+        if (lane < kSegLen && k < mfce[c]) wT[lane * kMaxSeg + sg] = A.mf_H[k * C + c];
+      }
+    for (int sg = ns + tid; sg < kMaxSeg; sg += kThreads) seg_k0[sg] = 0;   // padding segments: zero weights
   }
-  __syncthreads();  // the only CTA-wide barrier: window table + mbarrier init
+  __syncthreads();  // last CTA-wide barrier (tables + mbarrier init); the main loop has none
 
   const int n_warps = gridDim.x * kWarps;
   int q = blockIdx.x * kWarps + warp;   // consecutive warps take consecutive quads (L2 locality)
@@ -357,7 +391,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     float* rowA;
     float* rowB;
     if (FMT == kFmtMfcc) {
-      rowA = ostage + h * (2 * 257);   // float2 amp2[257] of this half-warp's frame pair
+      rowA = ostage + h * (2 * kAmpPitch);   // float2 amp2[kAmpPitch] of this half-warp's frame pair
       rowB = rowA;
     } else if (staged) {
       rowA = ostage + (2 * h) * 257;
@@ -390,37 +424,69 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     };
 
     if (FMT == kFmtMfcc) {
-      // ---- MFCC epilogue: each half-warp owns a frame pair, all arithmetic packed (A, B) ---------
+      // ---- MFCC epilogue (mfcc.py:243-256 on chip).  Amplitudes of the quad are staged as two rows of
+      //      float2 = (frame A, frame B); everything below is packed arithmetic on all four frames ----------
       split(std::true_type{});
+      if (l < kAmpPitch - 257) reinterpret_cast<float2*>(rowA)[257 + l] = make_float2(0.0f, 0.0f);
       __syncwarp();
       const int C = A.mf_C, M = A.mf_M, M1 = M + 1;
-      const float2* amp2 = reinterpret_cast<const float2*>(ostage) + h * 257;
-      float2* mel2 = reinterpret_cast<float2*>(ostage + kOutFloats + 4) + h * C;   // [C] log filter-bank outputs
-      for (int c = l; c < C; c += 16) {              // triangular filters: only their non-zero rows
-        // four independent partial sums: the filters are short dependent chains otherwise
-        float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, s2 = s0, s3 = s0;
-        const int kb = mfcb[c], ke = mfce[c];
-        int k = kb;
-        for (; k + 3 < ke; k += 4) {
-          s0 = fma2s(amp2[k], mfH[k * C + c], s0);
-          s1 = fma2s(amp2[k + 1], mfH[(k + 1) * C + c], s1);
-          s2 = fma2s(amp2[k + 2], mfH[(k + 2) * C + c], s2);
-          s3 = fma2s(amp2[k + 3], mfH[(k + 3) * C + c], s3);
-        }
-        for (; k < ke; ++k) s0 = fma2s(amp2[k], mfH[k * C + c], s0);
-        float2 acc = add2(add2(s0, s1), add2(s2, s3));
-        acc.x = fmaxf(acc.x, A.mf_floor);
-        acc.y = fmaxf(acc.y, A.mf_floor);
+      const float2* amp0 = reinterpret_cast<const float2*>(ostage);
+      const float2* amp1 = amp0 + kAmpPitch;
+      float4* segsum = reinterpret_cast<float4*>(ostage + 4 * kAmpPitch);   // [kMaxSeg] partial sums, 4 frames
+      float4* mel4 = segsum + kMaxSeg;                                       // [C] log filter-bank outputs
+      auto fb_out = [&](int c, float2 u, float2 v) {                         // fbank.py:195-202
+        u.x = fmaxf(u.x, A.mf_floor); u.y = fmaxf(u.y, A.mf_floor);
+        v.x = fmaxf(v.x, A.mf_floor); v.y = fmaxf(v.y, A.mf_floor);
         if (A.mf_gamma == 0.0f) {
-          mel2[c] = make_float2(__logf(acc.x), __logf(acc.y));
+          mel4[c] = make_float4(__logf(u.x), __logf(u.y), __logf(v.x), __logf(v.y));
         } else {
-          const float ig = 1.0f / A.mf_gamma;
-          mel2[c] = make_float2((powf(acc.x, A.mf_gamma) - 1.0f) * ig, (powf(acc.y, A.mf_gamma) - 1.0f) * ig);
+          const float g = A.mf_gamma, ig = 1.0f / g;
+          mel4[c] = make_float4((powf(u.x, g) - 1.0f) * ig, (powf(u.y, g) - 1.0f) * ig,
+                                (powf(v.x, g) - 1.0f) * ig, (powf(v.y, g) - 1.0f) * ig);
+        }
+      };
+      const int ns = mf_info[0];
+      if (ns > 0) {
+        // lane = segment of <= 8 bins of one filter; 32 segments x 4 frames per round
+        for (int s0 = 0; s0 < ns; s0 += 32) {
+          const int sg = s0 + lane;
+          const float2* p0 = amp0 + seg_k0[sg];
+          const float2* p1 = amp1 + seg_k0[sg];
+          float2 u = make_float2(0.0f, 0.0f), v = u;
+#pragma unroll
+          for (int i = 0; i < kSegLen; ++i) {
+            const float w = wT[i * kMaxSeg + sg];
+            u = fma2s(p0[i], w, u);
+            v = fma2s(p1[i], w, v);
+          }
+          segsum[sg] = make_float4(u.x, u.y, v.x, v.y);
+        }
+        __syncwarp();
+        for (int c = lane; c < C; c += 32) {
+          float2 u = make_float2(0.0f, 0.0f), v = u;
+          for (int sg = chs[c]; sg < chs[c + 1]; ++sg) {
+            const float4 t = segsum[sg];
+            u = add2(u, make_float2(t.x, t.y));
+            v = add2(v, make_float2(t.z, t.w));
+          }
+          fb_out(c, u, v);
+        }
+      } else {
+        // general filter bank (dense / learnable supports): lane = channel, weights from global memory
+        for (int c = lane; c < C; c += 32) {
+          float2 u = make_float2(0.0f, 0.0f), v = u;
+          for (int k = mfcb[c]; k < mfce[c]; ++k) {
+            const float w = A.mf_H[k * C + c];
+            u = fma2s(amp0[k], w, u);
+            v = fma2s(amp1[k], w, v);
+          }
+          fb_out(c, u, v);
         }
       }
       float2 En = make_float2(0.0f, 0.0f);
       const bool want_e = (A.mf_format == DSB200_MFCC_YE) || (A.mf_format == DSB200_MFCC_YCE);
       if (want_e) {                                  // E = log((2 sum_{0<k<256} x_k + x_0 + x_256) / 512)
+        const float2* amp2 = amp0 + h * kAmpPitch;
         float2 e = make_float2(0.0f, 0.0f);
         for (int k = l; k < 257; k += 16) {
           const float2 v = amp2[k];
@@ -435,24 +501,44 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         En = make_float2(__logf(e.x * (1.0f / 512.0f)), __logf(e.y * (1.0f / 512.0f)));
       }
       __syncwarp();
+      // DCT-II columns 0..M (lane l), the channel range split between the half-warps, then lifter and
+      // y | yE | yc | ycE packing; half-warp h writes frames 2h, 2h + 1.
       float* outA = A.y + (row0 + 2 * h) * A.mf_D;
       float* outB = outA + A.mf_D;
-      for (int m = l; m < M1; m += 16) {             // DCT-II columns 0..M, lifter, pack y | yE | yc | ycE
-        float2 s0 = make_float2(0.0f, 0.0f), s1 = s0, s2 = s0, s3 = s0;
-        int c = 0;
-        for (; c + 3 < C; c += 4) {
-          s0 = fma2s(mel2[c], mfW[c * M1 + m], s0);
-          s1 = fma2s(mel2[c + 1], mfW[(c + 1) * M1 + m], s1);
-          s2 = fma2s(mel2[c + 2], mfW[(c + 2) * M1 + m], s2);
-          s3 = fma2s(mel2[c + 3], mfW[(c + 3) * M1 + m], s3);
+      const int ch = (C + 1) >> 1, c0 = h * ch, c1 = (c0 + ch < C) ? c0 + ch : C;
+      for (int m0 = 0; m0 < M1; m0 += 16) {
+        const int m = m0 + l;
+        float2 u0 = make_float2(0.0f, 0.0f), v0 = u0, u1 = u0, v1 = u0;
+        if (m < M1) {
+          int c = c0;
+          for (; c + 1 < c1; c += 2) {
+            const float wa = mfW[c * M1 + m], wb = mfW[(c + 1) * M1 + m];
+            const float4 ta = mel4[c], tb = mel4[c + 1];
+            u0 = fma2s(make_float2(ta.x, ta.y), wa, u0);
+            v0 = fma2s(make_float2(ta.z, ta.w), wa, v0);
+            u1 = fma2s(make_float2(tb.x, tb.y), wb, u1);
+            v1 = fma2s(make_float2(tb.z, tb.w), wb, v1);
+          }
+          if (c < c1) {
+            const float wa = mfW[c * M1 + m];
+            const float4 ta = mel4[c];
+            u0 = fma2s(make_float2(ta.x, ta.y), wa, u0);
+            v0 = fma2s(make_float2(ta.z, ta.w), wa, v0);
+          }
         }
-        for (; c < C; ++c) s0 = fma2s(mel2[c], mfW[c * M1 + m], s0);
-        float2 acc = mul2s(add2(add2(s0, s1), add2(s2, s3)), mfL[m]);
-        int pos = m - 1;
-        if (m == 0) pos = (A.mf_format == DSB200_MFCC_YC || A.mf_format == DSB200_MFCC_YCE) ? M : -1;
-        if (pos >= 0) {
-          if (vA) outA[pos] = acc.x;
-          if (vB) outB[pos] = acc.y;
+        float2 u = add2(u0, u1), v = add2(v0, v1);
+        u.x += __shfl_xor_sync(0xffffffffu, u.x, 16);
+        u.y += __shfl_xor_sync(0xffffffffu, u.y, 16);
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, 16);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, 16);
+        if (m < M1) {
+          const float2 acc = mul2s(h ? v : u, mfL[m]);
+          int pos = m - 1;
+          if (m == 0) pos = (A.mf_format == DSB200_MFCC_YC || A.mf_format == DSB200_MFCC_YCE) ? M : -1;
+          if (pos >= 0) {
+            if (vA) outA[pos] = acc.x;
+            if (vB) outB[pos] = acc.y;
+          }
         }
       }
       if (l == 0 && want_e) {
@@ -531,7 +617,9 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
   A.P = f.frame_period;
   A.left = left;
   A.pad_mode = f.pad_mode;
-  A.span = (3 * f.frame_period + 32 * NJ + 3) & ~3;
+  // The quad's samples: 3 P + L.  The column loads below run up to 32 NJ - L floats past that into the next
+  // shared-memory region; those lanes are masked (p0 >= L), so the span is not padded to 32 NJ.
+  A.span = (3 * f.frame_period + f.frame_length + 3) & ~3;
   A.in_floats = A.span;
   // bulk copies need 16-byte aligned global addresses and sizes: every span start (4 g P - left) and
   // every utterance start (b T) must be a multiple of 4 floats.
@@ -578,12 +666,16 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   Args A{};
   int NJ = 16;
   if (int rc = setup_args(A, x, window, y, batch, T_len, sp, device, stream, &NJ)) return rc;
-  const int mf_floats = (257 * C + C * (M + 1) + (M + 1) + 2 * C + 3) & ~3;
-  constexpr int kWarps = kWarpsMfcc;
+  const int mf_floats = mf_table_floats(C, M);
+  // segment sums [kMaxSeg] and mel rows [C] (float4 each) live behind the staged amplitude rows inside the
+  // per-warp exchange region
+  if ((4 * kAmpPitch + 4 * kMaxSeg + 4 * C) * 4 > kXchBytesPerWarp) return DSB200_E_UNSUPPORTED;
+  const size_t smem_max = static_cast<size_t>(max_dynamic_smem(device));
+  // 16 warps (128 registers) when the tables fit next to 16 warp pipelines, else 12
+  const bool w16 = NJ == 13 && smem_bytes(A, mf_floats, kWarpsSpectrum) <= smem_max;
+  const int kWarps = w16 ? kWarpsSpectrum : kWarpsMfcc;
   const size_t smem = smem_bytes(A, mf_floats, kWarps);
-  // the mel rows [4][C] live behind the staged amplitude rows inside the exchange region
-  if (smem > static_cast<size_t>(max_dynamic_smem(device)) || (kOutFloats + 4 + 4 * C) * 4 > kXchBytesPerWarp)
-    return DSB200_E_UNSUPPORTED;
+  if (smem > smem_max) return DSB200_E_UNSUPPORTED;
   A.mf_H = H;
   A.mf_cb = cb;
   A.mf_ce = ce;
@@ -596,15 +688,16 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   A.mf_floor = static_cast<float>(mp->fbank.floor);
   A.mf_gamma = static_cast<float>(mp->fbank.gamma);
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));
-  if (NJ == 13) {
-    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<13, false, kFmtMfcc, kWarps>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    stft512_kernel<13, false, kFmtMfcc, kWarps><<<blocks, kWarps * 32, smem, stream>>>(A);
-  } else {
-    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<16, true, kFmtMfcc, kWarps>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    stft512_kernel<16, true, kFmtMfcc, kWarps><<<blocks, kWarps * 32, smem, stream>>>(A);
-  }
+  auto launch = [&](auto kern) -> int {
+    DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<blocks, kWarps * 32, smem, stream>>>(A);
+    return DSB200_OK;
+  };
+  int rc;
+  if (w16) rc = launch(stft512_kernel<13, false, kFmtMfcc, kWarpsSpectrum>);
+  else if (NJ == 13) rc = launch(stft512_kernel<13, false, kFmtMfcc, kWarpsMfcc>);
+  else rc = launch(stft512_kernel<16, true, kFmtMfcc, kWarpsMfcc>);
+  if (rc != DSB200_OK) return rc;
   return after_launch("stft512_kernel<mfcc>");
 }
 

@@ -429,6 +429,13 @@ class HostStftPipeline:
 # SURVEY.md section 8(f) rank 1.  The spectral half of the path (frame, window, fftr, spec (numerator),
 # stft, freqt, dct) is differentiable through native adjoint kernels; the LPC / cepstral solvers are
 # forward-only and raise instead of silently dropping gradients (modules call _no_grad_check).
+def _prep_grad(g: Tensor, dtype: torch.dtype) -> Tensor:
+    """Output gradient as a contiguous real tensor; complex gradients become interleaved (re, im) pairs."""
+    if g.is_complex():
+        g = torch.view_as_real(g.resolve_conj().contiguous())
+    return _prep(g, dtype)
+
+
 def _like_input(g: Tensor, x: Tensor) -> Tensor:
     return g.reshape(x.shape).to(x.dtype) if x.dtype.is_floating_point else None
 
@@ -438,7 +445,7 @@ def stft_backward(x: Tensor, window: Tensor, gy: Tensor, frame_period: int, fft_
                   zmean: bool, pad_mode: int, eps: float, relative_floor: float, out_format: int,
                   need_gw: bool) -> tuple[Tensor, Tensor]:
     dt = _native_dtype(x, window)
-    xc, wc, gc = _prep(x, dt), _prep(window, dt), _prep(gy, dt)
+    xc, wc, gc = _prep(x, dt), _prep(window, dt), _prep_grad(gy, dt)
     T = xc.shape[-1]
     B = xc.numel() // max(T, 1)
     gx = torch.empty_like(xc)
@@ -512,7 +519,7 @@ torch.library.register_autograd(f"{_NS}::frame", _frame_bwd, setup_context=_fram
 @torch.library.custom_op(f"{_NS}::rfft_backward", mutates_args=(), device_types="cuda")
 def rfft_backward(x: Tensor, gy: Tensor, fft_length: int, out_format: int) -> Tensor:
     dt = _native_dtype(x)
-    xc, gc = _prep(x, dt), _prep(gy, dt)
+    xc, gc = _prep(x, dt), _prep_grad(gy, dt)
     Lin = xc.shape[-1]
     rows = xc.numel() // max(Lin, 1)
     gx = torch.empty_like(xc)
@@ -543,7 +550,7 @@ torch.library.register_autograd(f"{_NS}::rfft", _rfft_bwd, setup_context=_rfft_s
 @torch.library.custom_op(f"{_NS}::spec_backward", mutates_args=(), device_types="cuda")
 def spec_backward(b: Tensor, gy: Tensor, fft_length: int, eps: float, relative_floor: float, out_format: int) -> Tensor:
     dt = _native_dtype(b)
-    bc, gc = _prep(b, dt), _prep(gy, dt)
+    bc, gc = _prep(b, dt), _prep_grad(gy, dt)
     Lb = bc.shape[-1]
     rows = bc.numel() // max(Lb, 1)
     gb = torch.empty_like(bc)

@@ -295,6 +295,9 @@ def test_lpc_wave_full_size_sampled():
     ((2, 5000), dict(out_format="yE", mode="reflect")),
     ((2, 4000), dict(out_format="yc", n_channel=24, mfcc_order=12, gamma=-0.5, floor=1e-3)),
     ((1, 333), dict(out_format="ycE", frame_length=320, frame_period=160, scale="mel")),
+    ((2, 3000), dict(out_format="yE", n_channel=120, mfcc_order=30)),  # > 128 filter segments: general in-kernel loop
+    ((2, 3000), dict(out_format="y", n_channel=8, mfcc_order=7)),      # few, long filters: many segments per channel
+    ((1, 2400), dict(out_format="yc", n_channel=20, mfcc_order=19, scale="bark")),   # two DCT rounds (M + 1 > 16)
 ])
 def test_mfcc_wave_fused_kernel_against_oracle(shape, kw):
     """waveform -> STFT power -> fbank -> DCT -> lifter in ONE kernel, against the oracle cascade."""
