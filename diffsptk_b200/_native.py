@@ -68,6 +68,12 @@ _TYPED = {
     "dsb200_rfft_backward": [_P, _P, _P, _I64, _I32, _I32, _I32, _INT, _P],
     "dsb200_spec_backward": [_P, _I32, _P, _P, _I64, C.POINTER(SpecParams), _INT, _P],
     "dsb200_frame_backward": [_P, _P, _I64, _I64, C.POINTER(FrameParams), _INT, _P],
+    "dsb200_ifftr": [_P, _P, _I64, _I32, _I32, _INT, _P],
+    "dsb200_unframe": [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _INT, _P],
+    "dsb200_istft": [_P, _P, _P, _I64, _I64, _I64, _I32, _I32, _I32, _I32, _INT, _P],
+    "dsb200_fbank_backward": [_P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(FbankParams), _INT, _P],
+    "dsb200_acorr_backward": [_P, _P, _P, _I64, _I32, _I32, _I32, _INT, _P],
+    "dsb200_levdur_backward": [_P, _P, _P, _I64, _I32, _D, _INT, _P],
     "dsb200_mfcc_wave": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, C.POINTER(StftParams),
                          C.POINTER(MfccParams), _INT, _P],
 }

@@ -17,6 +17,9 @@ __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -44,6 +47,10 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // one bulk copy completing on `bar` and the out-of-range part is zero-filled (constant padding); other
 // pad modes take the guarded-load path on the (rare) spans that touch an utterance end.
 // Returns true when a bulk copy is in flight (the caller must mbar_wait before reading).
+// With ALWAYS_ARRIVE the guarded path completes the barrier phase too (plain arrive by lane 0), so that the
+// caller can wait unconditionally and derive the phase parity from its iteration count instead of carrying
+// per-buffer phase bits and "was it a bulk copy" flags through its loop.
+template <bool ALWAYS_ARRIVE = false>
 __device__ __forceinline__ bool stage_span(const float* xb, int T, int s0, int span, int pad_mode, bool bulk_ok,
                                            float* dst, uint64_t* bar, int lane) {
   const int lo = s0 < 0 ? 0 : s0;
@@ -65,6 +72,7 @@ __device__ __forceinline__ bool stage_span(const float* xb, int T, int s0, int s
     const int64_t p = pad_index(static_cast<int64_t>(s0) + i, T, pad_mode);
     dst[i] = (p < 0 || p >= T) ? 0.0f : xb[p];
   }
+  if (ALWAYS_ARRIVE && lane == 0) mbar_arrive(bar);
   return false;
 }
 

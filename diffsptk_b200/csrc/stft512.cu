@@ -184,6 +184,13 @@ __device__ __forceinline__ float fmt1(float s) {
   return s;
 }
 
+// ln(x) for normal positive x: one MUFU.LG2 (no denormal pre-scaling, unlike __logf without -ftz).
+__device__ __forceinline__ float fast_ln(float x) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.6931471805599453f;
+}
+
 // One bin of both frames of the pair: to the shared staging rows (real formats, STAGED) or to HBM.
 template <int FMT, bool STAGED>
 __device__ __forceinline__ void put_bin(float* rowA, float* rowB, bool vB, int k, float2 re, float2 im, float eps) {
@@ -294,14 +301,14 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   int g = q - b * A.quads_per_utt;
   const int db = n_warps / A.quads_per_utt, dg = n_warps - db * A.quads_per_utt;
 
-  auto stage = [&](int bq, int gq, float* dst, uint64_t* bar) -> bool {
-    return stage_span(A.x + static_cast<int64_t>(bq) * A.T, A.T, 4 * gq * A.P - A.left, A.span, A.pad_mode,
-                      A.bulk_in != 0, dst, bar, lane);
+  auto stage = [&](int bq, int gq, float* dst, uint64_t* bar) {
+    stage_span<true>(A.x + static_cast<int64_t>(bq) * A.T, A.T, 4 * gq * A.P - A.left, A.span, A.pad_mode,
+                     A.bulk_in != 0, dst, bar, lane);
   };
 
-  uint32_t phase0 = 0u, phase1 = 0u;
-  bool cur_bulk = false;
-  if (q < A.n_quads) cur_bulk = stage(b, g, in0, &mbar[0]);
+  // Every staging completes one phase of its buffer's barrier (bulk copy or plain arrive), so the parity of
+  // buffer `it & 1` at iteration `it` is (it >> 1) & 1: no phase bits are carried through the loop.
+  if (q < A.n_quads) stage(b, g, in0, &mbar[0]);
   bool store_pending = false;
 
   for (int it = 0; q < A.n_quads; ++it) {
@@ -310,12 +317,8 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     const int qn = q + n_warps;
     int bn = b + db, gn = g + dg;
     if (gn >= A.quads_per_utt) { gn -= A.quads_per_utt; ++bn; }
-    bool next_bulk = false;
-    if (qn < A.n_quads) next_bulk = stage(bn, gn, in0 + (buf ^ 1) * A.in_floats, &mbar[buf ^ 1]);
-    if (cur_bulk) {
-      if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1u; }
-      else          { mbar_wait(&mbar[1], phase1); phase1 ^= 1u; }
-    }
+    if (qn < A.n_quads) stage(bn, gn, in0 + (buf ^ 1) * A.in_floats, &mbar[buf ^ 1]);
+    mbar_wait(&mbar[buf], static_cast<uint32_t>(it >> 1) & 1u);
     __syncwarp();  // zero-fill / guarded stores of the other lanes
     const float* span = in0 + buf * A.in_floats;
 
@@ -429,7 +432,20 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       split(std::true_type{});
       if (l < kAmpPitch - 257) reinterpret_cast<float2*>(rowA)[257 + l] = make_float2(0.0f, 0.0f);
       __syncwarp();
-      const int C = A.mf_C, M = A.mf_M, M1 = M + 1;
+      // Table pointers are re-derived here from an opaque offset: hoisted out of the quad loop they would pin
+      // ~12 registers across the register-tight FFT (128 per thread at 16 warps) and spill its loop state.
+      uint32_t tbl_off = 16u * kWarps + 512u * sizeof(float) + 128u * sizeof(float2);
+      int C = A.mf_C, M = A.mf_M;
+      asm volatile("" : "+r"(tbl_off), "+r"(C), "+r"(M));
+      const int M1 = M + 1;
+      const float* mfW = reinterpret_cast<const float*>(smem_raw + tbl_off);
+      const float* mfL = mfW + C * M1;
+      const int* mfcb = reinterpret_cast<const int*>(mfL + M1);
+      const int* mfce = mfcb + C;
+      const int* seg_k0 = mfce + C;
+      const int* chs = seg_k0 + kMaxSeg;
+      const float* wT = reinterpret_cast<const float*>(chs + C + 1);
+      const int* mf_info = reinterpret_cast<const int*>(wT + kSegLen * kMaxSeg);
       const float2* amp0 = reinterpret_cast<const float2*>(ostage);
       const float2* amp1 = amp0 + kAmpPitch;
       float4* segsum = reinterpret_cast<float4*>(ostage + 4 * kAmpPitch);   // [kMaxSeg] partial sums, 4 frames
@@ -438,7 +454,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         u.x = fmaxf(u.x, A.mf_floor); u.y = fmaxf(u.y, A.mf_floor);
         v.x = fmaxf(v.x, A.mf_floor); v.y = fmaxf(v.y, A.mf_floor);
         if (A.mf_gamma == 0.0f) {
-          mel4[c] = make_float4(__logf(u.x), __logf(u.y), __logf(v.x), __logf(v.y));
+          mel4[c] = make_float4(fast_ln(u.x), fast_ln(u.y), fast_ln(v.x), fast_ln(v.y));   // inputs >= floor > 0
         } else {
           const float g = A.mf_gamma, ig = 1.0f / g;
           mel4[c] = make_float4((powf(u.x, g) - 1.0f) * ig, (powf(u.y, g) - 1.0f) * ig,
@@ -510,18 +526,21 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         const int m = m0 + l;
         float2 u0 = make_float2(0.0f, 0.0f), v0 = u0, u1 = u0, v1 = u0;
         if (m < M1) {
-          int c = c0;
-          for (; c + 1 < c1; c += 2) {
-            const float wa = mfW[c * M1 + m], wb = mfW[(c + 1) * M1 + m];
-            const float4 ta = mel4[c], tb = mel4[c + 1];
+          const float* wp = mfW + c0 * M1 + m;
+          const float4* mp = mel4 + c0;
+          int left = c1 - c0;
+#pragma unroll 2
+          for (; left >= 2; left -= 2, wp += 2 * M1, mp += 2) {
+            const float wa = wp[0], wb = wp[M1];
+            const float4 ta = mp[0], tb = mp[1];
             u0 = fma2s(make_float2(ta.x, ta.y), wa, u0);
             v0 = fma2s(make_float2(ta.z, ta.w), wa, v0);
             u1 = fma2s(make_float2(tb.x, tb.y), wb, u1);
             v1 = fma2s(make_float2(tb.z, tb.w), wb, v1);
           }
-          if (c < c1) {
-            const float wa = mfW[c * M1 + m];
-            const float4 ta = mel4[c];
+          if (left > 0) {
+            const float wa = wp[0];
+            const float4 ta = mp[0];
             u0 = fma2s(make_float2(ta.x, ta.y), wa, u0);
             v0 = fma2s(make_float2(ta.z, ta.w), wa, v0);
           }
@@ -558,7 +577,6 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     }
 
     q = qn; b = bn; g = gn;
-    cur_bulk = next_bulk;
   }
   if (store_pending && lane == 0) bulk_wait_read();
 }
@@ -672,7 +690,11 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   if ((4 * kAmpPitch + 4 * kMaxSeg + 4 * C) * 4 > kXchBytesPerWarp) return DSB200_E_UNSUPPORTED;
   const size_t smem_max = static_cast<size_t>(max_dynamic_smem(device));
   // 16 warps (128 registers) when the tables fit next to 16 warp pipelines, else 12
-  const bool w16 = NJ == 13 && smem_bytes(A, mf_floats, kWarpsSpectrum) <= smem_max;
+  static const int warps_knob = [] {   // DSB200_MFCC_WARPS=12|16 (tuning knob, read once)
+    const char* e = getenv("DSB200_MFCC_WARPS");
+    return e != nullptr ? atoi(e) : 0;
+  }();
+  const bool w16 = NJ == 13 && warps_knob != 12 && smem_bytes(A, mf_floats, kWarpsSpectrum) <= smem_max;
   const int kWarps = w16 ? kWarpsSpectrum : kWarpsMfcc;
   const size_t smem = smem_bytes(A, mf_floats, kWarps);
   if (smem > smem_max) return DSB200_E_UNSUPPORTED;

@@ -28,7 +28,6 @@ def lpc_from_waveform(x: Tensor, *, frame_length: int = 400, frame_period: int =
     dt = x.dtype if x.dtype.is_floating_point else None
     if window_table is None:
         window_table = tables.make_window(frame_length, window, norm, symmetric, device=x.device, dtype=dt)
-    ops._no_grad_check(x, window_table)
     return ops.lpc_wave(x, window_table, frame_period, center, zmean, pad_mode_id(mode), lpc_order,
                         float(default_eps(eps, dt)))
 
@@ -55,7 +54,7 @@ def mfcc_from_waveform(x: Tensor, *, frame_length: int = 400, frame_period: int 
     if liftering_vector is None:
         liftering_vector = tables.make_lifter(mfcc_order, lifter, dev, dt)
     fmt = mfcc_format_id(out_format)
-    ops._no_grad_check(x, window_table, H)
+    ops._no_grad_check(H)  # gradients flow to the waveform and the window, not to a learnable filter bank
     cb, ce = support_of(H, H_begin, H_end)
     try:
         return ops.mfcc_wave(x, window_table, H, cb, ce, W, liftering_vector, frame_period, fft_length, center,

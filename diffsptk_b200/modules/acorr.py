@@ -50,5 +50,4 @@ class Autocorrelation(BaseFunctionalModule):
 
     @staticmethod
     def _forward(x: torch.Tensor, *, acr_order: int, out_format: int) -> torch.Tensor:
-        ops._no_grad_check(x)
         return ops.acorr(x, acr_order, out_format)

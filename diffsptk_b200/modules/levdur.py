@@ -60,5 +60,4 @@ class LevinsonDurbin(BaseFunctionalModule):
 
     @staticmethod
     def _forward(r: torch.Tensor, *, eps: float, eye: torch.Tensor) -> torch.Tensor:
-        ops._no_grad_check(r)
         return ops.levdur(r, eps)

@@ -53,5 +53,4 @@ class LinearPredictiveCodingAnalysis(BaseFunctionalModule):
                  levdur=None) -> torch.Tensor:
         if x.size(-1) != frame_length:
             raise ValueError(f"Unexpected length of waveform (input {x.size(-1)} vs target {frame_length}).")
-        ops._no_grad_check(x)
         return ops.lpc(x, lpc_order, eps)

@@ -59,9 +59,10 @@ def _dev(t: Tensor) -> int:
 def _no_grad_check(*ts):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
         raise NotImplementedError(
-            "this diffsptk_b200 op is forward-only (the spectral ops frame / window / fftr / spec / stft / "
-            "freqt / dct are differentiable; the LPC and cepstral solvers are not yet): wrap the call in "
-            "torch.no_grad() or detach() the inputs."
+            "this diffsptk_b200 op is forward-only for that input (differentiable: frame / window / fftr / spec / "
+            "stft / freqt / dct / acorr / levdur / lpc / fbank / mfcc with respect to their signal inputs; not "
+            "mcep, and not learnable filter-bank or DFT-basis tables): wrap the call in torch.no_grad() or "
+            "detach() the inputs."
         )
 
 
@@ -426,9 +427,9 @@ class HostStftPipeline:
 
 
 # ------------------------------------------------------------------------------------- autograd
-# SURVEY.md section 8(f) rank 1.  The spectral half of the path (frame, window, fftr, spec (numerator),
-# stft, freqt, dct) is differentiable through native adjoint kernels; the LPC / cepstral solvers are
-# forward-only and raise instead of silently dropping gradients (modules call _no_grad_check).
+# SURVEY.md section 8(f) rank 1.  frame, window, fftr, spec (numerator), stft, freqt, dct, acorr, levdur, lpc,
+# fbank and mfcc (and the fused waveform pipelines) are differentiable through native adjoint kernels;
+# mcep (the Newton solver) is forward-only and raises instead of silently dropping gradients.
 def _prep_grad(g: Tensor, dtype: torch.dtype) -> Tensor:
     """Output gradient as a contiguous real tensor; complex gradients become interleaved (re, im) pairs."""
     if g.is_complex():
@@ -615,3 +616,211 @@ def _rowmat_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{_NS}::rowmat", _rowmat_bwd, setup_context=_rowmat_setup)
+
+
+# ---- filter bank / MFCC (gradients with respect to the spectrum; the filter-bank matrix itself is not trained) ----
+@torch.library.custom_op(f"{_NS}::fbank_backward", mutates_args=(), device_types="cuda")
+def fbank_backward(x: Tensor, H: Tensor, col_begin: Optional[Tensor], col_end: Optional[Tensor], gy: Tensor,
+                   gE: Optional[Tensor], floor: float, gamma: float, use_power: bool) -> Tensor:
+    dt = _native_dtype(x, H)
+    xc, Hc, gc = _prep(x, dt), _prep(H, dt), _prep(gy, dt)
+    gEc = _prep(gE, dt) if gE is not None and gE.numel() else None
+    K, Cn = Hc.shape
+    rows = xc.numel() // max(K, 1)
+    gx = torch.empty_like(xc)
+    p = N.FbankParams(2 * (K - 1), Cn, int(use_power), int(gEc is not None), float(floor), float(gamma))
+    N.check(N.typed("dsb200_fbank_backward", dt == torch.float64)(
+        _ptr(xc), _ptr(Hc), _ptr(col_begin), _ptr(col_end), _ptr(gc), _ptr(gEc), _ptr(gx), rows, C.byref(p),
+        _dev(x), _stream(x)))
+    return gx
+
+
+@fbank_backward.register_fake
+def _(x, H, col_begin, col_end, gy, gE, floor, gamma, use_power):
+    return x.new_empty(x.shape, dtype=_native_dtype(x, H))
+
+
+def _fbank_setup(ctx, inputs, output):
+    x, H, cb, ce, floor, gamma, use_power, want_energy = inputs
+    if H.requires_grad:
+        raise NotImplementedError("gradients with respect to a learnable filter-bank matrix are not implemented")
+    ctx.save_for_backward(x, H, cb, ce)
+    ctx.rest = (floor, gamma, use_power)
+    ctx.want_energy = want_energy
+
+
+def _fbank_bwd(ctx, gy, gE):
+    x, H, cb, ce = ctx.saved_tensors
+    gx = fbank_backward(x, H, cb, ce, gy, gE if ctx.want_energy else None, *ctx.rest)
+    return (_like_input(gx, x),) + (None,) * 7
+
+
+torch.library.register_autograd(f"{_NS}::fbank", _fbank_bwd, setup_context=_fbank_setup)
+
+
+def _mfcc_grad_to_spectrum(g: Tensor, P: Tensor, H, cb, ce, W, lifter, floor, gamma, out_format) -> Tensor:
+    """Adjoint of lifter -> DCT -> log filter bank (mfcc.py:243-256): gradient of the packed output -> spectrum."""
+    M = lifter.shape[-1] - 1
+    g = g.to(lifter.dtype)
+    gcep = g.new_zeros((*g.shape[:-1], M + 1))
+    gcep[..., 1:] = g[..., :M]
+    if out_format in (2, 3):        # yc | ycE carry c0 right after the M cepstral coefficients
+        gcep[..., 0] = g[..., M]
+    gE = None
+    if out_format == 1:
+        gE = g[..., M].contiguous()
+    elif out_format == 3:
+        gE = g[..., M + 1].contiguous()
+    gmel = rowmat(gcep * lifter, W[:, : M + 1].t().contiguous())
+    return fbank_backward(P, H, cb, ce, gmel, gE, floor, gamma, False)
+
+
+def _mfcc_setup(ctx, inputs, output):
+    x, H, cb, ce, W, lifter, floor, gamma, out_format = inputs
+    if H.requires_grad:
+        raise NotImplementedError("gradients with respect to a learnable filter-bank matrix are not implemented")
+    ctx.save_for_backward(x, H, cb, ce, W, lifter)
+    ctx.rest = (floor, gamma, out_format)
+
+
+def _mfcc_bwd(ctx, g):
+    x, H, cb, ce, W, lifter = ctx.saved_tensors
+    gx = _mfcc_grad_to_spectrum(g, x, H, cb, ce, W, lifter, *ctx.rest)
+    return (_like_input(gx, x),) + (None,) * 8
+
+
+torch.library.register_autograd(f"{_NS}::mfcc", _mfcc_bwd, setup_context=_mfcc_setup)
+
+
+def _mfcc_wave_setup(ctx, inputs, output):
+    (x, window, H, cb, ce, W, lifter, frame_period, fft_length, center, zmean, pad_mode, eps, floor, gamma,
+     out_format) = inputs
+    if H.requires_grad:
+        raise NotImplementedError("gradients with respect to a learnable filter-bank matrix are not implemented")
+    ctx.save_for_backward(x, window, H, cb, ce, W, lifter)
+    ctx.stft_args = (frame_period, fft_length, center, zmean, pad_mode, eps, -1.0, 3)
+    ctx.rest = (floor, gamma, out_format)
+
+
+def _mfcc_wave_bwd(ctx, g):
+    # The fused forward keeps nothing: recompute the power spectrum, pull the gradient back through the
+    # filter bank, then through the STFT (all native kernels).
+    x, window, H, cb, ce, W, lifter = ctx.saved_tensors
+    with torch.no_grad():
+        P = stft(x, window, *ctx.stft_args)
+        gP = _mfcc_grad_to_spectrum(g, P, H, cb, ce, W, lifter, *ctx.rest)
+        need_gw = ctx.needs_input_grad[1]
+        gx, gw = stft_backward(x, window, gP, *ctx.stft_args, need_gw)
+    return (_like_input(gx, x), gw.to(window.dtype) if need_gw else None) + (None,) * 14
+
+
+torch.library.register_autograd(f"{_NS}::mfcc_wave", _mfcc_wave_bwd, setup_context=_mfcc_wave_setup)
+
+
+# ---- autocorrelation / Levinson-Durbin / LPC ----------------------------------------------------------------
+@torch.library.custom_op(f"{_NS}::acorr_backward", mutates_args=(), device_types="cuda")
+def acorr_backward(x: Tensor, gy: Tensor, acr_order: int, out_format: int) -> Tensor:
+    dt = _native_dtype(x)
+    xc, gc = _prep(x, dt), _prep(gy, dt)
+    L = xc.shape[-1]
+    rows = xc.numel() // max(L, 1)
+    gx = torch.empty_like(xc)
+    N.check(N.typed("dsb200_acorr_backward", dt == torch.float64)(_ptr(xc), _ptr(gc), _ptr(gx), rows, L, acr_order,
+                                                                  out_format, _dev(x), _stream(x)))
+    return gx
+
+
+@acorr_backward.register_fake
+def _(x, gy, acr_order, out_format):
+    return x.new_empty(x.shape, dtype=_native_dtype(x))
+
+
+@torch.library.custom_op(f"{_NS}::levdur_backward", mutates_args=(), device_types="cuda")
+def levdur_backward(r: Tensor, ga: Tensor, eps: float) -> Tensor:
+    dt = _native_dtype(r)
+    rc, gc = _prep(r, dt), _prep(ga, dt)
+    D = rc.shape[-1]
+    rows = rc.numel() // max(D, 1)
+    gr = torch.empty_like(rc)
+    N.check(N.typed("dsb200_levdur_backward", dt == torch.float64)(_ptr(rc), _ptr(gc), _ptr(gr), rows, D - 1, eps,
+                                                                   _dev(r), _stream(r)))
+    return gr
+
+
+@levdur_backward.register_fake
+def _(r, ga, eps):
+    return r.new_empty(r.shape, dtype=_native_dtype(r))
+
+
+def _acorr_setup(ctx, inputs, output):
+    x, acr_order, out_format = inputs
+    ctx.save_for_backward(x)
+    ctx.args = (acr_order, out_format)
+
+
+def _acorr_bwd(ctx, g):
+    (x,) = ctx.saved_tensors
+    return _like_input(acorr_backward(x, g, *ctx.args), x), None, None
+
+
+torch.library.register_autograd(f"{_NS}::acorr", _acorr_bwd, setup_context=_acorr_setup)
+
+
+def _levdur_setup(ctx, inputs, output):
+    r, eps = inputs
+    ctx.save_for_backward(r)
+    ctx.eps = eps
+
+
+def _levdur_bwd(ctx, g):
+    (r,) = ctx.saved_tensors
+    return _like_input(levdur_backward(r, g, ctx.eps), r), None
+
+
+torch.library.register_autograd(f"{_NS}::levdur", _levdur_bwd, setup_context=_levdur_setup)
+
+
+def _lpc_setup(ctx, inputs, output):
+    x, lpc_order, eps = inputs
+    ctx.save_for_backward(x)
+    ctx.args = (lpc_order, eps)
+
+
+def _lpc_bwd(ctx, g):
+    (x,) = ctx.saved_tensors
+    M, eps = ctx.args
+    with torch.no_grad():
+        r = acorr(x, M, 0)
+        gx = acorr_backward(x, levdur_backward(r, g, eps), M, 0)
+    return _like_input(gx, x), None, None
+
+
+torch.library.register_autograd(f"{_NS}::lpc", _lpc_bwd, setup_context=_lpc_setup)
+
+
+def _lpc_wave_setup(ctx, inputs, output):
+    x, window_t, frame_period, center, zmean, pad_mode, lpc_order, eps = inputs
+    ctx.save_for_backward(x, window_t)
+    ctx.frame_args = (frame_period, center, zmean, pad_mode)
+    ctx.args = (lpc_order, eps)
+
+
+def _lpc_wave_bwd(ctx, g):
+    # Recompute the windowed frames (the fused forward never materialises them), then chain the adjoints.
+    x, w = ctx.saved_tensors
+    M, eps = ctx.args
+    L = w.shape[-1]
+    with torch.no_grad():
+        fr = frame(x, L, *ctx.frame_args)
+        fw = window(fr, w, L)
+        r = acorr(fw, M, 0)
+        gfw = acorr_backward(fw, levdur_backward(r, g, eps), M, 0)
+        gfr = window(gfw, w, L)
+        gx = frame_backward(gfr, x.shape[-1], *ctx.frame_args)
+        gw = None
+        if ctx.needs_input_grad[1]:
+            gw = (gfw * fr).reshape(-1, L).sum(0).to(w.dtype)
+    return (gx.reshape(x.shape).to(x.dtype), gw) + (None,) * 6
+
+
+torch.library.register_autograd(f"{_NS}::lpc_wave", _lpc_wave_bwd, setup_context=_lpc_wave_setup)

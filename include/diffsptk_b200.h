@@ -215,6 +215,34 @@ DSB200_DECL2(dsb200_spec_backward, (const void* b, int32_t b_length, const void*
 /* d/dx of dsb200_frame: scatter-add of the frame gradients (adjoint of pad + unfold + mean removal). */
 DSB200_DECL2(dsb200_frame_backward, (const void* gy, void* gx, int64_t batch, int64_t T,
                                      const dsb200_frame_params* p, int device, void* stream))
+/* d/dx of dsb200_fbank (diffsptk/modules/fbank.py:305-330).  gy[rows, n_channel] is the gradient of the
+ * (log / power-law) filter-bank outputs, gE[rows] (or NULL) that of the log energy; gx[rows, K] is overwritten. */
+DSB200_DECL2(dsb200_fbank_backward, (const void* x, const void* H, const int32_t* col_begin,
+                                     const int32_t* col_end, const void* gy, const void* gE, void* gx,
+                                     int64_t rows, const dsb200_fbank_params* p, int device, void* stream))
+/* d/dx of dsb200_acorr (diffsptk/modules/acorr.py:112-121), every out_format. */
+DSB200_DECL2(dsb200_acorr_backward, (const void* x, const void* gy, void* gx, int64_t rows, int32_t frame_length,
+                                     int32_t acr_order, int32_t out_format, int device, void* stream))
+/* d/dr of dsb200_levdur (diffsptk/modules/levdur.py:113-127): ga[rows, M+1] = gradient of (K, a_1..a_M). */
+DSB200_DECL2(dsb200_levdur_backward, (const void* r, const void* ga, void* gr, int64_t rows, int32_t lpc_order,
+                                      double eps, int device, void* stream))
+
+/* ---- the inverse of the path -------------------------------------------
+ * Inverse real FFT (diffsptk/modules/ifftr.py:130-143): y[rows, fft_length/2+1] interleaved complex ->
+ * x[rows, out_length], out_length <= fft_length; DC / Nyquist imaginary parts are ignored like torch.fft.irfft. */
+DSB200_DECL2(dsb200_ifftr, (const void* y, void* x, int64_t rows, int32_t fft_length, int32_t out_length,
+                            int device, void* stream))
+/* Windowed overlap-add with sum-of-squares normalisation (diffsptk/modules/unframe.py:164-211):
+ * frames[batch, n_frames, frame_length] -> out[batch, out_length]; out_length counts from frame_length/2
+ * (center) or 0 and must not exceed the overlap-added span. */
+DSB200_DECL2(dsb200_unframe, (const void* frames, const void* window, void* out, int64_t batch, int64_t n_frames,
+                              int64_t out_length, int32_t frame_length, int32_t frame_period, int32_t center,
+                              int device, void* stream))
+/* Inverse STFT = unframe(ifftr(Y)[..., :frame_length]) in one kernel (diffsptk/modules/istft.py:186-193):
+ * Y[batch, n_frames, fft_length/2+1] interleaved complex -> out[batch, out_length]. */
+DSB200_DECL2(dsb200_istft, (const void* Y, const void* window, void* out, int64_t batch, int64_t n_frames,
+                            int64_t out_length, int32_t frame_length, int32_t frame_period, int32_t fft_length,
+                            int32_t center, int device, void* stream))
 
 /* ---- host-buffer pipeline (the end-to-end path: pinned host -> device -> kernel -> host) -------------
  * One object owns two device staging slots and three streams (H2D, compute, D2H) and runs

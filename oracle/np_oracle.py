@@ -226,6 +226,65 @@ def stft(x, *, frame_length=400, frame_period=80, fft_length=512, center=True, z
     return spec(g, fft_length=fft_length, eps=eps, relative_floor=relative_floor, out_format=out_format)
 
 
+# ----------------------------------------------------------------------------- ifftr / unframe / istft
+# the inverse of the hot path.
+def ifftr(y, out_length=None):
+    """Inverse real FFT, truncated to ``out_length``.  diffsptk/modules/ifftr.py:103-108,130-143.
+
+    x[n] = (1/N) (Re Y[0] + (-1)^n Re Y[N/2] + 2 sum_{0<k<N/2} Re(Y[k] e^{+2 pi i k n / N})), N = 2 (K - 1):
+    the imaginary parts of the DC and Nyquist bins do not contribute (torch.fft.irfft / numpy agree).
+    """
+    y = np.asarray(y)
+    n = 2 * (y.shape[-1] - 1)
+    if n <= 0 or n % 2 == 1:
+        raise ValueError("fft_length must be positive even.")
+    if out_length is not None and (out_length <= 0 or n < out_length):
+        raise ValueError("out_length must be in [1, fft_length].")
+    dt = np.float32 if y.dtype == np.complex64 else np.float64
+    x = np.fft.irfft(y.astype(np.complex128), n=n, axis=-1)[..., :out_length]
+    return x.astype(dt)
+
+
+def unframe(y, out_length=None, *, frame_period=80, center=True, window="rectangular", norm="none",
+            symmetric=True, table=None):
+    """Windowed overlap-add with sum-of-squares normalisation.  diffsptk/modules/unframe.py:128-211.
+
+    out[t] = sum_n y[n, j] w[j] / (sum_n w[j]^2 + 1e-16), j = t + s - n P, s = L // 2 if center else 0;
+    default length N P when centred, the whole folded span otherwise.
+    """
+    y = _as_float(y)
+    if y.ndim <= 1:
+        raise ValueError("Input must be at least 2D tensor.")
+    N, L = y.shape[-2], y.shape[-1]
+    if L <= 0:
+        raise ValueError("frame_length must be positive.")
+    if L < frame_period:
+        raise ValueError("frame_period must be less than or equal to frame_length.")
+    w = window_table(L, window, norm, symmetric, y.dtype) if table is None else np.asarray(table, dtype=y.dtype)
+    span = (N - 1) * frame_period + L
+    num = np.zeros(y.shape[:-2] + (span,), dtype=y.dtype)
+    den = np.zeros(span, dtype=y.dtype)
+    for n in range(N):   # F.fold sums the overlapping columns in frame order
+        num[..., n * frame_period:n * frame_period + L] += y[..., n, :] * w
+        den[n * frame_period:n * frame_period + L] += w * w
+    x = num / (den + np.asarray(1e-16, dtype=y.dtype))
+    if out_length is None and center:
+        out_length = N * frame_period
+    s = L // 2 if center else 0
+    e = None if out_length is None else s + out_length
+    return x[..., s:e]
+
+
+def istft(y, *, out_length=None, frame_length=400, frame_period=80, fft_length=512, center=True,
+          window="blackman", norm="power", symmetric=True, table=None):
+    """unframe(ifftr(y)[..., :frame_length]).  diffsptk/modules/istft.py:146-193."""
+    fr = ifftr(y, frame_length)
+    if fr.shape[-1] != frame_length or 2 * (np.asarray(y).shape[-1] - 1) != fft_length:
+        raise ValueError("dimension of spectrum does not match fft_length")
+    return unframe(fr, out_length, frame_period=frame_period, center=center, window=window, norm=norm,
+                   symmetric=symmetric, table=table)
+
+
 # ----------------------------------------------------------------------------- acorr / levdur / lpc
 def acorr(x, acr_order, out_format="naive"):
     """FFT-based autocorrelation.  diffsptk/modules/acorr.py:95-120."""

@@ -152,3 +152,149 @@ def test_gradient_flows_through_a_pipeline():
         opt.step()
         losses.append(float(loss))
     assert np.isfinite(losses).all() and losses[-1] < 0.6 * losses[0]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Feature ops behind the spectrum.  Composites restate the reference forward passes in torch float64
+# (fbank.py:305-330, mfcc.py:243-256, acorr.py:112-121, levdur.py:113-127) and are differentiated by torch.
+def _vjp(fn, inputs, gen):
+    out = fn(*inputs)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    ws = [torch.randn(o.shape, generator=gen, dtype=torch.float64).to(o.device) for o in outs]
+    loss = sum((o.double() * w).sum() for o, w in zip(outs, ws))
+    return torch.autograd.grad(loss, inputs), ws
+
+
+def _ref_vjp(fn, inputs, ws):
+    out = fn(*inputs)
+    outs = out if isinstance(out, (tuple, list)) else (out,)
+    return torch.autograd.grad(sum((o * w).sum() for o, w in zip(outs, ws)), inputs)
+
+
+def composite_fbank(x, Hm, floor, gamma, use_power):
+    y = x if use_power else torch.sqrt(x)
+    y = torch.clip(y @ Hm, min=floor)
+    y = torch.log(y) if gamma == 0 else (torch.pow(y, gamma) - 1) / gamma
+    E = (2 * x[..., 1:-1]).sum(-1) + x[..., 0] + x[..., -1]
+    return y, torch.log(E / (2 * (x.size(-1) - 1))).unsqueeze(-1)
+
+
+def composite_levdur(r, eps):
+    M = r.size(-1) - 1
+    idx = (torch.arange(M)[:, None] - torch.arange(M)[None, :]).abs().to(r.device)
+    R = r[..., :-1][..., idx] + eps * torch.eye(M, dtype=r.dtype, device=r.device)
+    a = torch.linalg.solve(R, -r[..., 1:].unsqueeze(-1)).squeeze(-1)
+    K = torch.sqrt((r[..., 1:] * a).sum(-1, keepdim=True) + r[..., :1])
+    return torch.cat((K, a), -1)
+
+
+def composite_acorr(x, M, fmt):
+    L = x.size(-1)
+    r = torch.stack([(x[..., : L - k] * x[..., k:]).sum(-1) for k in range(M + 1)], -1)
+    if fmt == "normalized":
+        r = r / r[..., :1]
+    elif fmt == "biased":
+        r = r / L
+    elif fmt == "unbiased":
+        r = r / torch.arange(L, L - M - 1, -1, device=x.device)
+    return r
+
+
+@pytest.mark.parametrize("gamma,use_power", [(0.0, False), (-0.5, True), (0.3, False)])
+def test_fbank_and_mfcc_gradients(gamma, use_power):
+    import diffsptk_b200 as B
+    d = dev()
+    g = torch.Generator().manual_seed(11)
+    x = (torch.rand(3, 5, 33, generator=g, dtype=torch.float64) + 0.05).to(d).requires_grad_(True)
+    fb = B.MelFilterBankAnalysis(fft_length=64, n_channel=10, sample_rate=8000, floor=0.2, gamma=gamma,
+                                 use_power=use_power, out_format="y,E", dtype=torch.float64).to(d)
+    (gx,), ws = _vjp(fb, (x,), g)
+    (ref,) = _ref_vjp(lambda t: composite_fbank(t, fb.H, 0.2, gamma, use_power), (x,), ws)
+    assert torch.allclose(gx, ref, rtol=1e-9, atol=1e-11)
+    if use_power:
+        return
+    for fmt in ("y", "yE", "yc", "ycE"):
+        mf = B.MFCC(fft_length=64, mfcc_order=6, n_channel=10, sample_rate=8000, lifter=5, floor=0.2, gamma=gamma,
+                    out_format=fmt, dtype=torch.float64).to(d)
+
+        def ref_mfcc(t):
+            y, E = composite_fbank(t, mf.fbank.H, 0.2, gamma, False)
+            c = (y @ mf.dct.W)[..., :7] * mf.liftering_vector
+            c0, c = c[..., :1], c[..., 1:]
+            return {"y": c, "yE": torch.cat((c, E), -1), "yc": torch.cat((c, c0), -1),
+                    "ycE": torch.cat((c, c0, E), -1)}[fmt]
+        (gx,), ws = _vjp(mf, (x,), g)
+        (ref,) = _ref_vjp(ref_mfcc, (x,), ws)
+        assert torch.allclose(gx, ref, rtol=1e-9, atol=1e-11), fmt
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_lpc_chain_gradients(prec):
+    import diffsptk_b200 as B
+    import diffsptk_b200.functional as F
+    d = dev()
+    dt = torch.float64 if prec == "f64" else torch.float32
+    g = torch.Generator().manual_seed(13)
+    tol = dict(rtol=1e-7, atol=1e-9) if prec == "f64" else dict(rtol=5e-3, atol=5e-3)
+
+    def close(a, b, what):
+        scale = max(1.0, float(b.abs().max()))
+        assert torch.allclose(a.double() / scale, b / scale, **tol), (what, float((a.double() - b).abs().max()), scale)
+
+    x64 = torch.randn(4, 6, 50, generator=g, dtype=torch.float64).to(d)
+    x = x64.to(dt).requires_grad_(True)
+    xr = x64.clone().requires_grad_(True)
+    for fmt in ("naive", "normalized", "biased", "unbiased"):
+        (gx,), ws = _vjp(lambda t: F.acorr(t, 7, fmt), (x,), g)
+        (ref,) = _ref_vjp(lambda t: composite_acorr(t, 7, fmt), (xr,), ws)
+        close(gx, ref, f"acorr {fmt}")
+    r64 = composite_acorr(x64, 7, "naive").detach()
+    r = r64.to(dt).requires_grad_(True)
+    rr = r64.clone().requires_grad_(True)
+    (gr,), ws = _vjp(lambda t: F.levdur(t, eps=1e-3), (r,), g)
+    (ref,) = _ref_vjp(lambda t: composite_levdur(t, 1e-3), (rr,), ws)
+    close(gr, ref, "levdur")
+    (gx,), ws = _vjp(lambda t: F.lpc(t, 7, eps=1e-3), (x,), g)
+    (ref,) = _ref_vjp(lambda t: composite_levdur(composite_acorr(t, 7, "naive"), 1e-3), (xr,), ws)
+    close(gx, ref, "lpc")
+    # module path + order 0 and 1 corner cases
+    for M in (0, 1):
+        lpc = B.LPC(50, M, eps=1e-3, dtype=dt).to(d)
+        (gx,), ws = _vjp(lpc, (x,), g)
+        (ref,) = _ref_vjp(lambda t: composite_levdur(composite_acorr(t, M, "naive"), 1e-3), (xr,), ws)
+        close(gx, ref, f"LPC module order {M}")
+
+
+def test_fused_waveform_pipelines_are_differentiable():
+    """lpc_from_waveform / mfcc_from_waveform (fused forward kernels) against frame->window->... composites."""
+    import diffsptk_b200 as B
+    import diffsptk_b200.functional as F
+    d = dev()
+    g = torch.Generator().manual_seed(17)
+    x64 = torch.randn(2, 1500, generator=g, dtype=torch.float64).to(d)
+    win = B.Window(400, window="hamming", norm="power", dtype=torch.float64).to(d).window.double()
+
+    def frames(t):
+        return TF.pad(t, (200, 199)).unfold(-1, 400, 80) * win
+
+    for dt, tol in ((torch.float64, dict(rtol=1e-7, atol=1e-9)), (torch.float32, dict(rtol=5e-3, atol=5e-3))):
+        x = x64.to(dt).requires_grad_(True)
+        xr = x64.clone().requires_grad_(True)
+        (gx,), ws = _vjp(lambda t: F.lpc_from_waveform(t, lpc_order=8, window="hamming", eps=1e-4), (x,), g)
+        (ref,) = _ref_vjp(lambda t: composite_levdur(composite_acorr(frames(t), 8, "naive"), 1e-4), (xr,), ws)
+        scale = float(ref.abs().max())
+        assert torch.allclose(gx.double() / scale, ref / scale, **tol), ("lpc_wave", dt)
+
+        mf = B.MFCC(fft_length=512, mfcc_order=12, n_channel=20, sample_rate=16000, lifter=22, out_format="ycE",
+                    dtype=torch.float64).to(d)
+
+        def ref_mfcc(t):
+            P = torch.fft.rfft(frames(t), n=512).abs().square() + 1e-6
+            y, E = composite_fbank(P, mf.fbank.H, 1e-5, 0.0, False)
+            c = (y @ mf.dct.W)[..., :13] * mf.liftering_vector
+            return torch.cat((c[..., 1:], c[..., :1], E), -1)
+        (gx,), ws = _vjp(lambda t: F.mfcc_from_waveform(t, mfcc_order=12, n_channel=20, lifter=22, window="hamming",
+                                                        eps=1e-6, out_format="ycE"), (x,), g)
+        (ref,) = _ref_vjp(ref_mfcc, (xr,), ws)
+        scale = float(ref.abs().max())
+        assert torch.allclose(gx.double() / scale, ref / scale, **tol), ("mfcc_wave", dt)

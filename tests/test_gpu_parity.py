@@ -224,8 +224,8 @@ def test_edge_cases():
         F.stft(torch.randn(100, device=d), fft_length=511)
     with pytest.raises((ValueError, RuntimeError)):
         F.frame(torch.randn(2, 100, device=d), mode="reflect")  # pad 200 >= T (torch raises here too)
-    with pytest.raises(NotImplementedError):  # the solvers are forward-only and must say so
-        F.lpc(torch.randn(4, 400, device=d, requires_grad=True), 24)
+    with pytest.raises(NotImplementedError):  # the Newton solver is forward-only and must say so
+        F.mcep(torch.rand(4, 257, device=d, requires_grad=True) + 0.1, 24, 0.42, 2)
     # a side stream is honoured
     s = torch.cuda.Stream(device=d)
     xs = torch.randn(4, 8000, device=d)
