@@ -34,6 +34,8 @@ WORKLOADS = {
     "mfcc": ("MFCC (fbank->DCT, 40 mel / 13 cep) from the waveform: 1024 utt x 10 s per GPU", 1024, 160000, 320, 52),
     "mcep": ("MelCepstralAnalysis (n_iter=10, M=24, alpha=0.42) over STFT power, 512 utt x 10 s", 512, 160000,
              1028, 100),
+    "istft": ("Inverse STFT (ifftr -> window -> overlap-add, one kernel): 256 utt x 10 s of complex spectra", 256,
+              160000, 2056, 320),
 }
 
 
@@ -125,6 +127,8 @@ def _cpu_task(args):
         y = O.lpc(O.window(O.frame(x, FL, FP), None), 24)
     elif workload == "mfcc":
         y = O.mfcc(O.stft(x), 13, 40, 16000)
+    elif workload == "istft":  # x holds complex spectra
+        y = O.istft(x)
     else:  # mcep: x holds power spectra
         y = O.mcep(x, 24, 0.42, 10)
     return float(np.sum(y[..., :1]))
@@ -143,6 +147,9 @@ def cpu_oracle_throughput(workload, utterances, T, steps, warmup, budget_s=25.0)
         from oracle import np_oracle as O
         utterances = min(utterances, max(1, cores // 16))  # ~1.5k frames/s/core: keep a step to seconds
         _CPU_X = O.stft(rng.standard_normal((utterances, T)).astype(np.float32))
+    elif workload == "istft":
+        from oracle import np_oracle as O
+        _CPU_X = O.stft(rng.standard_normal((utterances, T)).astype(np.float32), out_format="complex")
     else:
         _CPU_X = rng.standard_normal((utterances, T)).astype(np.float32)
     per = max(1, utterances // (cores * 2))
@@ -198,6 +205,12 @@ def make_step(workload, B, T, dev):
         with torch.no_grad():
             xs = [stft(torch.randn(B, T, generator=g, device=dev)) for _ in range(2)]
         return xs, lambda i: mcep(xs[i & 1])
+    if workload == "istft":
+        stft = D.STFT(FL, FP, NFFT, out_format="complex").to(dev)
+        istft = D.ISTFT(FL, FP, NFFT).to(dev)
+        with torch.no_grad():
+            xs = [stft(torch.randn(B, T, generator=g, device=dev)) for _ in range(2)]
+        return xs, lambda i: istft(xs[i & 1], T)
     xs = [torch.randn(B, T, generator=g, device=dev) for _ in range(2)]
     if workload == "stft":
         m = D.STFT(FL, FP, NFFT).to(dev)
@@ -304,11 +317,11 @@ def main():
             pipe(xh, yh)
     else:
         src = xs[0].cpu().pin_memory()
-        h2d = src.numel() * 4
+        h2d = src.numel() * src.element_size()
         xin = torch.empty_like(xs[0])
         probe = step(0)
         yh = torch.empty(probe.shape, dtype=probe.dtype).pin_memory()
-        d2h = yh.numel() * 4
+        d2h = yh.numel() * yh.element_size()
 
         def e2e_step():
             xin.copy_(src, non_blocking=True)
@@ -360,7 +373,7 @@ def main():
         v, ms, cores, desc = cpu_oracle_throughput(args.workload, min(B, 256), T, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
         extras = {}
-        for wl in ("lpc", "mfcc", "mcep"):
+        for wl in ("lpc", "mfcc", "mcep", "istft"):
             if wl == args.workload:
                 continue
             try:

@@ -100,6 +100,27 @@ def window(x: Tensor, out_length: int | None = None, *, window: str = "blackman"
     return nn.Window._func(x, out_length=out_length, window=window, norm=norm, symmetric=symmetric)
 
 
+def ifftr(y: Tensor, out_length: int | None = None) -> Tensor:
+    """Inverse real FFT, complex ``(..., L/2+1) -> (..., N)``."""
+    return nn.RealValuedInverseFastFourierTransform._func(y, out_length=out_length)
+
+
+def unframe(y: Tensor, out_length: int | None = None, *, frame_period: int = 80, center: bool = True,
+            window: str = "rectangular", norm: str = "none", symmetric: bool = True) -> Tensor:
+    """Windowed overlap-add ``(..., T/P, L) -> (..., T)``."""
+    return nn.Unframe._func(y, out_length, frame_period=frame_period, center=center, window=window, norm=norm,
+                            symmetric=symmetric)
+
+
+def istft(y: Tensor, *, out_length: int | None = None, frame_length: int = 400, frame_period: int = 80,
+          fft_length: int = 512, center: bool = True, window: str = "blackman", norm: str = "power",
+          symmetric: bool = True) -> Tensor:
+    """Inverse short-time Fourier transform, complex ``(..., T/P, N/2+1) -> (..., T)``, in one fused kernel."""
+    return nn.InverseShortTimeFourierTransform._func(
+        y, out_length, frame_length=frame_length, frame_period=frame_period, fft_length=fft_length, center=center,
+        window=window, norm=norm, symmetric=symmetric)
+
+
 # fused pipelines (one kernel chain from the waveform; see fused.py)
 lpc_from_waveform = _fused.lpc_from_waveform
 mfcc_from_waveform = _fused.mfcc_from_waveform

@@ -8,6 +8,9 @@ from .fbank import MelFilterBankAnalysis
 from .fbank import MelFilterBankAnalysis as FBANK
 from .fftr import RealValuedFastFourierTransform
 from .frame import Frame
+from .ifftr import RealValuedInverseFastFourierTransform
+from .istft import InverseShortTimeFourierTransform
+from .istft import InverseShortTimeFourierTransform as ISTFT
 from .freqt import FrequencyTransform
 from .levdur import LevinsonDurbin
 from .lpc import LinearPredictiveCodingAnalysis
@@ -18,6 +21,7 @@ from .mfcc import MelFrequencyCepstralCoefficientsAnalysis as MFCC
 from .spec import Spectrum
 from .stft import ShortTimeFourierTransform
 from .stft import ShortTimeFourierTransform as STFT
+from .unframe import Unframe
 from .window import Window
 
 __all__ = [
@@ -25,5 +29,5 @@ __all__ = [
     "RealValuedFastFourierTransform", "Frame", "FrequencyTransform", "LevinsonDurbin",
     "LinearPredictiveCodingAnalysis", "LPC", "MelCepstralAnalysis",
     "MelFrequencyCepstralCoefficientsAnalysis", "MFCC", "Spectrum", "ShortTimeFourierTransform", "STFT",
-    "Window",
+    "Window", "RealValuedInverseFastFourierTransform", "Unframe", "InverseShortTimeFourierTransform", "ISTFT",
 ]

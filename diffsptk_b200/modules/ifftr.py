@@ -1,0 +1,54 @@
+"""Inverse real FFT (drop-in for diffsptk/modules/ifftr.py)."""
+
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ..utils import check_size, filter_values
+from .base import BaseFunctionalModule, Precomputed
+
+
+class RealValuedInverseFastFourierTransform(BaseFunctionalModule):
+    """complex ``(..., L/2+1) -> (..., N)``; kernel ``dsb200_ifftr`` (no cuFFT / torch.fft on the path)."""
+
+    _takes_input_size = True
+
+    def __init__(self, fft_length: int, out_length: int | None = None, learnable: bool = False,
+                 device: torch.device | None = None, dtype: torch.dtype | None = None) -> None:
+        super().__init__()
+        self.in_dim = fft_length // 2 + 1
+        self._register_precomputed(self._precompute(**filter_values(locals())), learnable=learnable is True)
+
+    def forward(self, y: torch.Tensor) -> torch.Tensor:
+        check_size(y.size(-1), self.in_dim, "length of spectrum")
+        return self._call_forward(y)
+
+    @staticmethod
+    def _func(y: torch.Tensor, *args, **kwargs) -> torch.Tensor:
+        pre = RealValuedInverseFastFourierTransform._precompute(2 * y.size(-1) - 2, *args, **kwargs,
+                                                                learnable=False, device=y.device, dtype=None)
+        return RealValuedInverseFastFourierTransform._apply_precomputed(pre, y=y)
+
+    @staticmethod
+    def _check(fft_length: int, out_length: int | None) -> None:
+        if fft_length <= 0 or fft_length % 2 == 1:
+            raise ValueError("fft_length must be positive even.")
+        if out_length is not None and (out_length <= 0 or fft_length < out_length):
+            raise ValueError("out_length must be in [1, fft_length].")
+
+    @staticmethod
+    def _precompute(fft_length: int, out_length: int | None, learnable: bool, device: torch.device | None,
+                    dtype: torch.dtype | None) -> Precomputed:
+        RealValuedInverseFastFourierTransform._check(fft_length, out_length)
+        if learnable:
+            # the reference switches to a trainable inverse-DFT matrix (ifftr.py:117-124): a dense contraction
+            raise NotImplementedError("learnable DFT basis is not part of the B200 hot path")
+        return Precomputed(values={"fft_length": fft_length, "out_length": out_length})
+
+    @staticmethod
+    def _forward(y: torch.Tensor, *, fft_length: int, out_length: int | None) -> torch.Tensor:
+        if not y.is_complex():
+            raise ValueError("the input spectrum must be complex")
+        ops._no_grad_check(y)
+        return ops.ifftr(y, fft_length if out_length is None else out_length)

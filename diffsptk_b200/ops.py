@@ -824,3 +824,83 @@ def _lpc_wave_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{_NS}::lpc_wave", _lpc_wave_bwd, setup_context=_lpc_wave_setup)
+
+
+# ------------------------------------------------------------------ inverse of the path (section 8f rank 2)
+def _complex_rows(y: Tensor, dt: torch.dtype) -> Tensor:
+    """Complex (or trailing-2 real) spectrum as contiguous interleaved (re, im) rows of dtype ``dt``."""
+    if y.is_complex():
+        y = torch.view_as_real(y.resolve_conj().contiguous())
+    return _prep(y, dt)
+
+
+def _complex_native_dtype(y: Tensor) -> torch.dtype:
+    if y.is_complex():
+        return torch.float64 if y.dtype == torch.complex128 else torch.float32
+    return _native_dtype(y)
+
+
+@torch.library.custom_op(f"{_NS}::ifftr", mutates_args=(), device_types="cuda")
+def ifftr(y: Tensor, out_length: int) -> Tensor:
+    """``y`` complex ``(..., K)`` -> real ``(..., out_length)``, ``fft_length = 2 (K - 1)``."""
+    dt = _complex_native_dtype(y)
+    yc = _complex_rows(y, dt)
+    K = yc.shape[-2]
+    rows = yc.numel() // max(2 * K, 1)
+    x = torch.empty((*yc.shape[:-2], out_length), device=y.device, dtype=dt)
+    N.check(N.typed("dsb200_ifftr", dt == torch.float64)(_ptr(yc), _ptr(x), rows, 2 * (K - 1), out_length, _dev(y),
+                                                         _stream(y)))
+    return x
+
+
+@ifftr.register_fake
+def _(y, out_length):
+    return y.new_empty((*y.shape[:-1], out_length), dtype=_complex_native_dtype(y))
+
+
+def unframe_length(n_frames: int, frame_length: int, frame_period: int, center: bool,
+                   out_length: Optional[int]) -> int:
+    """Length of the reference's ``x[..., s:e]`` slice of the folded signal (unframe.py:182-195)."""
+    s = frame_length // 2 if center else 0
+    avail = (n_frames - 1) * frame_period + frame_length - s
+    if out_length is None:
+        out_length = n_frames * frame_period if center else avail
+    return max(0, min(out_length, avail))
+
+
+@torch.library.custom_op(f"{_NS}::unframe", mutates_args=(), device_types="cuda")
+def unframe(y: Tensor, window: Tensor, out_length: int, frame_period: int, center: bool) -> Tensor:
+    dt = _native_dtype(y, window)
+    yc, wc = _prep(y, dt), _prep(window, dt)
+    Nf, L = yc.shape[-2], yc.shape[-1]
+    B = yc.numel() // max(Nf * L, 1)
+    out = torch.empty((*yc.shape[:-2], out_length), device=y.device, dtype=dt)
+    if out_length > 0:
+        N.check(N.typed("dsb200_unframe", dt == torch.float64)(_ptr(yc), _ptr(wc), _ptr(out), B, Nf, out_length, L,
+                                                               frame_period, int(center), _dev(y), _stream(y)))
+    return out
+
+
+@unframe.register_fake
+def _(y, window, out_length, frame_period, center):
+    return y.new_empty((*y.shape[:-2], out_length), dtype=_native_dtype(y, window))
+
+
+@torch.library.custom_op(f"{_NS}::istft", mutates_args=(), device_types="cuda")
+def istft(y: Tensor, window: Tensor, out_length: int, frame_period: int, center: bool) -> Tensor:
+    """``y`` complex ``(..., N, K)`` -> ``(..., out_length)``; the frames never reach HBM."""
+    dt = _native_dtype(window)
+    yc, wc = _complex_rows(y, dt), _prep(window, dt)
+    Nf, K = yc.shape[-3], yc.shape[-2]
+    B = yc.numel() // max(2 * Nf * K, 1)
+    out = torch.empty((*yc.shape[:-3], out_length), device=y.device, dtype=dt)
+    if out_length > 0:
+        N.check(N.typed("dsb200_istft", dt == torch.float64)(_ptr(yc), _ptr(wc), _ptr(out), B, Nf, out_length,
+                                                             wc.shape[-1], frame_period, 2 * (K - 1), int(center),
+                                                             _dev(y), _stream(y)))
+    return out
+
+
+@istft.register_fake
+def _(y, window, out_length, frame_period, center):
+    return y.new_empty((*y.shape[:-2], out_length), dtype=_native_dtype(window))

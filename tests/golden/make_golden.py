@@ -178,6 +178,38 @@ def cases():
     for t in (1, 2, 3, 4):
         yield (f"dct_8_t{t}", "dct", dict(dct_type=t), [x8])
     yield ("dct_40", "dct", dict(), [r.standard_normal((5, 40))])
+    # ---- inverse path, SURVEY.md section 8(f) rank 2 (tests/test_ifftr.py, test_unframe.py, test_istft.py) ----
+    ri = _rng(4321)
+
+    def cplx(*shape):
+        return ri.standard_normal(shape) + 1j * ri.standard_normal(shape)
+    y9 = cplx(3, 9)
+    for ol in (None, 16, 5):
+        yield (f"ifftr_16_o{ol}", "ifftr", dict(out_length=ol), [y9])
+    yield ("ifftr_512_400", "ifftr", dict(out_length=400), [cplx(2, 3, 257)])
+    yield ("ifftr_24", "ifftr", dict(out_length=None), [cplx(2, 13)])
+    yield ("ifftr_2", "ifftr", dict(out_length=1), [cplx(2, 2)])
+    ramp_frames = np.array([[0, 0, 1, 2, 3], [1, 2, 3, 4, 5], [3, 4, 5, 6, 7], [5, 6, 7, 8, 9], [7, 8, 9, 0, 0]],
+                           dtype=np.float64)
+    yield ("unframe_ramp", "unframe", dict(out_length=9, frame_period=2), [ramp_frames])
+    fr12 = ri.standard_normal((3, 7, 12))
+    for ol in (None, 20):
+        yield (f"unframe_12_5_o{ol}", "unframe", dict(out_length=ol, frame_period=5), [fr12])
+        yield (f"unframe_12_3_nocenter_hamming_o{ol}", "unframe",
+               dict(out_length=ol, frame_period=3, center=False, window="hamming", norm="power"), [fr12])
+    yield ("unframe_12_12", "unframe", dict(out_length=None, frame_period=12), [fr12])
+    yield ("unframe_400_80_blackman", "unframe", dict(out_length=2000, frame_period=80, window="blackman",
+                                                      norm="power"), [ri.standard_normal((2, 2, 26, 400))])
+    Yb = cplx(2, 13, 257)
+    for ol in (None, 1000, 777):
+        yield (f"istft_baseline_o{ol}", "istft", dict(out_length=ol), [Yb])
+    yield ("istft_small", "istft", dict(out_length=30, frame_length=12, frame_period=5, fft_length=16), [cplx(3, 7, 9)])
+    yield ("istft_nonpow2", "istft", dict(out_length=None, frame_length=30, frame_period=7, fft_length=48,
+                                          window="hanning", norm="magnitude"), [cplx(2, 9, 25)])
+    yield ("istft_nocenter", "istft", dict(out_length=None, frame_length=40, frame_period=10, fft_length=64,
+                                           center=False, window="hamming", norm="none", symmetric=False),
+           [cplx(2, 3, 12, 33)])
+    yield ("istft_one_frame", "istft", dict(out_length=None), [cplx(1, 1, 257)])
 
 
 def main():
@@ -193,13 +225,15 @@ def main():
     for dt_name, tdt, ndt in (("f32", torch.float32, np.float32), ("f64", torch.float64, np.float64)):
         store = {}
         for name, op, params, inputs in cases():
-            tin = [None if v is None else torch.from_numpy(np.ascontiguousarray(v.astype(ndt))) for v in inputs]
+            cdt = np.complex64 if ndt is np.float32 else np.complex128
+            cast = lambda v: v.astype(cdt if np.iscomplexobj(v) else ndt)  # noqa: E731
+            tin = [None if v is None else torch.from_numpy(np.ascontiguousarray(cast(v))) for v in inputs]
             with torch.no_grad():
                 out = getattr(F, op)(*tin, **params)
             outs = out if isinstance(out, tuple) else (out,)
             for i, v in enumerate(inputs):
                 if v is not None:
-                    store[f"{name}/in{i}"] = v.astype(ndt)
+                    store[f"{name}/in{i}"] = cast(v)
             for i, o in enumerate(outs):
                 store[f"{name}/out{i}"] = o.numpy()
             manifest[name] = dict(op=op, params=params, n_in=len(inputs),

@@ -24,7 +24,12 @@ def dev():
 
 
 def to_dev(a, prec):
-    return None if a is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev(), TD[prec])
+    if a is None:
+        return None
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.is_complex():
+        return t.to(dev(), torch.complex64 if prec == "f32" else torch.complex128)
+    return t.to(dev(), TD[prec])
 
 
 def to_np(t):
@@ -93,7 +98,27 @@ def build_module(op, params, ins, prec):
         return B.MFCC(fft_length=2 * n - 2, **p, device=d, dtype=dt)
     if op == "dct":
         return B.DCT(n, **p, device=d, dtype=dt)
+    if op == "ifftr":
+        return B.RealValuedInverseFastFourierTransform(2 * n - 2, p.pop("out_length"), device=d, dtype=dt)
+    if op == "unframe":
+        ol = p.pop("out_length")
+        return _WithOutLength(B.Unframe(n, p.pop("frame_period"), **p, device=d, dtype=dt), ol)
+    if op == "istft":
+        ol = p.pop("out_length")
+        fl, fp, nfft = p.pop("frame_length", 400), p.pop("frame_period", 80), p.pop("fft_length", 512)
+        return _WithOutLength(B.ISTFT(fl, fp, nfft, **p, device=d, dtype=dt), ol)
     raise KeyError(op)
+
+
+class _WithOutLength(torch.nn.Module):
+    """The reference's Unframe / ISTFT take ``out_length`` in forward()."""
+
+    def __init__(self, mod, out_length):
+        super().__init__()
+        self.mod, self.out_length = mod, out_length
+
+    def forward(self, y):
+        return self.mod(y, self.out_length)
 
 
 MODULE_CASES = [n for n in H.case_names() if not n.startswith(("window_", "frame_ramp"))] + \
@@ -316,3 +341,79 @@ def test_mfcc_wave_fused_kernel_against_oracle(shape, kw):
     if kw.get("frame_period", 80) == 80:  # longer hops stage longer spans and may fall back to two kernels
         assert _native.launch_count() - n0 == 1, "expected the single fused kernel"
     H.assert_close(got, want, "f32", what=f"mfcc_wave {shape} {kw}", scale_atol=True, rtol_mul=2.0)
+
+
+# ------------------------------------------------------------------ inverse path
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_istft_against_oracle_and_roundtrip(prec):
+    """Random spectra against the oracle; STFT -> ISTFT reproduces the waveform (analysis/synthesis identity)."""
+    import diffsptk_b200.functional as F
+    from diffsptk_b200 import _native
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(21)
+    cdt = np.complex64 if prec == "f32" else np.complex128
+    for shape, kw in (((3, 40, 257), dict()),
+                      ((2, 2, 9, 33), dict(frame_length=50, frame_period=20, fft_length=64, window="hamming")),
+                      ((2, 11, 21), dict(frame_length=40, frame_period=40, fft_length=40, window="rectangular",
+                                         norm="none", center=False)),
+                      ((1, 300, 257), dict(out_length=23000, window="hanning", norm="magnitude"))):
+        Y = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cdt)
+        n0 = _native.launch_count()
+        got = to_np(F.istft(to_dev(Y, prec), **kw))
+        assert _native.launch_count() - n0 == 1, "ISTFT must be one fused kernel"
+        H.assert_close(got, O.istft(Y.astype(np.complex128), **kw), prec, what=f"istft {shape} {kw}", scale_atol=True)
+    x = torch.randn(7, 12345, device=dev(), dtype=TD[prec], generator=torch.Generator(device=dev()).manual_seed(1))
+    for kw in (dict(), dict(frame_length=400, frame_period=100, fft_length=400, window="hamming"),
+               dict(frame_length=63, frame_period=16, fft_length=64, window="sine", norm="none")):
+        y = F.istft(F.stft(x, out_format="complex", **kw), out_length=x.shape[-1], **kw)
+        tol = 2e-4 if prec == "f32" else 1e-10
+        assert float((y - x).abs().max()) < tol, (kw, float((y - x).abs().max()))
+
+
+def test_istft_full_size_roundtrip():
+    """BASELINE config 2 shapes: 256 x 10 s -> complex STFT -> fused ISTFT == waveform; one utterance vs the oracle."""
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    g = torch.Generator(device=dev()).manual_seed(5)
+    x = torch.randn(256, 160000, generator=g, device=dev())
+    Y = F.stft(x, out_format="complex")
+    assert Y.shape == (256, 2000, 257)
+    y = F.istft(Y, out_length=160000)
+    assert y.shape == x.shape
+    assert float((y - x).abs().max()) < 5e-4
+    want = O.istft(to_np(Y[77]).astype(np.complex128), out_length=160000)
+    H.assert_close(to_np(y[77]), want, "f32", what="istft utterance 77", scale_atol=True)
+
+
+def test_ifftr_unframe_edge_cases():
+    import diffsptk_b200 as B
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    d = dev()
+    rng = np.random.default_rng(8)
+    # ifftr inverts fftr, every even length, and ignores the imaginary parts of the DC / Nyquist bins
+    for n in (4, 6, 8, 30, 64, 100, 1024):
+        x = rng.standard_normal((3, n))
+        X = F.fftr(to_dev(x, "f64"), n)
+        H.assert_close(to_np(F.ifftr(X)), x, "f64", what=f"ifftr(fftr) n={n}", atol_mul=100)
+        X2 = X.clone()
+        X2[..., 0] += 3j
+        X2[..., -1] -= 2j
+        H.assert_close(to_np(F.ifftr(X2, n // 2 + 1)), x[..., : n // 2 + 1], "f64", what=f"ifftr imag n={n}", atol_mul=100)
+    with pytest.raises(ValueError):
+        F.ifftr(torch.zeros(2, 9, dtype=torch.complex64, device=d), 17)
+    with pytest.raises(ValueError):
+        B.Unframe(4, 5)
+    with pytest.raises(ValueError):
+        F.unframe(torch.zeros(5, device=d))
+    # unframe(frame(x)) == x for every overlap, centred or not; requested lengths beyond the span are clipped
+    x = torch.randn(2, 3, 501, device=d, dtype=torch.float64)
+    for L, P, center in ((5, 2, True), (5, 5, True), (400, 80, True), (33, 7, False), (8, 1, False)):
+        fr = F.frame(x, L, P, center=center)
+        y = F.unframe(fr, 501, frame_period=P, center=center)   # rectangular synthesis window: plain average
+        n = min(501, y.shape[-1])
+        assert n >= 501 - L and torch.allclose(y[..., :n], x[..., :n], rtol=1e-10, atol=1e-12), (L, P, center)
+        want = O.unframe(to_np(fr), 10 ** 6, frame_period=P, center=center)
+        assert F.unframe(fr, 10 ** 6, frame_period=P, center=center).shape == want.shape
+    with pytest.raises(NotImplementedError):
+        F.istft(torch.zeros(1, 3, 257, dtype=torch.complex64, device=d, requires_grad=True))
