@@ -404,23 +404,64 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       rowB = rowA + kStride;
     }
 
+    // X[k] and X[256 - k] (k = 16 k1 + l) of both frames from Z[k] = a[dig(k1)] and Z[256 - k] = r[7 - k1]
+    auto bin_pair = [&](int k1, float2& xr_, float2& xi_, float2& mr, float2& mi) {
+      const C2 z = a[dig(k1)], m = r[7 - k1];
+      const float2 sr = add2(z.re, m.re), dr = sub2(z.re, m.re);
+      const float2 si = add2(z.im, m.im), di = sub2(z.im, m.im);
+      const float2 hw = htw[16 * k1 + l];                          // W512^k / 2
+      const float2 tr = fma2s(dr, hw.y, mul2s(si, hw.x));          // T = (W/2) (si, -dr)
+      const float2 ti = fma2s(dr, -hw.x, mul2s(si, hw.y));
+      xr_ = fma2s(sr, 0.5f, tr);                                   // X[k]     = E + T
+      xi_ = fma2s(di, 0.5f, ti);
+      mr = fma2s(sr, 0.5f, make_float2(-tr.x, -tr.y));            // X[256-k] = conj(E - T)
+      mi = fma2s(di, -0.5f, ti);
+    };
     auto split = [&](auto staged_tag) {
       constexpr bool ST = decltype(staged_tag)::value;
+      if constexpr (ST && FMT != DSB200_SPEC_COMPLEX && FMT != kFmtMfcc) {
+        // Staged real-valued rows.  The two half-warps write rows that start 2 banks apart (514 floats), so a
+        // store of "bin 16 k1 + l" from both would always collide.  Bins are therefore written two k1 at a
+        // time and the upper half-warp swaps which of the two it writes first (all lanes but the two whose
+        // banks wrap around): every store instruction then touches 32 distinct banks.
+        const bool swF = h && (l < 14), swM = h && (l >= 2);
+        float* f1 = rowA + l + (swF ? 16 : 0);
+        float* f2 = rowA + l - (swF ? 16 : 0);
+        float* m1 = rowA + 256 - l - (swM ? 16 : 0);
+        float* m2 = rowA + 256 - l + (swM ? 16 : 0);
+        auto fmt2 = [&](float2 re, float2 im) {
+          const float2 s = fma2(re, re, fma2(im, im, make_float2(A.eps, A.eps)));
+          return make_float2(fmt1<FMT>(s.x), fmt1<FMT>(s.y));
+        };
 #pragma unroll
-      for (int k1 = 0; k1 < 8; ++k1) {
-        // z = Z[k], m = Z[256 - k], k = 16 k1 + l
-        const C2 z = a[dig(k1)], m = r[7 - k1];
-        const float2 sr = add2(z.re, m.re), dr = sub2(z.re, m.re);
-        const float2 si = add2(z.im, m.im), di = sub2(z.im, m.im);
-        const float2 hw = htw[16 * k1 + l];                          // W512^k / 2
-        const float2 tr = fma2s(dr, hw.y, mul2s(si, hw.x));          // T = (W/2) (si, -dr)
-        const float2 ti = fma2s(dr, -hw.x, mul2s(si, hw.y));
-        const float2 xr_ = fma2s(sr, 0.5f, tr), xi_ = fma2s(di, 0.5f, ti);   // X[k]     = E + T
-        const float2 mr = fma2s(sr, 0.5f, make_float2(-tr.x, -tr.y));         // X[256-k] = conj(E - T)
-        const float2 mi = fma2s(di, -0.5f, ti);
-        const int k = 16 * k1 + l;
-        put_bin<FMT, ST>(rowA, rowB, vB, k, xr_, xi_, A.eps);
-        put_bin<FMT, ST>(rowA, rowB, vB, 256 - k, mr, mi, A.eps);
+        for (int u = 0; u < 4; ++u) {
+          float2 xr_, xi_, mr, mi;
+          bin_pair(2 * u, xr_, xi_, mr, mi);
+          const float2 F0 = fmt2(xr_, xi_), M0 = fmt2(mr, mi);
+          bin_pair(2 * u + 1, xr_, xi_, mr, mi);
+          const float2 F1 = fmt2(xr_, xi_), M1 = fmt2(mr, mi);
+          float2 v = swF ? F1 : F0;
+          f1[32 * u] = v.x;
+          f1[32 * u + 257] = v.y;
+          v = swF ? F0 : F1;
+          f2[32 * u + 16] = v.x;
+          f2[32 * u + 16 + 257] = v.y;
+          v = swM ? M1 : M0;
+          m1[-32 * u] = v.x;
+          m1[-32 * u + 257] = v.y;
+          v = swM ? M0 : M1;
+          m2[-32 * u - 16] = v.x;
+          m2[-32 * u - 16 + 257] = v.y;
+        }
+      } else {
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+          float2 xr_, xi_, mr, mi;
+          bin_pair(k1, xr_, xi_, mr, mi);
+          const int k = 16 * k1 + l;
+          put_bin<FMT, ST>(rowA, rowB, vB, k, xr_, xi_, A.eps);
+          put_bin<FMT, ST>(rowA, rowB, vB, 256 - k, mr, mi, A.eps);
+        }
       }
       if (l == 0)  // bin 128 pairs with itself: X[128] = conj(Z[128])
         put_bin<FMT, ST>(rowA, rowB, vB, 128, a[dig(8)].re, make_float2(-a[dig(8)].im.x, -a[dig(8)].im.y), A.eps);
