@@ -34,6 +34,8 @@ WORKLOADS = {
     "mfcc": ("MFCC (fbank->DCT, 40 mel / 13 cep) from the waveform: 1024 utt x 10 s per GPU", 1024, 160000, 320, 52),
     "mcep": ("MelCepstralAnalysis (n_iter=10, M=24, alpha=0.42) over STFT power, 512 utt x 10 s", 512, 160000,
              1028, 100),
+    "stft_grad": ("STFT power forward + backward (d/dwaveform, native adjoint kernel): 256 utt x 10 s", 256, 160000,
+                  320 + 1028 + 320, 1028 + 320),
     "istft": ("Inverse STFT (ifftr -> window -> overlap-add, one kernel): 256 utt x 10 s of complex spectra", 256,
               160000, 2056, 320),
 }
@@ -129,6 +131,8 @@ def _cpu_task(args):
         y = O.mfcc(O.stft(x), 13, 40, 16000)
     elif workload == "istft":  # x holds complex spectra
         y = O.istft(x)
+    elif workload == "stft_grad":  # the oracle has no autograd: forward only (a lower bound on the CPU cost)
+        y = O.stft(x)
     else:  # mcep: x holds power spectra
         y = O.mcep(x, 24, 0.42, 10)
     return float(np.sum(y[..., :1]))
@@ -212,6 +216,16 @@ def make_step(workload, B, T, dev):
             xs = [stft(torch.randn(B, T, generator=g, device=dev)) for _ in range(2)]
         return xs, lambda i: istft(xs[i & 1], T)
     xs = [torch.randn(B, T, generator=g, device=dev) for _ in range(2)]
+    if workload == "stft_grad":
+        m = D.STFT(FL, FP, NFFT).to(dev)
+        gy = torch.randn(B, n_frames(T), NFFT // 2 + 1, generator=g, device=dev)
+
+        def grad_step(i):
+            with torch.enable_grad():
+                x = xs[i & 1].detach().requires_grad_(True)
+                m(x).backward(gy)
+            return x.grad
+        return xs, grad_step
     if workload == "stft":
         m = D.STFT(FL, FP, NFFT).to(dev)
         return xs, lambda i: m(xs[i & 1])
@@ -373,7 +387,7 @@ def main():
         v, ms, cores, desc = cpu_oracle_throughput(args.workload, min(B, 256), T, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
         extras = {}
-        for wl in ("lpc", "mfcc", "mcep", "istft"):
+        for wl in ("lpc", "mfcc", "mcep", "istft", "stft_grad"):
             if wl == args.workload:
                 continue
             try:

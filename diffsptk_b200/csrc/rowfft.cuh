@@ -7,26 +7,51 @@
 
 namespace dsb200 {
 
-// Stockham autosort radix-2 FFT of Nc complex points held in shared memory by one warp.
+// Stockham autosort FFT of Nc = 2^m complex points held in shared memory by one warp: radix-4 passes (half the
+// shared-memory round trips of radix-2), then one radix-2 pass when m is odd.
 // Returns the buffer that holds the natural-order result.
 // `tw_n` is the number of points on the unit circle the table samples: tw[k] = exp(-2 pi i k / tw_n);
 // the real-FFT packing uses tw_n = 2 Nc, a plain complex FFT of Nc points uses tw_n = Nc.
 template <typename T>
 __device__ cx_t<T>* warp_fft_pow2(cx_t<T>* in, cx_t<T>* out, int Nc, const cx_t<T>* tw, int lane, int tw_n) {
-  const int half = Nc >> 1;
-  for (int Ns = 1; Ns < Nc; Ns <<= 1) {
+  using C = cx_t<T>;
+  int Ns = 1;
+  const int quarter = Nc >> 2;
+  for (; Ns * 4 <= Nc; Ns <<= 2) {
+    // y[(j - k) 4 + k + t Ns] = sum_s (-i)^(s t) w^(s k) x[j + s Nc/4],  w = exp(-2 pi i / (4 Ns)), k = j mod Ns
+    const int tstride = tw_n / (4 * Ns);
+    for (int j = lane; j < quarter; j += 32) {
+      const int k = j & (Ns - 1);
+      const C a = in[j];
+      C b = in[j + quarter], c = in[j + 2 * quarter], d = in[j + 3 * quarter];
+      if (Ns > 1) {  // k == 0 in the first pass: all twiddles are 1
+        b = cmul(b, tw[k * tstride]);
+        c = cmul(c, tw[2 * k * tstride]);
+        d = cmul(d, tw[3 * k * tstride]);
+      }
+      const C ac = cadd(a, c), amc = csub(a, c), bd = cadd(b, d), bmd = csub(b, d);
+      const int j0 = ((j - k) << 2) + k;
+      out[j0] = cadd(ac, bd);
+      out[j0 + Ns] = mk<T>(amc.x + bmd.y, amc.y - bmd.x);       // a - i b - c + i d
+      out[j0 + 2 * Ns] = csub(ac, bd);
+      out[j0 + 3 * Ns] = mk<T>(amc.x - bmd.y, amc.y + bmd.x);   // a + i b - c - i d
+    }
+    __syncwarp();
+    C* t = in; in = out; out = t;
+  }
+  if (Ns < Nc) {  // one radix-2 pass left (Ns == Nc / 2)
+    const int half = Nc >> 1;
     const int tstride = tw_n / (2 * Ns);
     for (int j = lane; j < half; j += 32) {
       const int k = j & (Ns - 1);
-      const cx_t<T> w = tw[k * tstride];
-      const cx_t<T> u = in[j];
-      const cx_t<T> v = cmul(in[j + half], w);
+      const C u = in[j];
+      const C v = cmul(in[j + half], tw[k * tstride]);
       const int j0 = ((j - k) << 1) + k;
       out[j0] = cadd(u, v);
       out[j0 + Ns] = csub(u, v);
     }
     __syncwarp();
-    cx_t<T>* t = in; in = out; out = t;
+    C* t = in; in = out; out = t;
   }
   return in;
 }
