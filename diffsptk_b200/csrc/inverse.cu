@@ -8,11 +8,17 @@
 // (F.fold's order), so the [B, N, L] frame tensor never exists in HBM: 2 (K) * 8 B read + P * 4 B written per
 // frame instead of an extra 2 * L * 4 B round trip.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "rowfft.cuh"
 
 namespace dsb200 {
+
+// Fast fused kernel for fft_length = 512 (istft512.cu); DSB200_E_UNSUPPORTED outside its envelope.
+int istft512_try(const float* Y, const float* w, float* out, int64_t batch, int64_t N, int64_t T_out, int L, int P,
+                 int n, int center, int device, cudaStream_t stream);
+
 namespace {
 
 // One spectrum row Y[0..Nc] (global memory) -> min(out_len, n) real samples dst[j] (* win[j] if win != nullptr).
@@ -237,6 +243,11 @@ int istft_impl(const void* Y, const void* w, void* out, int64_t batch, int64_t N
   DeviceScope ds(device);
   DSB_CUDA(ds.err);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (sizeof(T) == 4 && getenv("DSB200_ISTFT_GENERIC") == nullptr) {
+    const int rc = istft512_try(static_cast<const float*>(Y), static_cast<const float*>(w), static_cast<float*>(out),
+                                batch, N, T_out, L, P, n, center, device, s);
+    if (rc != DSB200_E_UNSUPPORTED) return rc;
+  }
   const void* tw = twiddle_table(device, n, sizeof(T) == 8, s);
   if (tw == nullptr) return fail(DSB200_E_CUDA, "could not build the twiddle table for fft_length=%d", n);
   IstftArgs<T> A{};

@@ -1,0 +1,194 @@
+// Fused inverse STFT for fft_length = 512 (fp32, sm_100a): the mirror image of stft512.cu.
+//
+// Reference: diffsptk/modules/istft.py:186-193 = unframe(ifftr(Y)[..., :L]) (ifftr.py:138-140,
+// unframe.py:164-211).  One CTA (8 warps, two CTAs per SM) owns a tile of consecutive output samples of one
+// utterance and the <= 32 frames that overlap it:
+//   * every half-warp inverse-transforms a PAIR of frames in registers with the forward kernel's packed
+//     radix-16 x 16 machinery (fft16.cuh): the half-length spectrum conj(E + i O) is formed straight from the
+//     global rows (each lane reads the 16 bins k = 16 j + l and their mirrors 256 - k, 128-byte coalesced),
+//     x[2m] + i x[2m+1] = conj(FFT_256(conj(E + i O))) / 512, so no inverse butterflies are needed;
+//   * the samples are multiplied by the synthesis window and parked in shared memory (the [B, N, L] frame tensor
+//     never exists in HBM); after one CTA barrier each thread sums the <= ceil(L / P) contributions of its output
+//     samples in frame order and divides by sum w^2 + 1e-16, writing the waveform once, coalesced.
+// Algorithmic bytes: 2 056 B read + P * 4 B written per frame.
+#include <algorithm>
+
+#include "fft16.cuh"
+
+namespace dsb200 {
+namespace {
+
+using namespace fft16_detail;
+
+constexpr int kIW = 8;                 // warps per CTA
+constexpr int kIT = kIW * 32;
+constexpr int kTileFrames = 4 * kIW;   // frames a CTA can hold: one quad per warp
+
+struct IArgs {
+  const float2* Y;      // [batch, N, 257]
+  const float* w;       // [L]
+  const float2* tw512;  // W512^k, 512 entries
+  float* out;           // [batch, T_out]
+  int64_t batch, N, T_out, tiles_per_utt;
+  int L, P, s, tile, alias;
+};
+
+__global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int l = lane & 15, h = lane >> 4;
+  const int L = A.L;
+
+  float2* tws = reinterpret_cast<float2*>(smem_raw);           // [256] W512^k
+  float* wsm = reinterpret_cast<float*>(tws + 256);            // [512] window / 512 (zero beyond L)
+  float* w2 = wsm + 512;                                       // [512] window^2
+  float2* planes1 = reinterpret_cast<float2*>(w2 + 512);       // [kIW][2 kPlane] exchange planes of half-warp 1
+  float2* planes0 = planes1 + kIW * 2 * kPlane;                // [kIW][2 kPlane] (only when they cannot alias)
+  float* fbuf = reinterpret_cast<float*>(A.alias ? planes0 : planes0 + kIW * 2 * kPlane);   // [32][L]
+
+  for (int i = tid; i < 256; i += kIT) tws[i] = A.tw512[i];
+  for (int i = tid; i < 512; i += kIT) {
+    const float v = i < L ? A.w[i] : 0.0f;
+    wsm[i] = v * (1.0f / 512.0f);
+    w2[i] = v * v;
+  }
+  // per-lane inter-pass twiddles W256^(l k2), as in the forward kernel
+  float twr[16], twi[16];
+#pragma unroll
+  for (int k2 = 1; k2 < 16; ++k2) {
+    const float2 v = A.tw512[2 * l * k2];
+    twr[k2] = v.x;
+    twi[k2] = v.y;
+  }
+  // this half-warp's exchange planes: half-warp 0 borrows the first rows of the warp's own frames in fbuf
+  // (dead until the samples are written, after the last plane read); half-warp 1 has private planes
+  float2* xr = h ? planes1 + warp * 2 * kPlane
+                 : (A.alias ? reinterpret_cast<float2*>(fbuf + static_cast<size_t>(4 * warp) * L)
+                            : planes0 + warp * 2 * kPlane);
+  float2* xi = xr + kPlane;
+  __syncthreads();
+
+  const int64_t n_tiles = A.batch * A.tiles_per_utt;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b = tile / A.tiles_per_utt;
+    const int64_t t0 = (tile - b * A.tiles_per_utt) * A.tile;
+    const int64_t t1 = (t0 + A.tile < A.T_out) ? t0 + A.tile : A.T_out;
+    const int64_t q0 = t0 + A.s, q1 = t1 - 1 + A.s;
+    const int64_t n_lo = (q0 - L + 1 <= 0) ? 0 : (q0 - L + A.P) / A.P;
+    int64_t n_hi = q1 / A.P;
+    if (n_hi > A.N - 1) n_hi = A.N - 1;
+    const int nf = static_cast<int>(n_hi - n_lo + 1);          // <= kTileFrames by the choice of A.tile
+
+    const int fA = 4 * warp + 2 * h;                           // this half-warp's frames within the tile
+    const bool vA = fA < nf, vB = fA + 1 < nf;
+    if (4 * warp < nf) {                                       // warp-uniform: some frame of the quad exists
+      const float2* ya = A.Y + (b * A.N + n_lo + fA) * 257;
+      const float2* yb = ya + 257;
+      C2 a[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int k = 16 * j + l;
+        float2 pa = make_float2(0.0f, 0.0f), qa = pa, pb = pa, qb = pa;   // X[k], X[256 - k] of frames A, B
+        if (vA) { pa = __ldg(ya + k); qa = __ldg(ya + 256 - k); }
+        if (vB) { pb = __ldg(yb + k); qb = __ldg(yb + 256 - k); }
+        if (k == 0) { pa.y = 0.0f; qa.y = 0.0f; pb.y = 0.0f; qb.y = 0.0f; }   // irfft ignores these
+        // E = X[k] + conj X[256-k], D = X[k] - conj X[256-k], O = D conj(W512^k); input conj(E + i O)
+        const float2 Er = add2(make_float2(pa.x, pb.x), make_float2(qa.x, qb.x));
+        const float2 Ei = sub2(make_float2(pa.y, pb.y), make_float2(qa.y, qb.y));
+        const float2 Dr = sub2(make_float2(pa.x, pb.x), make_float2(qa.x, qb.x));
+        const float2 Di = add2(make_float2(pa.y, pb.y), make_float2(qa.y, qb.y));
+        const float2 wv = tws[k];
+        const float2 Or = fma2s(Di, wv.y, mul2s(Dr, wv.x));
+        const float2 Oi = fma2s(Dr, -wv.y, mul2s(Di, wv.x));
+        a[j].re = sub2(Er, Oi);
+        a[j].im = make_float2(-(Ei.x + Or.x), -(Ei.y + Or.y));
+      }
+      fft16<16>(a);
+#pragma unroll
+      for (int k2 = 1; k2 < 16; ++k2) a[dig(k2)] = cmul_s(a[dig(k2)], twr[k2], twi[k2]);
+#pragma unroll
+      for (int k2 = 0; k2 < 16; ++k2) {
+        xr[k2 * kXRow + l] = a[dig(k2)].re;
+        xi[k2 * kXRow + l] = a[dig(k2)].im;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int m1 = 0; m1 < 16; ++m1) {
+        a[m1].re = xr[l * kXRow + m1];
+        a[m1].im = xi[l * kXRow + m1];
+      }
+      __syncwarp();
+      fft16<16>(a);   // a[dig(k1)] = R[16 k1 + l];  x[2m] = Re R[m] / 512, x[2m+1] = -Im R[m] / 512
+      float* rowA = fbuf + static_cast<size_t>(fA) * L;
+      float* rowB = rowA + L;
+#pragma unroll
+      for (int k1 = 0; k1 < 16; ++k1) {
+        const int s = 32 * k1 + 2 * l;
+        if (s < L) {
+          const C2 v = a[dig(k1)];
+          const float w0 = wsm[s], w1 = wsm[s + 1];
+          if (s + 1 < L) {
+            if (vA) *reinterpret_cast<float2*>(rowA + s) = make_float2(v.re.x * w0, -v.im.x * w1);
+            if (vB) *reinterpret_cast<float2*>(rowB + s) = make_float2(v.re.y * w0, -v.im.y * w1);
+          } else {
+            if (vA) rowA[s] = v.re.x * w0;
+            if (vB) rowB[s] = v.re.y * w0;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    // overlap-add, frame order, then the sum-of-squares normalisation (unframe.py:204-206)
+    for (int64_t t = t0 + tid; t < t1; t += kIT) {
+      const int64_t q = t + A.s;
+      int64_t na = (q - L + 1 <= 0) ? 0 : (q - L + A.P) / A.P;
+      int64_t ne = q / A.P;
+      if (ne > A.N - 1) ne = A.N - 1;
+      float num = 0.0f, den = 0.0f;
+      for (int64_t n = na; n <= ne; ++n) {
+        const int j = static_cast<int>(q - n * A.P);
+        num += fbuf[static_cast<size_t>(n - n_lo) * L + j];
+        den += w2[j];
+      }
+      A.out[b * A.T_out + t] = num / (den + 1e-16f);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+// DSB200_E_UNSUPPORTED outside the envelope (fft_length 512, even frame_length in [.., 512], long enough hop).
+int istft512_try(const float* Y, const float* w, float* out, int64_t batch, int64_t N, int64_t T_out, int L, int P,
+                 int n, int center, int device, cudaStream_t stream) {
+  if (n != 512 || L > 512 || (L & 1) || L < 2) return DSB200_E_UNSUPPORTED;
+  int tile = (kTileFrames * P - L + 1) & ~3;   // largest tile whose overlapping frames number <= kTileFrames
+  if (tile < 8 * P) return DSB200_E_UNSUPPORTED;
+  const void* tw = twiddle_table(device, 512, false, stream);
+  if (tw == nullptr) return fail(DSB200_E_CUDA, "could not build the twiddle table for fft_length=512");
+  IArgs A{};
+  A.Y = reinterpret_cast<const float2*>(Y);
+  A.w = w;
+  A.tw512 = static_cast<const float2*>(tw);
+  A.out = out;
+  A.batch = batch;
+  A.N = N;
+  A.T_out = T_out;
+  A.L = L;
+  A.P = P;
+  A.s = center ? L / 2 : 0;
+  A.tile = tile;
+  A.tiles_per_utt = (T_out + tile - 1) / tile;
+  A.alias = (static_cast<size_t>(4) * L * sizeof(float) >= 2 * kPlane * sizeof(float2)) ? 1 : 0;
+  const size_t smem = 256 * sizeof(float2) + 2 * 512 * sizeof(float) +
+                      static_cast<size_t>(kIW) * 2 * kPlane * sizeof(float2) * (A.alias ? 1 : 2) +
+                      static_cast<size_t>(kTileFrames) * L * sizeof(float);
+  if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
+  DSB_CUDA(cudaFuncSetAttribute(istft512_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t n_tiles = batch * A.tiles_per_utt;
+  const int blocks = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count(device)) * 2));
+  istft512_kernel<<<blocks, kIT, smem, stream>>>(A);
+  return after_launch("istft512_kernel");
+}
+
+}  // namespace dsb200

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(256) rowfft_kernel(RowArgs<T> A) {
 
   // block-shared twiddles, then per-warp buffers
   C* tw = reinterpret_cast<C*>(smem_raw);
-  const int n_tw = A.pow2 ? Nc : n;
+  const int n_tw = n;   // the radix-4 passes index up to 3/4 of the circle, the direct DFT all of it
   for (int i = threadIdx.x; i < n_tw; i += blockDim.x) tw[i] = reinterpret_cast<const C*>(A.tw)[i];
   __syncthreads();
   C* buf0 = tw + n_tw + static_cast<size_t>(warp) * (2 * K) ;
@@ -204,7 +204,7 @@ int launch_rowfft(RowArgs<T>& A, int device, cudaStream_t stream) {
   if (tw == nullptr) return fail(DSB200_E_CUDA, "could not build the twiddle table for fft_length=%d", A.n);
   A.tw = static_cast<const T*>(tw);
   const int K = A.Nc + 1;
-  const size_t tw_bytes = static_cast<size_t>(A.pow2 ? A.Nc : A.n) * 2 * sizeof(T);
+  const size_t tw_bytes = static_cast<size_t>(A.n) * 2 * sizeof(T);
   const size_t per_warp = static_cast<size_t>(2 * K) * 2 * sizeof(T) + static_cast<size_t>(K) * sizeof(T);
   const size_t cap = static_cast<size_t>(max_dynamic_smem(device));
   if (tw_bytes + per_warp > cap)

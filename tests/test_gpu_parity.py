@@ -356,13 +356,30 @@ def test_istft_against_oracle_and_roundtrip(prec):
                       ((2, 2, 9, 33), dict(frame_length=50, frame_period=20, fft_length=64, window="hamming")),
                       ((2, 11, 21), dict(frame_length=40, frame_period=40, fft_length=40, window="rectangular",
                                          norm="none", center=False)),
-                      ((1, 300, 257), dict(out_length=23000, window="hanning", norm="magnitude"))):
+                      ((1, 300, 257), dict(out_length=23000, window="hanning", norm="magnitude")),
+                      # fft_length 512 takes the register-FFT kernel (istft512.cu) when fp32: other hops / lengths
+                      ((2, 50, 257), dict(frame_length=320, frame_period=160, window="hamming")),
+                      ((2, 40, 257), dict(frame_length=512, frame_period=128, center=False, window="hamming",
+                                          norm="none")),
+                      ((3, 70, 257), dict(frame_length=100, frame_period=50, window="rectangular")),
+                      ((1, 60, 257), dict(frame_length=400, frame_period=10)),      # hop too short: general kernel
+                      ((2, 1, 257), dict(frame_length=400, frame_period=80, out_length=50))):
         Y = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(cdt)
         F.istft(to_dev(Y, prec), **kw)          # first use of an FFT length also builds its twiddle table
         n0 = _native.launch_count()
         got = to_np(F.istft(to_dev(Y, prec), **kw))
         assert _native.launch_count() - n0 == 1, "ISTFT must be one fused kernel"
         H.assert_close(got, O.istft(Y.astype(np.complex128), **kw), prec, what=f"istft {shape} {kw}", scale_atol=True)
+    if prec == "f32":   # the two fp32 kernels agree with each other far inside the oracle tolerance
+        import os
+        Y = to_dev((rng.standard_normal((3, 90, 257)) + 1j * rng.standard_normal((3, 90, 257))).astype(cdt), prec)
+        fast = F.istft(Y)
+        os.environ["DSB200_ISTFT_GENERIC"] = "1"
+        try:
+            slow = F.istft(Y)
+        finally:
+            del os.environ["DSB200_ISTFT_GENERIC"]
+        assert float((fast - slow).abs().max()) < 1e-5 * float(slow.abs().max())
     x = torch.randn(7, 12345, device=dev(), dtype=TD[prec], generator=torch.Generator(device=dev()).manual_seed(1))
     for kw in (dict(), dict(frame_length=400, frame_period=100, fft_length=400, window="hamming"),
                dict(frame_length=63, frame_period=16, fft_length=64, window="sine", norm="none")):
