@@ -31,6 +31,7 @@ struct IArgs {
   float* out;           // [batch, T_out]
   int64_t batch, N, T_out, tiles_per_utt;
   int L, P, s, tile, alias;
+  int c, m;             // (L - 1) / P and (L - 1) % P
 };
 
 __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
@@ -138,19 +139,32 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
       }
     }
     __syncthreads();
-    // overlap-add, frame order, then the sum-of-squares normalisation (unframe.py:204-206)
-    for (int64_t t = t0 + tid; t < t1; t += kIT) {
-      const int64_t q = t + A.s;
-      int64_t na = (q - L + 1 <= 0) ? 0 : (q - L + A.P) / A.P;
-      int64_t ne = q / A.P;
-      if (ne > A.N - 1) ne = A.N - 1;
-      float num = 0.0f, den = 0.0f;
-      for (int64_t n = na; n <= ne; ++n) {
-        const int j = static_cast<int>(q - n * A.P);
-        num += fbuf[static_cast<size_t>(n - n_lo) * L + j];
-        den += w2[j];
+    // Overlap-add in frame order, then the sum-of-squares normalisation (unframe.py:204-206).  All index
+    // arithmetic is 32-bit and incremental: one division per thread and tile, none per sample.
+    {
+      const int P = A.P, Nm1 = static_cast<int>(A.N) - 1, nlo = static_cast<int>(n_lo);
+      const int cnt = static_cast<int>(t1 - t0);
+      const int q_first = static_cast<int>(q0) + tid;
+      int ne = q_first / P, r = q_first - ne * P;          // frame whose start is at or before q, offset in it
+      const int dq = kIT / P, dr = kIT - dq * P;           // advance of (ne, r) per kIT samples
+      float* outp = A.out + b * A.T_out + t0;
+      for (int i = tid; i < cnt; i += kIT) {
+        // frames n with 0 <= q - n P <= L - 1:  n in [ne - c + (r > m), ne], c = (L-1) / P, m = (L-1) % P
+        int na = ne - A.c + (r > A.m ? 1 : 0);
+        if (na < 0) na = 0;
+        const int nb = ne < Nm1 ? ne : Nm1;
+        int j = r + (ne - na) * P;                         // q - na P
+        const float* fp = fbuf + (na - nlo) * L + j;
+        float num = 0.0f, den = 0.0f;
+        for (int n = na; n <= nb; ++n, fp += L - P, j -= P) {
+          num += *fp;
+          den += w2[j];
+        }
+        outp[i] = num / (den + 1e-16f);
+        ne += dq;
+        r += dr;
+        if (r >= P) { r -= P; ++ne; }
       }
-      A.out[b * A.T_out + t] = num / (den + 1e-16f);
     }
     __syncthreads();
   }
@@ -162,6 +176,7 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
 int istft512_try(const float* Y, const float* w, float* out, int64_t batch, int64_t N, int64_t T_out, int L, int P,
                  int n, int center, int device, cudaStream_t stream) {
   if (n != 512 || L > 512 || (L & 1) || L < 2) return DSB200_E_UNSUPPORTED;
+  if (T_out + L >= (int64_t{1} << 30) || N >= (int64_t{1} << 30)) return DSB200_E_UNSUPPORTED;   // 32-bit sample indices
   int tile = (kTileFrames * P - L + 1) & ~3;   // largest tile whose overlapping frames number <= kTileFrames
   if (tile < 8 * P) return DSB200_E_UNSUPPORTED;
   const void* tw = twiddle_table(device, 512, false, stream);
@@ -178,6 +193,8 @@ int istft512_try(const float* Y, const float* w, float* out, int64_t batch, int6
   A.P = P;
   A.s = center ? L / 2 : 0;
   A.tile = tile;
+  A.c = (L - 1) / P;
+  A.m = (L - 1) % P;
   A.tiles_per_utt = (T_out + tile - 1) / tile;
   A.alias = (static_cast<size_t>(4) * L * sizeof(float) >= 2 * kPlane * sizeof(float2)) ? 1 : 0;
   const size_t smem = 256 * sizeof(float2) + 2 * 512 * sizeof(float) +
