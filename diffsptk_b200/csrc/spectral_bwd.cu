@@ -11,6 +11,7 @@
 // as one length-n complex FFT, multiplies by the window, removes the mean (zmean) and scatters the frame
 // back into the waveform gradient with atomics -- the adjoint of padding + unfold, for all four pad modes.
 #include <algorithm>
+#include <cstdlib>
 
 #include "rowfft.cuh"
 
@@ -288,6 +289,14 @@ int check_common(const dsb200_frame_params* f, int64_t T_len) {
   return DSB200_OK;
 }
 
+}  // namespace
+
+// Fused backward for the BASELINE shape (stft512_bwd.cu); DSB200_E_UNSUPPORTED outside its envelope.
+int stft512_bwd_try(const float* x, const float* window, const float* gy, float* gx, int64_t batch, int64_t T_len,
+                    const dsb200_stft_params* p, int device, cudaStream_t stream);
+
+namespace {
+
 template <typename T>
 int stft_bwd_impl(const void* x, const void* window, const void* gy, void* gx, void* gw, int64_t batch, int64_t T_len,
                   const dsb200_stft_params* p, int device, void* stream) {
@@ -299,6 +308,11 @@ int stft_bwd_impl(const void* x, const void* window, const void* gy, void* gx, v
   DeviceScope ds(device);
   DSB_CUDA(ds.err);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (sizeof(T) == 4 && gw == nullptr && getenv("DSB200_STFT_BWD_GENERIC") == nullptr) {
+    const int rc = stft512_bwd_try(static_cast<const float*>(x), static_cast<const float*>(window),
+                                   static_cast<const float*>(gy), static_cast<float*>(gx), batch, T_len, p, device, s);
+    if (rc != DSB200_E_UNSUPPORTED) return rc;
+  }
   DSB_CUDA(cudaMemsetAsync(gx, 0, static_cast<size_t>(batch) * T_len * sizeof(T), s));
   if (gw) DSB_CUDA(cudaMemsetAsync(gw, 0, static_cast<size_t>(p->frame.frame_length) * sizeof(T), s));
   BwdArgs<T> A{};

@@ -298,3 +298,43 @@ def test_fused_waveform_pipelines_are_differentiable():
         (ref,) = _ref_vjp(ref_mfcc, (xr,), ws)
         scale = float(ref.abs().max())
         assert torch.allclose(gx.double() / scale, ref / scale, **tol), ("mfcc_wave", dt)
+
+
+@pytest.mark.parametrize("fmt", ["power", "db", "log-magnitude", "magnitude"])
+def test_fused_stft_backward_kernel(fmt):
+    """stft512_bwd.cu (one kernel, no atomics) against the general adjoint kernel and torch autograd of the composite."""
+    import os
+
+    import diffsptk_b200.functional as F
+    from diffsptk_b200 import _native
+    d = dev()
+    g = torch.Generator().manual_seed(23)
+    for T, kw in ((9000, dict()), (1234, dict(frame_length=320, frame_period=160, window="hamming")),
+                  (4001, dict(frame_length=512, frame_period=128, center=False, window="hanning", norm="none")),
+                  (700, dict(frame_length=400, frame_period=80)), (90, dict(frame_length=100, frame_period=50))):
+        x64 = torch.randn(3, T, generator=g, dtype=torch.float64)
+        fl, fp = kw.get("frame_length", 400), kw.get("frame_period", 80)
+
+        def run(x):
+            y = F.stft(x, fft_length=512, eps=1e-3, out_format=fmt, **kw)
+            w = torch.randn(y.shape, generator=torch.Generator().manual_seed(1), dtype=torch.float64).to(d)
+            (gx,) = torch.autograd.grad((y.double() * w).sum(), x)
+            return gx, w
+        x = x64.to(d, torch.float32).requires_grad_(True)
+        F.stft(x.detach(), fft_length=512, **kw)          # warm the twiddle cache
+        n0 = _native.launch_count()
+        fast, w = run(x)
+        assert _native.launch_count() - n0 == 2, "one forward and one backward kernel"
+        os.environ["DSB200_STFT_BWD_GENERIC"] = "1"
+        try:
+            slow, _ = run(x)
+        finally:
+            del os.environ["DSB200_STFT_BWD_GENERIC"]
+        xr = x64.to(d).requires_grad_(True)
+        win = F.window(torch.ones(fl, dtype=torch.float64, device=d), None, window=kw.get("window", "blackman"),
+                       norm=kw.get("norm", "power"))
+        yr = composite_stft(xr, win, fl, fp, 512, kw.get("center", True), False, "constant", 1e-3, None, fmt)
+        (ref,) = torch.autograd.grad((yr * w).sum(), xr)
+        scale = float(ref.abs().max())
+        assert float((fast.double() - ref).abs().max()) < 2e-3 * scale, (fmt, T, kw)
+        assert float((fast - slow).abs().max()) < 2e-4 * scale, (fmt, T, kw)
