@@ -13,6 +13,19 @@ constexpr int kXRow = 17;                              // float2 units per trans
 constexpr int kPlane = 16 * kXRow;                     // float2 units per plane
 constexpr int kXchBytesPerWarp = 2 * 2 * kPlane * 8;   // 2 half-warps x (re, im) planes = 8704 B
 
+// Hint the L2 to fetch [p, p + bytes) of a global tensor spanning [base, base + total): the range is shrunk to
+// 16-byte boundaries inside the tensor (cp.async.bulk.prefetch.L2 needs aligned address and size).
+__device__ __forceinline__ void prefetch_l2(const void* base, size_t total, const void* p, size_t bytes) {
+  const uintptr_t lo0 = reinterpret_cast<uintptr_t>(base), hi0 = lo0 + total;
+  uintptr_t lo = reinterpret_cast<uintptr_t>(p), hi = lo + bytes;
+  if (lo < lo0) lo = lo0;
+  if (hi > hi0) hi = hi0;
+  lo = (lo + 15) & ~static_cast<uintptr_t>(15);
+  hi &= ~static_cast<uintptr_t>(15);
+  if (hi > lo)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(lo), "r"(static_cast<uint32_t>(hi - lo)) : "memory");
+}
+
 struct C2 {  // one complex value for each of the two frames of a pair
   float2 re, im;
 };

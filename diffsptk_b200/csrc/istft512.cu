@@ -79,6 +79,13 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
     int64_t n_hi = q1 / A.P;
     if (n_hi > A.N - 1) n_hi = A.N - 1;
     const int nf = static_cast<int>(n_hi - n_lo + 1);          // <= kTileFrames by the choice of A.tile
+    if (tid == 0 && tile + gridDim.x < n_tiles) {              // pull the next tile's spectra into the L2 now
+      const int64_t tn = tile + gridDim.x, bn = tn / A.tiles_per_utt;
+      const int64_t qn = (tn - bn * A.tiles_per_utt) * A.tile + A.s;
+      const int64_t nl = (qn - L + 1 <= 0) ? 0 : (qn - L + A.P) / A.P;
+      prefetch_l2(A.Y, static_cast<size_t>(A.batch) * A.N * 257 * sizeof(float2), A.Y + (bn * A.N + nl) * 257,
+                  static_cast<size_t>(kTileFrames) * 257 * sizeof(float2));
+    }
 
     const int fA = 4 * warp + 2 * h;                           // this half-warp's frames within the tile
     const bool vA = fA < nf, vB = fA + 1 < nf;

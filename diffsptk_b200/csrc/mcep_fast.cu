@@ -23,6 +23,11 @@
 namespace dsb200 {
 namespace {
 
+#ifndef MCEP_Q
+#define MCEP_Q 4
+#endif
+constexpr int kQ = MCEP_Q;           // packed frame pairs eliminated per pass (4: all 8 frames at once; or 2)
+constexpr int kH = kQ / 2;           // float4 groups (two pairs each) exchanged through shared memory
 constexpr int kMW = 8;               // warps per CTA (2 per scheduler -> 255 registers per thread)
 constexpr int kMT = kMW * 32;
 constexpr int kKT = 9;               // bins per lane: k = lane + 32 t
@@ -206,15 +211,17 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
       }
       __syncwarp();
 
-      // ---- Newton systems of all 8 frames (4 packed pairs) in one pass: lane = row ---------------------
-      {
+      // ---- Newton systems, kQ packed frame pairs per pass (default: all 8 frames in one pass): lane = row ----
+#pragma unroll 1
+      for (int pass = 0; pass < 4 / kQ; ++pass) {
         const int i = lane;
-        float2 a[4][kDM], b[4];
+        const float2* rt0 = rts + pass * kQ * kJS;
+        float2 a[kQ][kDM], b[kQ];
         if (i < D) {
           const float alpha_i = avs[i];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2* rt = rts + q * kJS;
+          for (int q = 0; q < kQ; ++q) {
+            const float2* rt = rt0 + q * kJS;
 #pragma unroll
             for (int c = 0; c < kDM; ++c) {
               const int d = i > c ? i - c : c - i;
@@ -227,48 +234,54 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
           // never pivots): the elimination can then run all 25 pivots unconditionally -- no run-time
           // `pv < D` tests, which the compiler otherwise keeps as a bit mask of 50 predicates.
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < kQ; ++q) {
 #pragma unroll
             for (int c = 0; c < kDM; ++c) a[q][c] = f2(c == i ? 1.0f : 0.0f, c == i ? 1.0f : 0.0f);
             b[q] = f2(0, 0);
           }
         }
         // Elimination.  The sub-matrix stays symmetric, so pivot-row entry c == column entry held by lane c:
-        // one parallel store publishes the whole pivot row.
-        float2 dinv[4] = {f2(1, 1), f2(1, 1), f2(1, 1), f2(1, 1)};   // 1 / (this lane's own pivot)
+        // one parallel store publishes the whole pivot row (float4 = two frame pairs).
+        float2 dinv[kQ];                                   // 1 / (this lane's own pivot)
+#pragma unroll
+        for (int q = 0; q < kQ; ++q) dinv[q] = f2(1, 1);
         static_for<0, kDM>([&](auto pv_c) {
           constexpr int pv = decltype(pv_c)::value;
-          col[lane] = make_float4(a[0][pv].x, a[0][pv].y, a[1][pv].x, a[1][pv].y);
-          col[32 + lane] = make_float4(a[2][pv].x, a[2][pv].y, a[3][pv].x, a[3][pv].y);
+#pragma unroll
+          for (int g = 0; g < kH; ++g)
+            col[32 * g + lane] = make_float4(a[2 * g][pv].x, a[2 * g][pv].y, a[2 * g + 1][pv].x, a[2 * g + 1][pv].y);
           if (lane == pv) {
-            pb[0] = make_float4(b[0].x, b[0].y, b[1].x, b[1].y);
-            pb[1] = make_float4(b[2].x, b[2].y, b[3].x, b[3].y);
+#pragma unroll
+            for (int g = 0; g < kH; ++g) pb[g] = make_float4(b[2 * g].x, b[2 * g].y, b[2 * g + 1].x, b[2 * g + 1].y);
           }
           __syncwarp();
-          const float4 p01 = col[pv], p23 = col[32 + pv];
-          const float2 r[4] = {f2(fast_rcp(p01.x), fast_rcp(p01.y)), f2(fast_rcp(p01.z), fast_rcp(p01.w)),
-                               f2(fast_rcp(p23.x), fast_rcp(p23.y)), f2(fast_rcp(p23.z), fast_rcp(p23.w))};
           const bool act = i > pv;                 // identity / zero rows hold a zero here: factor 0
-          float2 f[4];
+          float2 f[kQ];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            f[q] = act ? __fmul2_rn(a[q][pv], f2(-r[q].x, -r[q].y)) : f2(0, 0);   // -a_ip / a_pp
-            dinv[q] = sel2(lane == pv, r[q], dinv[q]);
+          for (int g = 0; g < kH; ++g) {
+            const float4 p = col[32 * g + pv];
+            const float2 r0 = f2(fast_rcp(p.x), fast_rcp(p.y)), r1 = f2(fast_rcp(p.z), fast_rcp(p.w));
+            f[2 * g] = act ? __fmul2_rn(a[2 * g][pv], f2(-r0.x, -r0.y)) : f2(0, 0);       // -a_ip / a_pp
+            f[2 * g + 1] = act ? __fmul2_rn(a[2 * g + 1][pv], f2(-r1.x, -r1.y)) : f2(0, 0);
+            dinv[2 * g] = sel2(lane == pv, r0, dinv[2 * g]);
+            dinv[2 * g + 1] = sel2(lane == pv, r1, dinv[2 * g + 1]);
           }
           if constexpr (pv < kDM - 1) {
 #pragma unroll
             for (int c = pv + 1; c < kDM; ++c) {
-              const float4 c01 = col[c], c23 = col[32 + c];
-              a[0][c] = __ffma2_rn(f[0], f2(c01.x, c01.y), a[0][c]);
-              a[1][c] = __ffma2_rn(f[1], f2(c01.z, c01.w), a[1][c]);
-              a[2][c] = __ffma2_rn(f[2], f2(c23.x, c23.y), a[2][c]);
-              a[3][c] = __ffma2_rn(f[3], f2(c23.z, c23.w), a[3][c]);
+#pragma unroll
+              for (int g = 0; g < kH; ++g) {
+                const float4 cv = col[32 * g + c];
+                a[2 * g][c] = __ffma2_rn(f[2 * g], f2(cv.x, cv.y), a[2 * g][c]);
+                a[2 * g + 1][c] = __ffma2_rn(f[2 * g + 1], f2(cv.z, cv.w), a[2 * g + 1][c]);
+              }
             }
-            const float4 b01 = pb[0], b23 = pb[1];
-            b[0] = __ffma2_rn(f[0], f2(b01.x, b01.y), b[0]);
-            b[1] = __ffma2_rn(f[1], f2(b01.z, b01.w), b[1]);
-            b[2] = __ffma2_rn(f[2], f2(b23.x, b23.y), b[2]);
-            b[3] = __ffma2_rn(f[3], f2(b23.z, b23.w), b[3]);
+#pragma unroll
+            for (int g = 0; g < kH; ++g) {
+              const float4 bv = pb[g];
+              b[2 * g] = __ffma2_rn(f[2 * g], f2(bv.x, bv.y), b[2 * g]);
+              b[2 * g + 1] = __ffma2_rn(f[2 * g + 1], f2(bv.z, bv.w), b[2 * g + 1]);
+            }
           }
           __syncwarp();
         });
@@ -277,30 +290,32 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
         static_for<0, kDM>([&](auto cc) {
           constexpr int c = kDM - 1 - decltype(cc)::value;
           if (lane == c) {
-            float2 x[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) x[q] = __fmul2_rn(b[q], dinv[q]);
-            xs[c] = make_float4(x[0].x, x[0].y, x[1].x, x[1].y);
-            xs[32 + c] = make_float4(x[2].x, x[2].y, x[3].x, x[3].y);
+            for (int g = 0; g < kH; ++g) {
+              const float2 x0 = __fmul2_rn(b[2 * g], dinv[2 * g]), x1 = __fmul2_rn(b[2 * g + 1], dinv[2 * g + 1]);
+              xs[32 * g + c] = make_float4(x0.x, x0.y, x1.x, x1.y);
+            }
           }
           __syncwarp();
           if (i < c) {
-            const float4 x01 = xs[c], x23 = xs[32 + c];
-            b[0] = __ffma2_rn(a[0][c], f2(-x01.x, -x01.y), b[0]);
-            b[1] = __ffma2_rn(a[1][c], f2(-x01.z, -x01.w), b[1]);
-            b[2] = __ffma2_rn(a[2][c], f2(-x23.x, -x23.y), b[2]);
-            b[3] = __ffma2_rn(a[3][c], f2(-x23.z, -x23.w), b[3]);
+#pragma unroll
+            for (int g = 0; g < kH; ++g) {
+              const float4 xv = xs[32 * g + c];
+              b[2 * g] = __ffma2_rn(a[2 * g][c], f2(-xv.x, -xv.y), b[2 * g]);
+              b[2 * g + 1] = __ffma2_rn(a[2 * g + 1][c], f2(-xv.z, -xv.w), b[2 * g + 1]);
+            }
           }
         });
         __syncwarp();
-        if (i < D) {  // mc += g
-          float4* mp = reinterpret_cast<float4*>(mcs + i * 8);
-          const float4 g0 = xs[i], g1 = xs[32 + i];
-          float4 m0 = mp[0], m1 = mp[1];
-          m0.x += g0.x; m0.y += g0.y; m0.z += g0.z; m0.w += g0.w;
-          m1.x += g1.x; m1.y += g1.y; m1.z += g1.z; m1.w += g1.w;
-          mp[0] = m0;
-          mp[1] = m1;
+        if (i < D) {  // mc += g for the frames of this pass
+          float4* mp = reinterpret_cast<float4*>(mcs + i * 8 + pass * kQ * 2);
+#pragma unroll
+          for (int g = 0; g < kH; ++g) {
+            const float4 gv = xs[32 * g + i];
+            float4 m = mp[g];
+            m.x += gv.x; m.y += gv.y; m.z += gv.z; m.w += gv.w;
+            mp[g] = m;
+          }
         }
         __syncwarp();
       }

@@ -93,6 +93,15 @@ __global__ void __launch_bounds__(kBT, 2) stft512_bwd_kernel(const BArgs A) {
     if (n_hi > A.N - 1) n_hi = A.N - 1;
     const int nf = static_cast<int>(n_hi - n_lo + 1);          // <= kBFrames by the choice of A.tile (may be <= 0)
 
+    if (tid == 0 && tile + gridDim.x < n_tiles) {              // pull the next tile's inputs into the L2 now
+      const int64_t tn = tile + gridDim.x, bn = tn / A.tiles_per_utt;
+      const int64_t qn = (tn - bn * A.tiles_per_utt) * A.tile + A.left;
+      const int64_t nl = (qn - L + 1 <= 0) ? 0 : (qn - L + A.P) / A.P;
+      prefetch_l2(A.gy, static_cast<size_t>(A.batch) * A.N * 257 * sizeof(float), A.gy + (bn * A.N + nl) * 257,
+                  static_cast<size_t>(kBFrames) * 257 * sizeof(float));
+      prefetch_l2(A.x, static_cast<size_t>(A.batch) * A.T * sizeof(float), A.x + bn * A.T + nl * A.P - A.left,
+                  static_cast<size_t>(A.span) * sizeof(float));
+    }
     // stage the samples of frames n_lo .. n_lo + 31 (constant padding outside the utterance)
     {
       const float* xb = A.x + b * A.T;

@@ -97,3 +97,96 @@ def lpc_wave_model(frame, M, eps):
     out = a.copy()
     out[0] = np.sqrt(r[0] + np.dot(r[1:], a[1:]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# istft512.cu / stft512_bwd.cu: lane-level data flow of the synthesis half.  The 256-point FFT itself is the
+# forward kernel's (modelled above); what is new is how its input conj(E + i O) is built from the spectrum rows,
+# how the outputs map back to samples, how the backward kernel forms G = g X in the split domain and returns
+# the mirrored bins to their owner lanes, and the incremental overlap-add indexing.
+def istft512_frame_model(X):
+    """One frame: X[0..256] complex -> 512 real samples, mirroring istft512_kernel's steps A and C."""
+    tw = np.exp(-2j * np.pi * np.arange(512) / 512)
+    c = np.zeros(256, complex)
+    for l in range(16):           # lane within the half-warp
+        for j in range(16):       # register
+            k = 16 * j + l
+            a, b = X[k], X[256 - k]
+            if k == 0:            # irfft ignores the imaginary parts of the DC and Nyquist bins
+                a, b = complex(a.real, 0), complex(b.real, 0)
+            b = np.conj(b)
+            E, D = a + b, a - b
+            wr, wi = tw[k].real, tw[k].imag
+            Or, Oi = D.real * wr + D.imag * wi, D.imag * wr - D.real * wi     # O = D conj(W512^k)
+            c[16 * j + l] = complex(E.real - Oi, -(E.imag + Or))              # conj(E + i O)
+    R = np.fft.fft(c)
+    x = np.zeros(512)
+    for l in range(16):
+        for k1 in range(16):
+            m = 16 * k1 + l
+            x[2 * m], x[2 * m + 1] = R[m].real / 512, -R[m].imag / 512
+    return x
+
+
+def stft512_bwd_frame_model(xw, g):
+    """Gradient of sum(g * |rfft(xw)|^2) wrt the 512 windowed samples, mirroring stft512_bwd_kernel's data flow
+    (split, G = g X, inverse split, mirrored halves returned by shuffle with lane 0's special cases)."""
+    tw = np.exp(-2j * np.pi * np.arange(512) / 512)
+    Z = np.fft.fft(xw[0::2] + 1j * xw[1::2])          # Z[16 k1 + l] lives in lane l, register k1
+    c = np.zeros(256, complex)
+    received = {}
+    for l in range(16):
+        cm = {}
+        for k1 in range(8):
+            k, kp = 16 * k1 + l, 256 - (16 * k1 + l)
+            z = Z[k]
+            m = Z[0] if (l == 0 and k1 == 0) else Z[kp % 256]
+            sr, dr, si, di = z.real + m.real, z.real - m.real, z.imag + m.imag, z.imag - m.imag
+            wr, wi = tw[k].real, tw[k].imag
+            tr, ti = 0.5 * (dr * wi + si * wr), 0.5 * (-dr * wr + si * wi)
+            Xk, Xm = complex(0.5 * sr + tr, 0.5 * di + ti), complex(0.5 * sr - tr, -0.5 * di + ti)
+            Gk, Gm = g[k] * Xk, g[kp] * Xm            # the factor 2 of d|X|^2 is folded into the final scale
+            if k == 0:
+                Gk, Gm = complex(2 * Gk.real, 0), complex(2 * Gm.real, 0)
+            Er, Ei, Dr, Di = Gk.real + Gm.real, Gk.imag - Gm.imag, Gk.real - Gm.real, Gk.imag + Gm.imag
+            Or, Oi = Dr * wr + Di * wi, Di * wr - Dr * wi
+            c[k] = complex(Er - Oi, -(Ei + Or))
+            cm[k1] = complex(Er + Oi, Ei - Or)        # c[256 - k], owned by lane 16 - l
+        c128 = None
+        if l == 0:
+            G128 = g[128] * np.conj(Z[128])
+            c128 = complex(2 * G128.real, 2 * G128.imag)
+        for j in range(8):                            # shuffle step j: the receiver stores into register 8 + j
+            s = cm[7 - j]
+            if l == 0:
+                s = c128 if j == 0 else cm[8 - j]
+            received[((16 - l) % 16, 8 + j)] = s
+    for (lane, reg), v in received.items():
+        c[16 * reg + lane] = v
+    R = np.fft.fft(c)
+    out = np.zeros(512)
+    for l in range(16):
+        for k1 in range(16):
+            m = 16 * k1 + l
+            out[2 * m], out[2 * m + 1] = R[m].real, -R[m].imag
+    return out
+
+
+def overlap_add_ranges_model(L, P, N, s, T_out, tile, threads=256):
+    """Yield (q, na, nb, j) per output sample from the incremental indexing of the fused kernels' gather loop."""
+    c, m = (L - 1) // P, (L - 1) % P
+    for t0 in range(0, T_out, tile):
+        t1, q0 = min(t0 + tile, T_out), t0 + s
+        for tid in range(threads):
+            q_first = q0 + tid
+            ne, r = q_first // P, q_first % P
+            dq, dr = threads // P, threads % P
+            i = tid
+            while i < t1 - t0:
+                na = max(ne - c + (1 if r > m else 0), 0)
+                nb = min(ne, N - 1)
+                yield q0 + i, na, nb, r + (ne - na) * P
+                ne, r = ne + dq, r + dr
+                if r >= P:
+                    r, ne = r - P, ne + 1
+                i += threads

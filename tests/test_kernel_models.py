@@ -27,3 +27,36 @@ def test_lpc_wave_model_matches_oracle():
     want = O.lpc(fr, 24, eps=1e-5)
     got = np.stack([KM.lpc_wave_model(f, 24, 1e-5) for f in fr])
     np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)
+
+
+def test_istft512_lane_model_matches_oracle():
+    rng = np.random.default_rng(3)
+    Y = rng.standard_normal((4, 257)) + 1j * rng.standard_normal((4, 257))
+    want = O.ifftr(Y)
+    got = np.stack([KM.istft512_frame_model(y) for y in Y])
+    np.testing.assert_allclose(got, want, rtol=1e-11, atol=1e-12)
+
+
+def test_stft512_bwd_lane_model_matches_the_adjoint():
+    rng = np.random.default_rng(4)
+    xw = rng.standard_normal(512)
+    xw[400:] = 0
+    g = rng.standard_normal(257)
+    G = 2 * g * np.fft.rfft(xw)
+    kk = np.arange(257)
+    want = np.array([np.real(np.sum(np.conj(G) * np.exp(-2j * np.pi * j * kk / 512))) for j in range(512)])
+    np.testing.assert_allclose(KM.stft512_bwd_frame_model(xw, g), want, rtol=1e-9, atol=1e-9)
+    # and it is the gradient: finite differences of sum(g |X|^2)
+    f = lambda v: float(np.sum(g * np.abs(np.fft.rfft(v)) ** 2))  # noqa: E731
+    for j in (0, 7, 399):
+        e = np.zeros(512)
+        e[j] = 1e-6
+        assert abs((f(xw + e) - f(xw - e)) / 2e-6 - want[j]) < 1e-4 * max(1.0, abs(want[j]))
+
+
+def test_overlap_add_incremental_indexing():
+    for L, P, N, s, T_out, tile in ((400, 80, 30, 200, 2300, 2160), (100, 50, 7, 0, 399, 1500), (6, 4, 9, 3, 35, 8),
+                                    (512, 128, 5, 256, 600, 3584), (398, 7, 11, 0, 400, 64)):
+        for q, na, nb, j in KM.overlap_add_ranges_model(L, P, N, s, T_out, tile):
+            a_ref = 0 if q - L + 1 <= 0 else (q - L + P) // P
+            assert (na, nb) == (a_ref, min(q // P, N - 1)) and j == q - na * P
