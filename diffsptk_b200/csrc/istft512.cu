@@ -31,6 +31,7 @@ struct IArgs {
   float* out;           // [batch, T_out]
   int64_t batch, N, T_out, tiles_per_utt;
   int L, P, s, tile, alias;
+  int fbuf_off;         // float2 units from the second plane array to the frame rows (0 when they alias)
   int c, m;             // (L - 1) / P and (L - 1) % P
 };
 
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
   float* w2 = wsm + 512;                                       // [512] window^2
   float2* planes1 = reinterpret_cast<float2*>(w2 + 512);       // [kIW][2 kPlane] exchange planes of half-warp 1
   float2* planes0 = planes1 + kIW * 2 * kPlane;                // [kIW][2 kPlane] (only when they cannot alias)
-  float* fbuf = reinterpret_cast<float*>(A.alias ? planes0 : planes0 + kIW * 2 * kPlane);   // [32][L]
+  float* fbuf = reinterpret_cast<float*>(planes0 + A.fbuf_off);                              // [32][L]
 
   for (int i = tid; i < 256; i += kIT) tws[i] = A.tw512[i];
   for (int i = tid; i < 512; i += kIT) {
@@ -101,10 +102,9 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
         if (vB) { pb = __ldg(yb + k); qb = __ldg(yb + 256 - k); }
         if (k == 0) { pa.y = 0.0f; qa.y = 0.0f; pb.y = 0.0f; qb.y = 0.0f; }   // irfft ignores these
         // E = X[k] + conj X[256-k], D = X[k] - conj X[256-k], O = D conj(W512^k); input conj(E + i O)
-        const float2 Er = add2(make_float2(pa.x, pb.x), make_float2(qa.x, qb.x));
-        const float2 Ei = sub2(make_float2(pa.y, pb.y), make_float2(qa.y, qb.y));
-        const float2 Dr = sub2(make_float2(pa.x, pb.x), make_float2(qa.x, qb.x));
-        const float2 Di = add2(make_float2(pa.y, pb.y), make_float2(qa.y, qb.y));
+        // scalar adds write the (frame A, frame B) halves in place: cheaper than packing the loaded values first
+        const float2 Er = make_float2(pa.x + qa.x, pb.x + qb.x), Ei = make_float2(pa.y - qa.y, pb.y - qb.y);
+        const float2 Dr = make_float2(pa.x - qa.x, pb.x - qb.x), Di = make_float2(pa.y + qa.y, pb.y + qb.y);
         const float2 wv = tws[k];
         const float2 Or = fma2s(Di, wv.y, mul2s(Dr, wv.x));
         const float2 Oi = fma2s(Dr, -wv.y, mul2s(Di, wv.x));
@@ -156,16 +156,19 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
       const int dq = kIT / P, dr = kIT - dq * P;           // advance of (ne, r) per kIT samples
       float* outp = A.out + b * A.T_out + t0;
       for (int i = tid; i < cnt; i += kIT) {
-        // frames n with 0 <= q - n P <= L - 1:  n in [ne - c + (r > m), ne], c = (L-1) / P, m = (L-1) % P
+        // frames n with 0 <= q - n P <= L - 1:  n in [ne - c + (r > m), ne], c = (L-1) / P, m = (L-1) % P.
+        // The loop runs c + 1 times for every lane (no divergence); out-of-range frames are predicated off.
         int na = ne - A.c + (r > A.m ? 1 : 0);
         if (na < 0) na = 0;
         const int nb = ne < Nm1 ? ne : Nm1;
-        int j = r + (ne - na) * P;                         // q - na P
-        const float* fp = fbuf + (na - nlo) * L + j;
+        int n = ne, j = r;
+        const float* fp = fbuf + (ne - nlo) * L + r;
         float num = 0.0f, den = 0.0f;
-        for (int n = na; n <= nb; ++n, fp += L - P, j -= P) {
-          num += *fp;
-          den += w2[j];
+        for (int u = 0; u <= A.c; ++u, --n, fp -= L - P, j += P) {
+          if (n >= na && n <= nb) {
+            num += *fp;
+            den += w2[j];
+          }
         }
         outp[i] = num / (den + 1e-16f);
         ne += dq;
@@ -204,6 +207,7 @@ int istft512_try(const float* Y, const float* w, float* out, int64_t batch, int6
   A.m = (L - 1) % P;
   A.tiles_per_utt = (T_out + tile - 1) / tile;
   A.alias = (static_cast<size_t>(4) * L * sizeof(float) >= 2 * kPlane * sizeof(float2)) ? 1 : 0;
+  A.fbuf_off = A.alias ? 0 : kIW * 2 * kPlane;
   const size_t smem = 256 * sizeof(float2) + 2 * 512 * sizeof(float) +
                       static_cast<size_t>(kIW) * 2 * kPlane * sizeof(float2) * (A.alias ? 1 : 2) +
                       static_cast<size_t>(kTileFrames) * L * sizeof(float);

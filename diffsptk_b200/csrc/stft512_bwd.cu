@@ -35,6 +35,7 @@ struct BArgs {
   float* gx;            // [batch, T]
   int64_t batch, N, T, tiles_per_utt;
   int L, P, left, tile, alias, span;
+  int fbuf_off;         // float2 units from the second plane array to the frame rows (0 when they alias)
   int c, m;             // (L - 1) / P and (L - 1) % P
   int fmt;
   float eps;
@@ -65,7 +66,7 @@ __global__ void __launch_bounds__(kBT, 2) stft512_bwd_kernel(const BArgs A) {
   float* xs = win + 512;                                       // [span] waveform samples of the tile's frames
   float2* planes1 = reinterpret_cast<float2*>(xs + A.span);    // [kBW][2 kPlane] exchange planes of half-warp 1
   float2* planes0 = planes1 + kBW * 2 * kPlane;                // [kBW][2 kPlane] (only when they cannot alias)
-  float* fbuf = reinterpret_cast<float*>(A.alias ? planes0 : planes0 + kBW * 2 * kPlane);   // [32][L]
+  float* fbuf = reinterpret_cast<float*>(planes0 + A.fbuf_off);                              // [32][L]
 
   for (int i = tid; i < 256; i += kBT) tws[i] = A.tw512[i];
   for (int i = tid; i < 512; i += kBT) win[i] = i < L ? A.w[i] : 0.0f;
@@ -268,9 +269,11 @@ __global__ void __launch_bounds__(kBT, 2) stft512_bwd_kernel(const BArgs A) {
         int na = ne - A.c + (rr > A.m ? 1 : 0);
         if (na < 0) na = 0;
         const int nb = ne < Nm1 ? ne : Nm1;
-        const float* fp = fbuf + (na - nlo) * L + rr + (ne - na) * P;
+        int n = ne;
+        const float* fp = fbuf + (ne - nlo) * L + rr;
         float num = 0.0f;
-        for (int n = na; n <= nb; ++n, fp += L - P) num += *fp;
+        for (int u = 0; u <= A.c; ++u, --n, fp -= L - P)      // same trip count in every lane, frames predicated
+          if (n >= na && n <= nb) num += *fp;
         outp[i] = num;
         ne += dq;
         rr += drm;
@@ -316,6 +319,7 @@ int stft512_bwd_try(const float* x, const float* window, const float* gy, float*
   A.eps = static_cast<float>(p->spec.eps);
   A.span = ((kBFrames - 1) * P + 512 + 3) & ~3;
   A.alias = (static_cast<size_t>(4) * L * sizeof(float) >= 2 * kPlane * sizeof(float2)) ? 1 : 0;
+  A.fbuf_off = A.alias ? 0 : kBW * 2 * kPlane;
   const size_t smem = 256 * sizeof(float2) + 512 * sizeof(float) + static_cast<size_t>(A.span) * sizeof(float) +
                       static_cast<size_t>(kBW) * 2 * kPlane * sizeof(float2) * (A.alias ? 1 : 2) +
                       static_cast<size_t>(kBFrames) * L * sizeof(float);
