@@ -100,6 +100,11 @@ def window(x: Tensor, out_length: int | None = None, *, window: str = "blackman"
     return nn.Window._func(x, out_length=out_length, window=window, norm=norm, symmetric=symmetric)
 
 
+def fftcep(x: Tensor, cep_order: int, accel: float = 0, n_iter: int = 0) -> Tensor:
+    """Cepstral analysis ``(..., L/2+1) -> (..., M+1)`` (improved cepstral method)."""
+    return nn.CepstralAnalysis._func(x, cep_order=cep_order, accel=accel, n_iter=n_iter)
+
+
 def ifftr(y: Tensor, out_length: int | None = None) -> Tensor:
     """Inverse real FFT, complex ``(..., L/2+1) -> (..., N)``."""
     return nn.RealValuedInverseFastFourierTransform._func(y, out_length=out_length)

@@ -5,6 +5,7 @@ from .acorr import Autocorrelation
 from .dct import DiscreteCosineTransform
 from .dct import DiscreteCosineTransform as DCT
 from .fbank import MelFilterBankAnalysis
+from .fftcep import CepstralAnalysis
 from .fbank import MelFilterBankAnalysis as FBANK
 from .fftr import RealValuedFastFourierTransform
 from .frame import Frame
@@ -29,5 +30,5 @@ __all__ = [
     "RealValuedFastFourierTransform", "Frame", "FrequencyTransform", "LevinsonDurbin",
     "LinearPredictiveCodingAnalysis", "LPC", "MelCepstralAnalysis",
     "MelFrequencyCepstralCoefficientsAnalysis", "MFCC", "Spectrum", "ShortTimeFourierTransform", "STFT",
-    "Window", "RealValuedInverseFastFourierTransform", "Unframe", "InverseShortTimeFourierTransform", "ISTFT",
+    "Window", "RealValuedInverseFastFourierTransform", "Unframe", "InverseShortTimeFourierTransform", "ISTFT", "CepstralAnalysis",
 ]

@@ -226,6 +226,41 @@ def stft(x, *, frame_length=400, frame_period=80, fft_length=512, center=True, z
     return spec(g, fft_length=fft_length, eps=eps, relative_floor=relative_floor, out_format=out_format)
 
 
+# ----------------------------------------------------------------------------- fftcep
+# a direct consumer of the STFT power spectrum.
+def fftcep(x, cep_order, accel=0.0, n_iter=0):
+    """Cepstral analysis by the improved cepstral method.  diffsptk/modules/fftcep.py:94-136."""
+    x = _as_float(x)
+    H = x.shape[-1]
+    n = 2 * (H - 1)
+    if n <= 1:
+        raise ValueError("fft_length must be greater than 1.")
+    if cep_order < 0:
+        raise ValueError("cep_order must be non-negative.")
+    if n < 2 * cep_order:
+        raise ValueError("cep_order must be less than or equal to fft_length // 2.")
+    if accel < 0:
+        raise ValueError("accel must be non-negative.")
+    if n_iter < 0:
+        raise ValueError("n_iter must be non-negative.")
+    N = cep_order + 1
+    dt = x.dtype
+    e = np.fft.irfft(np.log(x), axis=-1).astype(dt)
+    v = e[..., :N].copy()
+    pad = [(0, 0)] * (x.ndim - 1)
+    e = np.pad(e[..., N:H], pad + [(N, 0)])
+    for _ in range(n_iter):
+        e = np.fft.hfft(e, axis=-1).astype(dt)
+        e[e < 0] = 0
+        e = np.fft.ihfft(e, axis=-1).real.astype(dt)
+        t = e[..., :N] * (1 + accel)
+        v += t
+        e -= np.pad(t, pad + [(0, H - N)])
+    idx = [0, N - 1] if H == N else [0]
+    v[..., idx] *= 0.5
+    return v
+
+
 # ----------------------------------------------------------------------------- ifftr / unframe / istft
 # SURVEY.md section 8(f) rank 2: the inverse of the hot path.
 def ifftr(y, out_length=None):

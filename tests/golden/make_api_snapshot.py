@@ -1,7 +1,7 @@
 """Snapshot the reference's public signatures for the hot path (run in the build container).
 
 Writes ``tests/golden/api_signatures.json``: constructor / functional parameter names, kinds and
-defaults of the 22 exported classes (incl. aliases) and 16 functional delegates, plus the
+defaults of the 23 exported classes (incl. aliases) and 17 functional delegates, plus the
 ``_takes_input_size`` flags -- the drop-in contract of SURVEY.md section 8(b).
 """
 
@@ -18,9 +18,9 @@ CLASSES = ["Autocorrelation", "DiscreteCosineTransform", "DCT", "MelFilterBankAn
            "LinearPredictiveCodingAnalysis", "LPC", "MelCepstralAnalysis",
            "MelFrequencyCepstralCoefficientsAnalysis", "MFCC", "Spectrum", "ShortTimeFourierTransform", "STFT",
            "Window", "RealValuedInverseFastFourierTransform", "Unframe", "InverseShortTimeFourierTransform",
-           "ISTFT"]
+           "ISTFT", "CepstralAnalysis"]
 FUNCTIONS = ["acorr", "dct", "fbank", "fftr", "frame", "freqt", "levdur", "lpc", "mcep", "mfcc", "spec", "stft",
-             "window", "ifftr", "unframe", "istft"]
+             "window", "ifftr", "unframe", "istft", "fftcep"]
 
 
 def describe(fn):

@@ -210,6 +210,14 @@ def cases():
                                            center=False, window="hamming", norm="none", symmetric=False),
            [cplx(2, 3, 12, 33)])
     yield ("istft_one_frame", "istft", dict(out_length=None), [cplx(1, 1, 257)])
+    # ---- fftcep, section 8(f) rank 3 (tests/test_fftcep.py) --------------------------------------------------
+    P9 = ri.standard_normal((2, 9)) ** 2 + 0.1
+    for M in (3, 8):
+        for it in (0, 3):
+            yield (f"fftcep_16_m{M}_i{it}", "fftcep", dict(cep_order=M, accel=0.5 if it else 0.0, n_iter=it), [P9])
+    P257 = ri.standard_normal((2, 5, 257)) ** 2 + 1e-3
+    yield ("fftcep_512_m24", "fftcep", dict(cep_order=24, accel=0.0, n_iter=0), [P257])
+    yield ("fftcep_512_m24_i5", "fftcep", dict(cep_order=24, accel=1.0, n_iter=5), [P257])
 
 
 def main():

@@ -98,6 +98,8 @@ def build_module(op, params, ins, prec):
         return B.MFCC(fft_length=2 * n - 2, **p, device=d, dtype=dt)
     if op == "dct":
         return B.DCT(n, **p, device=d, dtype=dt)
+    if op == "fftcep":
+        return B.CepstralAnalysis(fft_length=2 * n - 2, **p)
     if op == "ifftr":
         return B.RealValuedInverseFastFourierTransform(2 * n - 2, p.pop("out_length"), device=d, dtype=dt)
     if op == "unframe":
