@@ -437,3 +437,40 @@ def test_ifftr_unframe_edge_cases():
         assert F.unframe(fr, 10 ** 6, frame_period=P, center=center).shape == want.shape
     with pytest.raises(NotImplementedError):
         F.istft(torch.zeros(1, 3, 257, dtype=torch.complex64, device=d, requires_grad=True))
+
+
+def test_extreme_shapes_long_utterance_and_many_short_ones():
+    """Index arithmetic at the ends of the envelope: one 2^25-sample utterance (419 431 frames) and 70 000
+    utterances of a few frames, through the fused forward, inverse and backward kernels."""
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(9)
+    x = torch.randn(1, 1 << 25, generator=g, device=d)
+    P = F.stft(x)
+    assert P.shape == (1, ((1 << 25) - 1) // 80 + 1, 257)
+    for lo in (0, 17_000_000, (1 << 25) - 4000):          # windows at the start, the middle and the very end
+        seg = to_np(x[0, max(lo - 200, 0): lo + 4000 + 200]).astype(np.float64)
+        f0 = lo // 80
+        pad = 200 - min(lo, 200)
+        fr = O.frame(np.pad(seg, (pad, 400)), 400, 80, center=False)[: 40]
+        want = O.spec(O.window(fr, 512), fft_length=512, eps=1e-9)
+        n = min(40, P.shape[1] - f0)
+        H.assert_close(to_np(P[0, f0: f0 + n]), want[:n], "f32", what=f"long utterance @{lo}", scale_atol=True)
+    Y = F.stft(x, out_format="complex")
+    xr = F.istft(Y, out_length=x.shape[-1])
+    assert float((xr - x).abs().max()) < 5e-4
+    del Y, xr, P
+    xg = x.detach().requires_grad_(True)
+    F.stft(xg, eps=1e-3, out_format="log-magnitude").sum().backward()
+    assert bool(torch.isfinite(xg.grad).all()) and float(xg.grad.abs().max()) > 0
+    del xg
+    xs = torch.randn(70_000, 333, generator=g, device=d)
+    Ps = F.stft(xs)
+    assert Ps.shape == (70_000, 5, 257)
+    for b in (0, 34_567, 69_999):
+        H.assert_close(to_np(Ps[b]), O.stft(to_np(xs[b]).astype(np.float64)), "f32", what=f"short utterance {b}",
+                       scale_atol=True)
+    Ys = F.stft(xs, out_format="complex")
+    back = F.istft(Ys, out_length=333)
+    assert float((back - xs).abs().max()) < 5e-4
