@@ -12,7 +12,15 @@ _FORMATS = {"naive": 0, "normalized": 1, "biased": 2, "unbiased": 3}
 
 
 class Autocorrelation(BaseFunctionalModule):
-    """``(..., L) -> (..., M+1)``; kernel ``dsb200_acorr`` (time-domain lag sums, no FFT)."""
+    """``(..., L) -> (..., M+1)``; kernel ``dsb200_acorr`` (time-domain lag sums, no FFT).
+
+    The reference goes through ``rfft -> |.|^2 -> irfft`` (acorr.py:112-121); with ``M << L`` the M + 1 lag sums
+    ``r_k = sum_n x_n x_{n+k}`` are cheaper computed directly: one warp per frame, lanes over lags, float64
+    accumulators (speech frames are badly conditioned for the Levinson solve that follows), formatter applied in
+    the same pass.  From the waveform the fused ``lpc_from_waveform`` keeps a 25-deep sliding register window
+    instead (``csrc/fused_wave.cu``).  Backward: ``dsb200_acorr_backward``,
+    ``gx_n = sum_k gr_k (x_{n+k} + x_{n-k})``.
+    """
 
     _takes_input_size = True
 

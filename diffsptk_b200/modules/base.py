@@ -62,3 +62,9 @@ class BaseFunctionalModule(ABC, nn.Module):
     @staticmethod
     @abstractmethod
     def _forward(*args, **kwargs) -> Any: ...
+
+
+# Differences from the reference's base class are deliberate and small: buffers are registered non-persistent
+# exactly like the reference (state_dict stays empty), but sub-layers and values are plain attributes collected
+# by name, so that fused forwards (STFT, ISTFT, MFCC, LPC) can read a sub-layer's table (``self.window.window``)
+# without calling the sub-layer.

@@ -55,26 +55,27 @@ class CepstralAnalysis(BaseFunctionalModule):
     @staticmethod
     def _forward(x: torch.Tensor, *, cep_order: int, accel: float, n_iter: int) -> torch.Tensor:
         ops._no_grad_check(x)
-        N, H = cep_order + 1, x.size(-1)
-        n = 2 * (H - 1)
         if not x.dtype.is_floating_point:
             x = x.to(torch.get_default_dtype())
+        n_bins = x.size(-1)
+        n_fft, n_cep = 2 * (n_bins - 1), cep_order + 1
+        as_half_spectrum = lambda t: torch.complex(t, torch.zeros_like(t))  # noqa: E731  (real, even sequence)
 
-        def hermitian(t):  # real, even sequence of H points as the half spectrum the inverse kernel takes
-            return torch.complex(t, torch.zeros_like(t))
-
-        e_full = ops.ifftr(hermitian(torch.log(x)), n)                  # irfft(log x)
-        v = e_full[..., :N].clone()
-        e = torch.zeros_like(x)
-        e[..., N:H] = e_full[..., N:H]
+        # cepstrum of the log spectrum; its first M + 1 terms are the estimate, the tail is the residual
+        cep = ops.ifftr(as_half_spectrum(torch.log(x)), n_fft)
+        estimate = cep[..., :n_cep].clone()
+        residual = torch.zeros_like(x)
+        residual[..., n_cep:n_bins] = cep[..., n_cep:n_bins]
+        gain = 1 + accel
         for _ in range(n_iter):
-            E = ops.ifftr(hermitian(e), n) * n                           # hfft(e) of a real sequence
-            E.clamp_(min=0)
-            e = ops.rfft(E, n, 1) / n                                    # ihfft(E).real
-            t = e[..., :N] * (1 + accel)
-            v += t
-            e[..., :N] -= t
-        v[..., 0] *= 0.5
-        if H == N:
-            v[..., N - 1] *= 0.5
-        return v
+            # residual -> log-spectral domain (hfft of a real sequence = n * irfft), keep only what lies above
+            # the current envelope, and come back (ihfft(.).real = rfft(.).real / n)
+            above = ops.ifftr(as_half_spectrum(residual), n_fft).mul_(n_fft).clamp_(min=0)
+            residual = ops.rfft(above, n_fft, 1).div_(n_fft)
+            step = residual[..., :n_cep] * gain
+            estimate += step
+            residual[..., :n_cep] -= step
+        estimate[..., 0] *= 0.5
+        if n_bins == n_cep:
+            estimate[..., n_cep - 1] *= 0.5
+        return estimate

@@ -10,7 +10,15 @@ from .base import BaseFunctionalModule, Precomputed
 
 
 class RealValuedInverseFastFourierTransform(BaseFunctionalModule):
-    """complex ``(..., L/2+1) -> (..., N)``; kernel ``dsb200_ifftr`` (no cuFFT / torch.fft on the path)."""
+    """complex ``(..., L/2+1) -> (..., N)``; kernel ``dsb200_ifftr`` (no cuFFT / torch.fft on the path).
+
+    One warp per spectrum row.  For power-of-two lengths the row is folded into the half-length complex
+    sequence ``E + iO`` (``E``/``O`` = spectra of the even / odd samples), transformed by the radix-4 Stockham
+    passes of ``csrc/rowfft.cuh`` as ``conj(FFT(conj(.)))`` and de-interleaved; other even lengths use a
+    table-driven direct sum.  Like ``torch.fft.irfft`` the imaginary parts of the DC and Nyquist bins are
+    ignored.  Only the first ``out_length`` samples are produced.  The fused inverse STFT never calls this op:
+    it keeps the frames on chip (``csrc/istft512.cu``, ``csrc/inverse.cu``).
+    """
 
     _takes_input_size = True
 
