@@ -54,7 +54,6 @@ def mfcc_from_waveform(x: Tensor, *, frame_length: int = 400, frame_period: int 
     if liftering_vector is None:
         liftering_vector = tables.make_lifter(mfcc_order, lifter, dev, dt)
     fmt = mfcc_format_id(out_format)
-    ops._no_grad_check(H)  # gradients flow to the waveform and the window, not to a learnable filter bank
     cb, ce = support_of(H, H_begin, H_end)
     try:
         return ops.mfcc_wave(x, window_table, H, cb, ce, W, liftering_vector, frame_period, fft_length, center,

@@ -100,7 +100,6 @@ class MelFilterBankAnalysis(BaseFunctionalModule):
     @staticmethod
     def _forward(x: torch.Tensor, *, floor: float, gamma: float, use_power: bool, out_format: int,
                  H: torch.Tensor, H_begin: torch.Tensor | None = None, H_end: torch.Tensor | None = None):
-        ops._no_grad_check(H)  # gradients flow to the spectrum, not to a learnable filter bank
         cb, ce = support_of(H, H_begin, H_end)
         y, E = ops.fbank(x, H, cb, ce, floor, gamma, use_power, out_format != 0)
         if out_format == 0:

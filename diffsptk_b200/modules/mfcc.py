@@ -95,6 +95,5 @@ class MelFrequencyCepstralCoefficientsAnalysis(BaseFunctionalModule):
         W = W_table if W_table is not None else dct.W
         if x.size(-1) != H.size(0):
             raise ValueError(f"Unexpected dimension of spectrum (input {x.size(-1)} vs target {H.size(0)}).")
-        ops._no_grad_check(H)  # gradients flow to the spectrum, not to a learnable filter bank
         cb, ce = support_of(H, H_begin, H_end)
         return ops.mfcc(x, H, cb, ce, W, liftering_vector, floor, gamma, out_format)

@@ -60,8 +60,8 @@ def _no_grad_check(*ts):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
         raise NotImplementedError(
             "this diffsptk_b200 op is forward-only for that input (differentiable: frame / window / fftr / spec / "
-            "stft / freqt / dct / acorr / levdur / lpc / fbank / mfcc with respect to their signal inputs; not "
-            "mcep, and not learnable filter-bank or DFT-basis tables): wrap the call in torch.no_grad() or "
+            "stft / freqt / dct / acorr / levdur / lpc / fbank / mfcc, including learnable windows and filter banks; not "
+            "mcep, the inverse path, or a learnable DFT basis): wrap the call in torch.no_grad() or "
             "detach() the inputs."
         )
 
@@ -640,10 +640,16 @@ def _(x, H, col_begin, col_end, gy, gE, floor, gamma, use_power):
     return x.new_empty(x.shape, dtype=_native_dtype(x, H))
 
 
+def _fbank_weight_grad(P: Tensor, H: Tensor, gmel: Tensor, floor: float, gamma: float, use_power: bool) -> Tensor:
+    """d/dH of the filter-bank outputs (learnable filter bank): amp^T @ (gmel * dy/dz), a plain dense GEMM."""
+    amp = (P if use_power else torch.sqrt(P)).reshape(-1, P.shape[-1]).to(H.dtype)
+    z = amp @ H
+    dz = torch.where(z >= floor, (1.0 / z) if gamma == 0 else z.pow(gamma - 1.0), torch.zeros_like(z))
+    return amp.t() @ (gmel.reshape(-1, H.shape[1]).to(H.dtype) * dz)
+
+
 def _fbank_setup(ctx, inputs, output):
     x, H, cb, ce, floor, gamma, use_power, want_energy = inputs
-    if H.requires_grad:
-        raise NotImplementedError("gradients with respect to a learnable filter-bank matrix are not implemented")
     ctx.save_for_backward(x, H, cb, ce)
     ctx.rest = (floor, gamma, use_power)
     ctx.want_energy = want_energy
@@ -651,15 +657,17 @@ def _fbank_setup(ctx, inputs, output):
 
 def _fbank_bwd(ctx, gy, gE):
     x, H, cb, ce = ctx.saved_tensors
-    gx = fbank_backward(x, H, cb, ce, gy, gE if ctx.want_energy else None, *ctx.rest)
-    return (_like_input(gx, x),) + (None,) * 7
+    gx = fbank_backward(x, H, cb, ce, gy, gE if ctx.want_energy else None, *ctx.rest) if ctx.needs_input_grad[0] else None
+    gH = _fbank_weight_grad(x, H, gy, *ctx.rest) if ctx.needs_input_grad[1] else None
+    return (_like_input(gx, x) if gx is not None else None, gH) + (None,) * 6
 
 
 torch.library.register_autograd(f"{_NS}::fbank", _fbank_bwd, setup_context=_fbank_setup)
 
 
-def _mfcc_grad_to_spectrum(g: Tensor, P: Tensor, H, cb, ce, W, lifter, floor, gamma, out_format) -> Tensor:
-    """Adjoint of lifter -> DCT -> log filter bank (mfcc.py:243-256): gradient of the packed output -> spectrum."""
+def _mfcc_grad_to_spectrum(g: Tensor, P: Tensor, H, cb, ce, W, lifter, floor, gamma, out_format, want_gH=False):
+    """Adjoint of lifter -> DCT -> log filter bank (mfcc.py:243-256): gradient of the packed output -> spectrum
+    (and, for a learnable filter bank, -> H)."""
     M = lifter.shape[-1] - 1
     g = g.to(lifter.dtype)
     gcep = g.new_zeros((*g.shape[:-1], M + 1))
@@ -672,21 +680,20 @@ def _mfcc_grad_to_spectrum(g: Tensor, P: Tensor, H, cb, ce, W, lifter, floor, ga
     elif out_format == 3:
         gE = g[..., M + 1].contiguous()
     gmel = rowmat(gcep * lifter, W[:, : M + 1].t().contiguous())
-    return fbank_backward(P, H, cb, ce, gmel, gE, floor, gamma, False)
+    gP = fbank_backward(P, H, cb, ce, gmel, gE, floor, gamma, False)
+    return (gP, _fbank_weight_grad(P, H, gmel, floor, gamma, False)) if want_gH else (gP, None)
 
 
 def _mfcc_setup(ctx, inputs, output):
     x, H, cb, ce, W, lifter, floor, gamma, out_format = inputs
-    if H.requires_grad:
-        raise NotImplementedError("gradients with respect to a learnable filter-bank matrix are not implemented")
     ctx.save_for_backward(x, H, cb, ce, W, lifter)
     ctx.rest = (floor, gamma, out_format)
 
 
 def _mfcc_bwd(ctx, g):
     x, H, cb, ce, W, lifter = ctx.saved_tensors
-    gx = _mfcc_grad_to_spectrum(g, x, H, cb, ce, W, lifter, *ctx.rest)
-    return (_like_input(gx, x),) + (None,) * 8
+    gx, gH = _mfcc_grad_to_spectrum(g, x, H, cb, ce, W, lifter, *ctx.rest, want_gH=ctx.needs_input_grad[1])
+    return (_like_input(gx, x), gH) + (None,) * 7
 
 
 torch.library.register_autograd(f"{_NS}::mfcc", _mfcc_bwd, setup_context=_mfcc_setup)
@@ -695,8 +702,6 @@ torch.library.register_autograd(f"{_NS}::mfcc", _mfcc_bwd, setup_context=_mfcc_s
 def _mfcc_wave_setup(ctx, inputs, output):
     (x, window, H, cb, ce, W, lifter, frame_period, fft_length, center, zmean, pad_mode, eps, floor, gamma,
      out_format) = inputs
-    if H.requires_grad:
-        raise NotImplementedError("gradients with respect to a learnable filter-bank matrix are not implemented")
     ctx.save_for_backward(x, window, H, cb, ce, W, lifter)
     ctx.stft_args = (frame_period, fft_length, center, zmean, pad_mode, eps, -1.0, 3)
     ctx.rest = (floor, gamma, out_format)
@@ -708,10 +713,10 @@ def _mfcc_wave_bwd(ctx, g):
     x, window, H, cb, ce, W, lifter = ctx.saved_tensors
     with torch.no_grad():
         P = stft(x, window, *ctx.stft_args)
-        gP = _mfcc_grad_to_spectrum(g, P, H, cb, ce, W, lifter, *ctx.rest)
+        gP, gH = _mfcc_grad_to_spectrum(g, P, H, cb, ce, W, lifter, *ctx.rest, want_gH=ctx.needs_input_grad[2])
         need_gw = ctx.needs_input_grad[1]
         gx, gw = stft_backward(x, window, gP, *ctx.stft_args, need_gw)
-    return (_like_input(gx, x), gw.to(window.dtype) if need_gw else None) + (None,) * 14
+    return (_like_input(gx, x), gw.to(window.dtype) if need_gw else None, gH) + (None,) * 13
 
 
 torch.library.register_autograd(f"{_NS}::mfcc_wave", _mfcc_wave_bwd, setup_context=_mfcc_wave_setup)

@@ -338,3 +338,40 @@ def test_fused_stft_backward_kernel(fmt):
         scale = float(ref.abs().max())
         assert float((fast.double() - ref).abs().max()) < 2e-3 * scale, (fmt, T, kw)
         assert float((fast - slow).abs().max()) < 2e-4 * scale, (fmt, T, kw)
+
+
+def test_learnable_filter_bank_gradients():
+    """learnable=True turns H into a Parameter (fbank.py:112): its gradient is amp^T (g dy/dz), x's comes from the
+    native kernel; the MFCC module chains both."""
+    import diffsptk_b200 as B
+    d = dev()
+    g = torch.Generator().manual_seed(29)
+    x = (torch.rand(4, 6, 33, generator=g, dtype=torch.float64) + 0.05).to(d).requires_grad_(True)
+    fb = B.MelFilterBankAnalysis(fft_length=64, n_channel=10, sample_rate=8000, floor=0.2, out_format="yE",
+                                 learnable=True, dtype=torch.float64).to(d)
+    assert isinstance(fb.H, torch.nn.Parameter)
+    (gx, gH), ws = _vjp(lambda t, Hm: fb(t), (x, fb.H), g)
+    Hr = fb.H.detach().clone().requires_grad_(True)
+    rx, rH = _ref_vjp(lambda t, Hm: torch.cat(composite_fbank(t, Hm, 0.2, 0.0, False), -1), (x, Hr), ws)
+    assert torch.allclose(gx, rx, rtol=1e-9, atol=1e-11) and torch.allclose(gH, rH, rtol=1e-9, atol=1e-11)
+
+    mf = B.MFCC(fft_length=64, mfcc_order=6, n_channel=10, sample_rate=8000, lifter=5, floor=0.2, out_format="yc",
+                learnable=True, dtype=torch.float64).to(d)
+    (gx, gH), ws = _vjp(lambda t, Hm: mf(t), (x, mf.fbank.H), g)
+
+    def ref(t, Hm):
+        y, _ = composite_fbank(t, Hm, 0.2, 0.0, False)
+        c = (y @ mf.dct.W)[..., :7] * mf.liftering_vector
+        return torch.cat((c[..., 1:], c[..., :1]), -1)
+    Hr = mf.fbank.H.detach().clone().requires_grad_(True)
+    rx, rH = _ref_vjp(ref, (x, Hr), ws)
+    assert torch.allclose(gx, rx, rtol=1e-9, atol=1e-11) and torch.allclose(gH, rH, rtol=1e-9, atol=1e-11)
+    # an optimiser step on a learnable front end: window and filter bank both receive gradients
+    front = torch.nn.Sequential(B.STFT(400, 80, 512, learnable=["window"]),
+                                B.MFCC(fft_length=512, mfcc_order=12, n_channel=24, sample_rate=16000,
+                                       learnable=True)).to(d)
+    wav = torch.randn(2, 3000, device=d)
+    front(wav).square().mean().backward()
+    grads = [p.grad for p in front.parameters()]
+    assert len(grads) == 2 and all(gr is not None and bool(torch.isfinite(gr).all()) and float(gr.abs().max()) > 0
+                                   for gr in grads)
