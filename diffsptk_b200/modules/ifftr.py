@@ -58,5 +58,4 @@ class RealValuedInverseFastFourierTransform(BaseFunctionalModule):
     def _forward(y: torch.Tensor, *, fft_length: int, out_length: int | None) -> torch.Tensor:
         if not y.is_complex():
             raise ValueError("the input spectrum must be complex")
-        ops._no_grad_check(y)
         return ops.ifftr(y, fft_length if out_length is None else out_length)

@@ -73,6 +73,6 @@ class InverseShortTimeFourierTransform(BaseFunctionalModule):
             raise ValueError("Input must be at least 2D tensor.")
         if 2 * (y.size(-1) - 1) != fft_length:
             raise ValueError(f"Unexpected dimension of spectrum (input {y.size(-1)} vs target {fft_length // 2 + 1}).")
-        ops._no_grad_check(y, table)
+        ops._no_grad_check(table)  # gradients flow to the spectrogram, not to a learnable synthesis window
         T = ops.unframe_length(y.size(-2), table.shape[-1], frame_period, center, out_length)
         return ops.istft(y, table, T, frame_period, center)

@@ -56,6 +56,6 @@ class Unframe(BaseFunctionalModule):
                  window: torch.Tensor) -> torch.Tensor:
         if y.dim() <= 1:
             raise ValueError("Input must be at least 2D tensor.")
-        ops._no_grad_check(y, window)
+        ops._no_grad_check(window)  # gradients flow to the frames, not to a learnable synthesis window
         T = ops.unframe_length(y.size(-2), y.size(-1), frame_period, center, out_length)
         return ops.unframe(y, window, T, frame_period, center)

@@ -60,8 +60,8 @@ def _no_grad_check(*ts):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
         raise NotImplementedError(
             "this diffsptk_b200 op is forward-only for that input (differentiable: frame / window / fftr / spec / "
-            "stft / freqt / dct / acorr / levdur / lpc / fbank / mfcc, including learnable windows and filter banks; not "
-            "mcep, the inverse path, or a learnable DFT basis): wrap the call in torch.no_grad() or "
+            "stft / freqt / dct / acorr / levdur / lpc / fbank / mfcc, including learnable analysis windows and filter banks, and ifftr / unframe / istft; not "
+            "mcep, learnable synthesis windows, or a learnable DFT basis): wrap the call in torch.no_grad() or "
             "detach() the inputs."
         )
 
@@ -909,3 +909,104 @@ def istft(y: Tensor, window: Tensor, out_length: int, frame_period: int, center:
 @istft.register_fake
 def _(y, window, out_length, frame_period, center):
     return y.new_empty((*y.shape[:-2], out_length), dtype=_native_dtype(window))
+
+
+# ---- gradients of the inverse path: the adjoints are the forward kernels of the analysis path -----------------
+def _irfft_bin_weights(n: int, like: Tensor) -> Tensor:
+    """c_k / n with c_k = 2 for the interior bins and 1 for DC / Nyquist (whose imaginary parts get no gradient)."""
+    c = torch.full((n // 2 + 1,), 2.0 / n, device=like.device, dtype=like.dtype)
+    c[0] = c[-1] = 1.0 / n
+    return c
+
+
+def _scale_half_spectrum(G: Tensor, n: int) -> Tensor:
+    """interleaved (re, im) rows of rfft(g) -> gradient of irfft's complex input (torch convention dRe + i dIm)."""
+    G = G * _irfft_bin_weights(n, G).unsqueeze(-1)
+    G[..., 0, 1] = 0
+    G[..., -1, 1] = 0
+    return torch.view_as_complex(G.contiguous())
+
+
+def _ifftr_setup(ctx, inputs, output):
+    y, out_length = inputs
+    ctx.n = 2 * (y.shape[-1] - 1)
+    ctx.is_c64 = y.dtype == torch.complex64
+
+
+def _ifftr_bwd(ctx, g):
+    # x_j = (1/n) sum_k c_k Re(Y_k e^{+2 pi i jk/n})  =>  dL/dY = (c_k / n) rfft(g zero-padded to n)
+    G = rfft(g, ctx.n, 0)
+    out = _scale_half_spectrum(G, ctx.n)
+    return out.to(torch.complex64 if ctx.is_c64 else torch.complex128), None
+
+
+torch.library.register_autograd(f"{_NS}::ifftr", _ifftr_bwd, setup_context=_ifftr_setup)
+
+
+def _ola_denominator(window: Tensor, n_frames: int, frame_period: int) -> Tensor:
+    """sum_n w^2[q - n P] over the folded span (a batch-independent vector of (N-1) P + L values)."""
+    L = window.shape[-1]
+    w2 = (window.detach() * window.detach()).reshape(1, L, 1).expand(1, L, n_frames)
+    span = (n_frames - 1) * frame_period + L
+    return torch.nn.functional.fold(w2, (1, span), (1, L), stride=(1, frame_period)).reshape(span)
+
+
+def _unframe_grad_signal(g: Tensor, window: Tensor, n_frames: int, frame_period: int, center: bool) -> Tensor:
+    """g / (sum w^2 + 1e-16), laid out so that frame n of it starts where frame n was overlap-added."""
+    L = window.shape[-1]
+    s = L // 2 if center else 0
+    den = _ola_denominator(window, n_frames, frame_period)
+    T_out = g.shape[-1]
+    u = g / (den[s:s + T_out] + 1e-16)
+    need = (n_frames - 1) * frame_period + 1          # enough samples for the framing ops to produce N frames
+    if T_out < need:
+        u = torch.nn.functional.pad(u, (0, need - T_out))
+    return u
+
+
+def _unframe_setup(ctx, inputs, output):
+    y, window_t, out_length, frame_period, center = inputs
+    ctx.save_for_backward(y, window_t)
+    ctx.args = (frame_period, center)
+
+
+def _unframe_bwd(ctx, g):
+    y, w = ctx.saved_tensors
+    P, center = ctx.args
+    Nf, L = y.shape[-2], y.shape[-1]
+    if ctx.needs_input_grad[1]:
+        raise NotImplementedError("gradients with respect to a learnable synthesis window are not implemented")
+    with torch.no_grad():
+        u = _unframe_grad_signal(g, w, Nf, P, center)
+        # d out[t] / d y[n, j] = w[j] / den(t) at t = n P + j - s: frame the scaled gradient, apply the window
+        fr = frame(u, L, P, center, False, 0)[..., :Nf, :]
+        gy = window(fr, w, L)
+    return _like_input(gy, y), None, None, None, None
+
+
+torch.library.register_autograd(f"{_NS}::unframe", _unframe_bwd, setup_context=_unframe_setup)
+
+
+def _istft_setup(ctx, inputs, output):
+    y, window_t, out_length, frame_period, center = inputs
+    ctx.save_for_backward(window_t)
+    ctx.meta = (y.shape[-2], 2 * (y.shape[-1] - 1), y.dtype == torch.complex64)
+    ctx.args = (frame_period, center)
+
+
+def _istft_bwd(ctx, g):
+    # unframe's adjoint is window * frame(g / den), irfft's is (c_k / n) rfft: together, the complex STFT of
+    # g / den -- the fused forward kernel -- scaled per bin.
+    (w,) = ctx.saved_tensors
+    Nf, n, is_c64 = ctx.meta
+    P, center = ctx.args
+    if ctx.needs_input_grad[1]:
+        raise NotImplementedError("gradients with respect to a learnable synthesis window are not implemented")
+    with torch.no_grad():
+        u = _unframe_grad_signal(g, w, Nf, P, center)
+        G = stft(u, w, P, n, center, False, 0, 0.0, -1.0, 4)[..., :Nf, :, :]
+        out = _scale_half_spectrum(G, n)
+    return out.to(torch.complex64 if is_c64 else torch.complex128), None, None, None, None
+
+
+torch.library.register_autograd(f"{_NS}::istft", _istft_bwd, setup_context=_istft_setup)

@@ -375,3 +375,76 @@ def test_learnable_filter_bank_gradients():
     grads = [p.grad for p in front.parameters()]
     assert len(grads) == 2 and all(gr is not None and bool(torch.isfinite(gr).all()) and float(gr.abs().max()) > 0
                                    for gr in grads)
+
+
+def composite_unframe(fr, w, P, center, out_length):
+    """unframe.py:164-211 restated with torch.nn.functional.fold (differentiated by torch)."""
+    N, L = fr.shape[-2], fr.shape[-1]
+    span = (N - 1) * P + L
+    lead = fr.shape[:-2]
+    x = (fr * w).reshape(-1, N, L).transpose(-2, -1)
+    num = TF.fold(x, (1, span), (1, L), stride=(1, P)).reshape(*lead, span)
+    den = TF.fold((w * w).reshape(1, L, 1).expand(1, L, N), (1, span), (1, L), stride=(1, P)).reshape(span)
+    s = L // 2 if center else 0
+    if out_length is None:
+        out_length = N * P if center else span
+    return (num / (den + 1e-16))[..., s:s + out_length]
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_inverse_path_gradients(prec):
+    import diffsptk_b200.functional as F
+    d = dev()
+    g = torch.Generator().manual_seed(31)
+    cdt = torch.complex128 if prec == "f64" else torch.complex64
+    tol = dict(rtol=1e-8, atol=1e-10) if prec == "f64" else dict(rtol=2e-3, atol=2e-3)
+
+    def close(a, b, what):
+        scale = max(float(b.abs().max()), 1e-30)
+        a, b = torch.view_as_real(a.to(torch.complex128)) if a.is_complex() else a.double(), \
+            torch.view_as_real(b) if b.is_complex() else b
+        assert torch.allclose(a / scale, b / scale, **tol), (what, float((a - b).abs().max()), scale)
+
+    def cplx(*shape):
+        return torch.complex(torch.randn(*shape, generator=g, dtype=torch.float64),
+                             torch.randn(*shape, generator=g, dtype=torch.float64)).to(d)
+    # ifftr: every out_length, non power of two as well
+    for K, ol in ((9, None), (9, 5), (13, 24), (257, 400)):
+        Y64 = cplx(3, K)
+        Y = Y64.to(cdt).requires_grad_(True)
+        Yr = Y64.clone().requires_grad_(True)
+        n = 2 * (K - 1)
+        (gy,), ws = _vjp(lambda t: F.ifftr(t, ol), (Y,), g)
+        (ref,) = _ref_vjp(lambda t: torch.fft.irfft(t, n=n)[..., :ol], (Yr,), ws)
+        close(gy, ref, f"ifftr K={K} out_length={ol}")
+    # unframe: windows with and without zeros at the ends, short requested lengths, no centring
+    for shape, P, kw, ol in (((2, 9, 12), 5, dict(), None), ((2, 9, 12), 5, dict(), 20),
+                             ((3, 30, 400), 80, dict(window="hamming", norm="power"), 2000),
+                             ((2, 11, 33), 7, dict(center=False, window="hamming", norm="none"), None)):
+        fr64 = torch.randn(*shape, generator=g, dtype=torch.float64).to(d)
+        fr = fr64.to(torch.float64 if prec == "f64" else torch.float32).requires_grad_(True)
+        frr = fr64.clone().requires_grad_(True)
+        w = F.window(torch.ones(shape[-1], dtype=torch.float64, device=d), None,
+                     window=kw.get("window", "rectangular"), norm=kw.get("norm", "none"))
+        (gf,), ws = _vjp(lambda t: F.unframe(t, ol, frame_period=P, **kw), (fr,), g)
+        (ref,) = _ref_vjp(lambda t: composite_unframe(t, w, P, kw.get("center", True), ol), (frr,), ws)
+        close(gf, ref, f"unframe {shape} P={P} {kw} out_length={ol}")
+    # istft: the fused kernel forward, the fused complex STFT as its adjoint
+    for shape, kw, ol in (((2, 13, 257), dict(), 1000), ((2, 13, 257), dict(), None), ((1, 40, 257), dict(), 700),
+                          ((3, 7, 9), dict(frame_length=12, frame_period=5, fft_length=16, center=False,
+                                           window="hamming"), None),
+                          ((2, 9, 25), dict(frame_length=30, frame_period=7, fft_length=48, window="hanning"), 50)):
+        Y64 = cplx(*shape)
+        Y = Y64.to(cdt).requires_grad_(True)
+        Yr = Y64.clone().requires_grad_(True)
+        fl, fp, n = kw.get("frame_length", 400), kw.get("frame_period", 80), kw.get("fft_length", 512)
+        w = F.window(torch.ones(fl, dtype=torch.float64, device=d), None, window=kw.get("window", "blackman"),
+                     norm=kw.get("norm", "power"))
+        (gy,), ws = _vjp(lambda t: F.istft(t, out_length=ol, **kw), (Y,), g)
+        (ref,) = _ref_vjp(lambda t: composite_unframe(torch.fft.irfft(t, n=n)[..., :fl], w, fp,
+                                                      kw.get("center", True), ol), (Yr,), ws)
+        close(gy, ref, f"istft {shape} {kw} out_length={ol}")
+    # analysis -> synthesis round trip is differentiable end to end: d sum(istft(stft(x))) / dx == 1
+    x = torch.randn(2, 4000, device=d, dtype=torch.float64 if prec == "f64" else torch.float32, requires_grad=True)
+    F.istft(F.stft(x, out_format="complex"), out_length=4000).sum().backward()
+    assert float((x.grad - 1).abs().max()) < (1e-9 if prec == "f64" else 2e-4)

@@ -435,8 +435,6 @@ def test_ifftr_unframe_edge_cases():
         assert n >= 501 - L and torch.allclose(y[..., :n], x[..., :n], rtol=1e-10, atol=1e-12), (L, P, center)
         want = O.unframe(to_np(fr), 10 ** 6, frame_period=P, center=center)
         assert F.unframe(fr, 10 ** 6, frame_period=P, center=center).shape == want.shape
-    with pytest.raises(NotImplementedError):
-        F.istft(torch.zeros(1, 3, 257, dtype=torch.complex64, device=d, requires_grad=True))
 
 
 def test_extreme_shapes_long_utterance_and_many_short_ones():
