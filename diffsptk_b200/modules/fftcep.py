@@ -3,7 +3,8 @@
 SURVEY.md section 8(f) rank 3, first version: the transforms (one inverse real FFT, then one Hermitian FFT pair
 per iteration) run on this package's kernels -- ``dsb200_ifftr`` and ``dsb200_rfft``, no torch.fft -- while the
 elementwise steps in between (log, clamp at zero, the accelerated update) are torch elementwise ops on the
-device.  A single fused kernel per iteration is the natural next step.
+device (so autograd flows through the composite: every transform has a native adjoint).  A single fused
+kernel per iteration is the natural next step.
 """
 
 from __future__ import annotations
@@ -54,7 +55,6 @@ class CepstralAnalysis(BaseFunctionalModule):
 
     @staticmethod
     def _forward(x: torch.Tensor, *, cep_order: int, accel: float, n_iter: int) -> torch.Tensor:
-        ops._no_grad_check(x)
         if not x.dtype.is_floating_point:
             x = x.to(torch.get_default_dtype())
         n_bins = x.size(-1)
@@ -63,19 +63,19 @@ class CepstralAnalysis(BaseFunctionalModule):
 
         # cepstrum of the log spectrum; its first M + 1 terms are the estimate, the tail is the residual
         cep = ops.ifftr(as_half_spectrum(torch.log(x)), n_fft)
-        estimate = cep[..., :n_cep].clone()
-        residual = torch.zeros_like(x)
-        residual[..., n_cep:n_bins] = cep[..., n_cep:n_bins]
+        estimate = cep[..., :n_cep]
+        residual = torch.cat((torch.zeros_like(cep[..., :n_cep]), cep[..., n_cep:n_bins]), -1)
         gain = 1 + accel
         for _ in range(n_iter):
             # residual -> log-spectral domain (hfft of a real sequence = n * irfft), keep only what lies above
             # the current envelope, and come back (ihfft(.).real = rfft(.).real / n)
-            above = ops.ifftr(as_half_spectrum(residual), n_fft).mul_(n_fft).clamp_(min=0)
-            residual = ops.rfft(above, n_fft, 1).div_(n_fft)
+            above = (ops.ifftr(as_half_spectrum(residual), n_fft) * n_fft).clamp(min=0)
+            residual = ops.rfft(above, n_fft, 1) / n_fft
             step = residual[..., :n_cep] * gain
-            estimate += step
-            residual[..., :n_cep] -= step
-        estimate[..., 0] *= 0.5
+            estimate = estimate + step
+            residual = torch.cat((residual[..., :n_cep] - step, residual[..., n_cep:]), -1)
+        halve = torch.ones(n_cep, device=x.device, dtype=estimate.dtype)   # out of place: autograd flows through
+        halve[0] = 0.5
         if n_bins == n_cep:
-            estimate[..., n_cep - 1] *= 0.5
-        return estimate
+            halve[n_cep - 1] = 0.5
+        return estimate * halve

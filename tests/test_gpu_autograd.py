@@ -448,3 +448,31 @@ def test_inverse_path_gradients(prec):
     x = torch.randn(2, 4000, device=d, dtype=torch.float64 if prec == "f64" else torch.float32, requires_grad=True)
     F.istft(F.stft(x, out_format="complex"), out_length=4000).sum().backward()
     assert float((x.grad - 1).abs().max()) < (1e-9 if prec == "f64" else 2e-4)
+
+
+def test_fftcep_gradients():
+    import diffsptk_b200.functional as F
+    d = dev()
+    g = torch.Generator().manual_seed(37)
+    x = (torch.rand(3, 4, 33, generator=g, dtype=torch.float64) + 0.1).to(d).requires_grad_(True)
+
+    def ref(t, M, accel, n_iter):   # fftcep.py:116-136
+        N, Hn = M + 1, t.size(-1)
+        e = torch.fft.irfft(torch.log(t))
+        v = e[..., :N]
+        e = TF.pad(e[..., N:Hn], (N, 0))
+        for _ in range(n_iter):
+            e = torch.fft.hfft(e).clamp(min=0)
+            e = torch.fft.ihfft(e).real
+            tt = e[..., :N] * (1 + accel)
+            v = v + tt
+            e = e - TF.pad(tt, (0, Hn - N))
+        scale = torch.ones(N, dtype=t.dtype, device=t.device)
+        scale[0] = 0.5
+        if Hn == N:
+            scale[N - 1] = 0.5
+        return v * scale
+    for M, accel, n_iter in ((8, 0.0, 0), (8, 0.5, 3), (32, 0.0, 2)):
+        (gx,), ws = _vjp(lambda t: F.fftcep(t, M, accel, n_iter), (x,), g)
+        (rx,) = _ref_vjp(lambda t: ref(t, M, accel, n_iter), (x,), ws)
+        assert torch.allclose(gx, rx, rtol=1e-8, atol=1e-10), (M, accel, n_iter)
