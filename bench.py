@@ -36,6 +36,8 @@ WORKLOADS = {
              1028, 100),
     "stft_grad": ("STFT power forward + backward (d/dwaveform, native adjoint kernel): 256 utt x 10 s", 256, 160000,
                   320 + 1028 + 320, 1028 + 320),
+    "delta": ("Delta + delta-delta features (widths 2, 2) of 13-dim cepstra: 4096 utt x 2001 frames", 4096, 160000,
+              52, 156),
     "istft": ("Inverse STFT (ifftr -> window -> overlap-add, one kernel): 256 utt x 10 s of complex spectra", 256,
               160000, 2056, 320),
 }
@@ -131,6 +133,8 @@ def _cpu_task(args):
         y = O.mfcc(O.stft(x), 13, 40, 16000)
     elif workload == "istft":  # x holds complex spectra
         y = O.istft(x)
+    elif workload == "delta":  # x holds 13-dim features
+        y = O.delta(x, [2, 2], True)
     elif workload == "stft_grad":  # the oracle has no autograd: forward only (a lower bound on the CPU cost)
         y = O.stft(x)
     else:  # mcep: x holds power spectra
@@ -154,6 +158,8 @@ def cpu_oracle_throughput(workload, utterances, T, steps, warmup, budget_s=25.0)
     elif workload == "istft":
         from oracle import np_oracle as O
         _CPU_X = O.stft(rng.standard_normal((utterances, T)).astype(np.float32), out_format="complex")
+    elif workload == "delta":
+        _CPU_X = rng.standard_normal((utterances, n_frames(T), 13)).astype(np.float32)
     else:
         _CPU_X = rng.standard_normal((utterances, T)).astype(np.float32)
     per = max(1, utterances // (cores * 2))
@@ -209,6 +215,10 @@ def make_step(workload, B, T, dev):
         with torch.no_grad():
             xs = [stft(torch.randn(B, T, generator=g, device=dev)) for _ in range(2)]
         return xs, lambda i: mcep(xs[i & 1])
+    if workload == "delta":
+        dl = D.Delta([2, 2], True).to(dev)
+        xs = [torch.randn(B, n_frames(T), 13, generator=g, device=dev) for _ in range(2)]
+        return xs, lambda i: dl(xs[i & 1])
     if workload == "istft":
         stft = D.STFT(FL, FP, NFFT, out_format="complex").to(dev)
         istft = D.ISTFT(FL, FP, NFFT).to(dev)
@@ -387,7 +397,7 @@ def main():
         v, ms, cores, desc = cpu_oracle_throughput(args.workload, min(B, 256), T, 3, 1)
         line["cpu_baseline"] = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
         extras = {}
-        for wl in ("lpc", "mfcc", "mcep", "istft", "stft_grad"):
+        for wl in ("lpc", "mfcc", "mcep", "istft", "stft_grad", "delta"):
             if wl == args.workload:
                 continue
             try:

@@ -100,6 +100,11 @@ def window(x: Tensor, out_length: int | None = None, *, window: str = "blackman"
     return nn.Window._func(x, out_length=out_length, window=window, norm=norm, symmetric=symmetric)
 
 
+def delta(x: Tensor, seed=[[-0.5, 0, 0.5]], static_out: bool = True) -> Tensor:  # noqa: B006 (reference default)
+    """Delta features ``(B, T, D) or (T, D) -> (..., T, D x H)``."""
+    return nn.Delta._func(x, seed, static_out=static_out)
+
+
 def fftcep(x: Tensor, cep_order: int, accel: float = 0, n_iter: int = 0) -> Tensor:
     """Cepstral analysis ``(..., L/2+1) -> (..., M+1)`` (improved cepstral method)."""
     return nn.CepstralAnalysis._func(x, cep_order=cep_order, accel=accel, n_iter=n_iter)

@@ -4,6 +4,7 @@ diffsptk/modules/__init__.py:17-175)."""
 from .acorr import Autocorrelation
 from .dct import DiscreteCosineTransform
 from .dct import DiscreteCosineTransform as DCT
+from .delta import Delta
 from .fbank import MelFilterBankAnalysis
 from .fftcep import CepstralAnalysis
 from .fbank import MelFilterBankAnalysis as FBANK
@@ -30,5 +31,5 @@ __all__ = [
     "RealValuedFastFourierTransform", "Frame", "FrequencyTransform", "LevinsonDurbin",
     "LinearPredictiveCodingAnalysis", "LPC", "MelCepstralAnalysis",
     "MelFrequencyCepstralCoefficientsAnalysis", "MFCC", "Spectrum", "ShortTimeFourierTransform", "STFT",
-    "Window", "RealValuedInverseFastFourierTransform", "Unframe", "InverseShortTimeFourierTransform", "ISTFT", "CepstralAnalysis",
+    "Window", "RealValuedInverseFastFourierTransform", "Unframe", "InverseShortTimeFourierTransform", "ISTFT", "CepstralAnalysis", "Delta",
 ]

@@ -1010,3 +1010,52 @@ def _istft_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{_NS}::istft", _istft_bwd, setup_context=_istft_setup)
+
+
+# ------------------------------------------------------------------ delta features (section 8f rank 4)
+def _delta_call(name: str, src: Tensor, window: Tensor, dim_out: int, D: int) -> Tensor:
+    dt = _native_dtype(src, window)
+    sc, wc = _prep(src, dt), _prep(window, dt)
+    Tn = sc.shape[-2]
+    B = sc.numel() // max(Tn * sc.shape[-1], 1)
+    out = torch.empty((*sc.shape[:-1], dim_out), device=src.device, dtype=dt)
+    N.check(N.typed(name, dt == torch.float64)(_ptr(sc), _ptr(wc), _ptr(out), B, Tn, D, wc.shape[0], wc.shape[1],
+                                               _dev(src), _stream(src)))
+    return out
+
+
+@torch.library.custom_op(f"{_NS}::delta", mutates_args=(), device_types="cuda")
+def delta(x: Tensor, window: Tensor) -> Tensor:
+    """``x`` ``(..., T, D)``, ``window`` ``(H, W)`` -> ``(..., T, H D)`` (replicate padding over T)."""
+    return _delta_call("dsb200_delta", x, window, window.shape[0] * x.shape[-1], x.shape[-1])
+
+
+@delta.register_fake
+def _(x, window):
+    return x.new_empty((*x.shape[:-1], window.shape[0] * x.shape[-1]), dtype=_native_dtype(x, window))
+
+
+@torch.library.custom_op(f"{_NS}::delta_backward", mutates_args=(), device_types="cuda")
+def delta_backward(gy: Tensor, window: Tensor) -> Tensor:
+    D = gy.shape[-1] // window.shape[0]
+    return _delta_call("dsb200_delta_backward", gy, window, D, D)
+
+
+@delta_backward.register_fake
+def _(gy, window):
+    return gy.new_empty((*gy.shape[:-1], gy.shape[-1] // window.shape[0]), dtype=_native_dtype(gy, window))
+
+
+def _delta_setup(ctx, inputs, output):
+    x, window_t = inputs
+    ctx.save_for_backward(x, window_t)
+
+
+def _delta_bwd(ctx, g):
+    x, w = ctx.saved_tensors
+    if ctx.needs_input_grad[1]:
+        raise NotImplementedError("gradients with respect to the regression window are not implemented")
+    return _like_input(delta_backward(g, w), x), None
+
+
+torch.library.register_autograd(f"{_NS}::delta", _delta_bwd, setup_context=_delta_setup)

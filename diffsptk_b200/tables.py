@@ -292,3 +292,52 @@ def make_lifter(mfcc_order, lifter, device=None, dtype=None):
     v = 1 + (lifter / 2) * torch.sin((torch.pi / lifter) * ramp)
     v[0] = 2 ** 0.5
     return v.to(dtype=_default_dtype(dtype))
+
+
+@functools.lru_cache(maxsize=64)
+def _delta_window_cached(seed_key, static_out: bool, device, dtype):
+    """Regression windows (H, W), built in double exactly like diffsptk/modules/delta.py:98-170."""
+    seed = [list(s) if isinstance(s, tuple) else s for s in seed_key]
+    if isinstance(seed[0], list):
+        rows = ([[1.0]] if static_out else []) + [list(map(float, c)) for c in seed]
+        max_len = max(len(c) for c in rows)
+        if max_len % 2 == 0:
+            max_len += 1
+        window = []
+        for c in rows:
+            diff = max_len - len(c)
+            left, right = (diff // 2, diff // 2) if diff % 2 == 0 else ((diff - 1) // 2, (diff + 1) // 2)
+            window.append(torch.tensor([0.0] * left + c + [0.0] * right, dtype=torch.double))
+    else:
+        if min(seed) <= 0:
+            raise ValueError("The width of regression coefficients must be positive.")
+        if len(seed) >= 3:
+            raise ValueError("3rd order regression is not supported.")
+        max_len = max(seed) * 2 + 1
+        window = []
+        if static_out:
+            w = torch.zeros(max_len, dtype=torch.double)
+            w[(max_len - 1) // 2] = 1
+            window.append(w)
+        n = seed[0]
+        z = 1 / (n * (n + 1) * (2 * n + 1) / 3)
+        j = torch.arange(-n, n + 1, dtype=torch.double)
+        p = (max_len - (n * 2 + 1)) // 2
+        window.append(torch.nn.functional.pad(j * z, (p, p)))
+        if len(seed) >= 2:
+            n = seed[1]
+            a0 = 2 * n + 1
+            a1 = a0 * n * (n + 1) / 3
+            a2 = a1 * (3 * n * n + 3 * n - 1) / 5
+            z = 1 / (2 * (a2 * a0 - a1 * a1))
+            j = torch.arange(-n, n + 1, dtype=torch.double)
+            p = (max_len - (n * 2 + 1)) // 2
+            window.append(torch.nn.functional.pad((a0 * j * j - a1) * z, (p, p)))
+    return _cast(torch.stack(window), device, dtype)
+
+
+def make_delta_window(seed, static_out: bool = True, device=None, dtype=None) -> Tensor:
+    if not isinstance(seed, (tuple, list)):
+        raise ValueError("seed must be tuple or list.")
+    key = tuple(tuple(s) if isinstance(s, (tuple, list)) else s for s in seed)
+    return _delta_window_cached(key, bool(static_out), _dev_key(device), dtype).clone()

@@ -244,6 +244,15 @@ DSB200_DECL2(dsb200_istft, (const void* Y, const void* window, void* out, int64_
                             int64_t out_length, int32_t frame_length, int32_t frame_period, int32_t fft_length,
                             int32_t center, int device, void* stream))
 
+/* Delta (regression) features over the frame axis (diffsptk/modules/delta.py:172-194), replicate padding:
+ * x[batch, n_frames, dim], window[n_windows, width] (width odd) -> y[batch, n_frames, n_windows * dim];
+ * the backward entry takes gy with y's layout and overwrites gx[batch, n_frames, dim]. */
+DSB200_DECL2(dsb200_delta, (const void* x, const void* window, void* y, int64_t batch, int64_t n_frames,
+                            int32_t dim, int32_t n_windows, int32_t width, int device, void* stream))
+DSB200_DECL2(dsb200_delta_backward, (const void* gy, const void* window, void* gx, int64_t batch,
+                                     int64_t n_frames, int32_t dim, int32_t n_windows, int32_t width, int device,
+                                     void* stream))
+
 /* ---- host-buffer pipeline (the end-to-end path: pinned host -> device -> kernel -> host) -------------
  * One object owns two device staging slots and three streams (H2D, compute, D2H) and runs
  * dsb200_stft on utterance chunks so that copies overlap compute.  x_host[batch,T], y_host[batch,N,K]

@@ -226,6 +226,62 @@ def stft(x, *, frame_length=400, frame_period=80, fft_length=512, center=True, z
     return spec(g, fft_length=fft_length, eps=eps, relative_floor=relative_floor, out_format=out_format)
 
 
+# ----------------------------------------------------------------------------- delta
+# regression features over the frame axis.
+def delta_window(seed, static_out=True, dtype=np.float64):
+    """Regression windows (H, W).  diffsptk/modules/delta.py:98-170."""
+    if not isinstance(seed, (tuple, list)):
+        raise ValueError("seed must be tuple or list.")
+    if isinstance(seed[0], (tuple, list)):
+        rows = ([[1.0]] if static_out else []) + [list(map(float, c)) for c in seed]
+        max_len = max(len(c) for c in rows)
+        max_len += 1 if max_len % 2 == 0 else 0
+        out = []
+        for c in rows:
+            diff = max_len - len(c)
+            left = diff // 2 if diff % 2 == 0 else (diff - 1) // 2
+            out.append(np.array([0.0] * left + c + [0.0] * (diff - left)))
+    else:
+        if min(seed) <= 0:
+            raise ValueError("The width of regression coefficients must be positive.")
+        if len(seed) >= 3:
+            raise ValueError("3rd order regression is not supported.")
+        max_len = max(seed) * 2 + 1
+        out = []
+        if static_out:
+            w = np.zeros(max_len)
+            w[(max_len - 1) // 2] = 1
+            out.append(w)
+        n = seed[0]
+        j = np.arange(-n, n + 1, dtype=np.float64)
+        p = (max_len - (2 * n + 1)) // 2
+        out.append(np.pad(j * (1 / (n * (n + 1) * (2 * n + 1) / 3)), (p, p)))
+        if len(seed) >= 2:
+            n = seed[1]
+            a0 = 2 * n + 1
+            a1 = a0 * n * (n + 1) / 3
+            a2 = a1 * (3 * n * n + 3 * n - 1) / 5
+            j = np.arange(-n, n + 1, dtype=np.float64)
+            p = (max_len - (2 * n + 1)) // 2
+            out.append(np.pad((a0 * j * j - a1) * (1 / (2 * (a2 * a0 - a1 * a1))), (p, p)))
+    return np.stack(out).astype(dtype)
+
+
+def delta(x, seed=[[-0.5, 0, 0.5]], static_out=True):  # noqa: B006
+    """y[b, t, h D + d] = sum_w window[h, w] x[b, clamp(t + w - (W-1)/2), d].  delta.py:172-194."""
+    x = _as_float(x)
+    if x.ndim not in (2, 3):
+        raise ValueError("Input must be 2D or 3D tensor.")
+    win = delta_window(seed, static_out, x.dtype)
+    Hn, W = win.shape
+    T, D = x.shape[-2], x.shape[-1]
+    pad = (W - 1) // 2
+    idx = np.clip(np.arange(T)[:, None] + np.arange(W)[None, :] - pad, 0, T - 1)      # [T, W]
+    taps = x[..., idx, :]                                                            # [..., T, W, D]
+    y = np.einsum("hw,...twd->...thd", win, taps).astype(x.dtype)
+    return y.reshape(*x.shape[:-1], Hn * D)
+
+
 # ----------------------------------------------------------------------------- fftcep
 # SURVEY.md section 8(f) rank 3: a direct consumer of the STFT power spectrum.
 def fftcep(x, cep_order, accel=0.0, n_iter=0):

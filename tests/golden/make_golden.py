@@ -217,6 +217,14 @@ def cases():
             yield (f"fftcep_16_m{M}_i{it}", "fftcep", dict(cep_order=M, accel=0.5 if it else 0.0, n_iter=it), [P9])
     P257 = ri.standard_normal((2, 5, 257)) ** 2 + 1e-3
     yield ("fftcep_512_m24", "fftcep", dict(cep_order=24, accel=0.0, n_iter=0), [P257])
+    # ---- delta, section 8(f) rank 4 (tests/test_delta.py) ---------------------------------------------------
+    xd = ri.standard_normal((2, 9, 3))
+    for i, (seed, so) in enumerate(([[[-0.5, 0, 0.5]], True], [[[-0.5, 0, 0.5], [1, -2, 1]], True],
+                                    [[[1, -1]], False], [[2], True], [[3, 2], False], [[1, 1], True])):
+        yield (f"delta_seed{i}", "delta", dict(seed=seed, static_out=so), [xd])
+    yield ("delta_2d", "delta", dict(seed=[[-0.5, 0, 0.5], [1, -2, 1]], static_out=True), [ri.standard_normal((7, 4))])
+    yield ("delta_one_frame", "delta", dict(seed=[2, 2], static_out=True), [ri.standard_normal((3, 1, 5))])
+    yield ("delta_mfcc_like", "delta", dict(seed=[2, 2], static_out=True), [ri.standard_normal((4, 200, 13))])
     yield ("fftcep_512_m24_i5", "fftcep", dict(cep_order=24, accel=1.0, n_iter=5), [P257])
 
 

@@ -476,3 +476,26 @@ def test_fftcep_gradients():
         (gx,), ws = _vjp(lambda t: F.fftcep(t, M, accel, n_iter), (x,), g)
         (rx,) = _ref_vjp(lambda t: ref(t, M, accel, n_iter), (x,), ws)
         assert torch.allclose(gx, rx, rtol=1e-8, atol=1e-10), (M, accel, n_iter)
+
+
+def test_delta_gradients():
+    import diffsptk_b200 as B
+    d = dev()
+    g = torch.Generator().manual_seed(41)
+    for shape, seed, so in (((2, 9, 3), [[-0.5, 0, 0.5], [1, -2, 1]], True), ((7, 4), [3, 2], False),
+                            ((3, 1, 5), [2, 2], True), ((2, 2, 6), [[1, -1, 2, 0.5, 3]], True)):
+        x = torch.randn(*shape, generator=g, dtype=torch.float64).to(d).requires_grad_(True)
+        mod = B.Delta(seed, so, dtype=torch.float64).to(d)
+
+        def ref(t):   # delta.py:172-194
+            t3 = t if t.dim() == 3 else t.unsqueeze(0)
+            Bn, Tn, _ = t3.shape
+            W = mod.window.size(-1)
+            p = (W - 1) // 2
+            y = TF.conv2d(TF.pad(t3.unsqueeze(1), (0, 0, p, p), mode="replicate"), mod.window.view(-1, 1, W, 1))
+            y = y.permute(0, 2, 1, 3).reshape(Bn, Tn, -1)
+            return y if t.dim() == 3 else y.squeeze(0)
+        (gx,), ws = _vjp(mod, (x,), g)
+        (rx,) = _ref_vjp(ref, (x,), ws)
+        assert torch.allclose(mod(x), ref(x), rtol=1e-12, atol=1e-12), (shape, seed)
+        assert torch.allclose(gx, rx, rtol=1e-10, atol=1e-12), (shape, seed)

@@ -100,6 +100,8 @@ def build_module(op, params, ins, prec):
         return B.DCT(n, **p, device=d, dtype=dt)
     if op == "fftcep":
         return B.CepstralAnalysis(fft_length=2 * n - 2, **p)
+    if op == "delta":
+        return B.Delta(**p, device=d, dtype=dt)
     if op == "ifftr":
         return B.RealValuedInverseFastFourierTransform(2 * n - 2, p.pop("out_length"), device=d, dtype=dt)
     if op == "unframe":
