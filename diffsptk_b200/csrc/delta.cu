@@ -1,8 +1,8 @@
 // Delta (regression) features over the frame axis: diffsptk/modules/delta.py:172-194.
 //   y[b, t, h D + d] = sum_w window[h, w] x[b, clamp(t + w - (W-1)/2, 0, T-1), d]      (replicate padding)
 // A pure HBM-bound stencil: D * 4 B read (the W-row halo stays in L1/L2) and H * D * 4 B written per frame.
-// One thread per (frame, feature) pair, consecutive threads on consecutive features: every load and store is
-// coalesced.  The backward kernel is the adjoint gather (border frames collect the clamped taps).
+// Forward: CTA tiles of frames staged in shared memory, fully coalesced loads and stores.  The backward kernel is
+// the adjoint gather, one thread per (frame, feature) pair (border frames collect the clamped taps).
 #include <algorithm>
 
 #include "common.cuh"
@@ -12,31 +12,53 @@ namespace {
 
 constexpr int kMaxTaps = 1024;   // H * W window coefficients kept in shared memory
 
+// A CTA owns a tile of `tt` consecutive frames of one utterance: the tt + W - 1 input rows it needs (clamped at the
+// utterance ends = replicate padding) are staged in shared memory with coalesced loads, and the tile's
+// tt x (H D) outputs, one contiguous span of y, are written with coalesced stores.
 template <typename T>
 __global__ void __launch_bounds__(256) delta_kernel(const T* __restrict__ x, const T* __restrict__ win,
                                                     T* __restrict__ y, int64_t batch, int64_t Tn, int D, int Hn,
-                                                    int W) {
-  __shared__ T ws[kMaxTaps];
+                                                    int W, int tt, int64_t tiles_per_utt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* ws = reinterpret_cast<T*>(smem_raw);      // [H W]
+  T* xs = ws + Hn * W;                         // [tt + W - 1][D] staged input rows
+  T* ys = xs + (tt + W - 1) * D;               // [tt][H D] staged outputs
   for (int i = threadIdx.x; i < Hn * W; i += blockDim.x) ws[i] = win[i];
-  __syncthreads();
-  const int pad = (W - 1) / 2;
-  const int64_t total = batch * Tn * D;
-  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const int64_t bt = i / D;
-    const int d = static_cast<int>(i - bt * D);
-    const int64_t b = bt / Tn, t = bt - b * Tn;
-    const T* xb = x + b * Tn * D + d;
-    T* yo = y + bt * (static_cast<int64_t>(Hn) * D) + d;
-    for (int h = 0; h < Hn; ++h) {
-      T acc = 0;
-      for (int w = 0; w < W; ++w) {
-        int64_t tt = t + w - pad;
-        tt = tt < 0 ? 0 : (tt > Tn - 1 ? Tn - 1 : tt);
-        acc = dfma(ws[h * W + w], xb[tt * D], acc);
-      }
-      yo[static_cast<int64_t>(h) * D] = acc;
+  const int pad = (W - 1) / 2, HD = Hn * D;
+  // (row, feature) of flat index tid, advanced by blockDim per iteration without divisions
+  const int nthr = blockDim.x, step_r = nthr / D, step_d = nthr - step_r * D;
+  const int r0 = threadIdx.x / D, d0 = threadIdx.x - r0 * D;
+  const int64_t n_tiles = batch * tiles_per_utt;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b = tile / tiles_per_utt;
+    const int64_t t0 = (tile - b * tiles_per_utt) * tt;
+    const int nt = static_cast<int>(Tn - t0 < tt ? Tn - t0 : tt);
+    const T* xb = x + b * Tn * D;
+    __syncthreads();                           // previous tile's copy-out (and the window table) is done
+    for (int i = threadIdx.x, r = r0, d = d0; i < (nt + W - 1) * D; i += nthr) {
+      int64_t t = t0 + r - pad;
+      t = t < 0 ? 0 : (t > Tn - 1 ? Tn - 1 : t);
+      xs[i] = xb[t * D + d];
+      r += step_r;
+      d += step_d;
+      if (d >= D) { d -= D; ++r; }
     }
+    __syncthreads();
+    for (int i = threadIdx.x, r = r0, d = d0; i < nt * D; i += nthr) {
+      const T* xp = xs + i;                    // tap w of frame r, feature d is xs[(r + w) D + d]
+      T* yp = ys + r * HD + d;
+      for (int h = 0; h < Hn; ++h) {
+        T acc = 0;
+        for (int w = 0; w < W; ++w) acc = dfma(ws[h * W + w], xp[w * D], acc);
+        yp[h * D] = acc;
+      }
+      r += step_r;
+      d += step_d;
+      if (d >= D) { d -= D; ++r; }
+    }
+    __syncthreads();
+    T* yo = y + (b * Tn + t0) * HD;            // the tile's outputs are one contiguous span
+    for (int o = threadIdx.x; o < nt * HD; o += nthr) yo[o] = ys[o];
   }
 }
 
@@ -94,15 +116,26 @@ int delta_impl(const void* in, const void* win, void* out, int64_t batch, int64_
   DSB_REQUIRE(in && win && out, "NULL data pointer");
   DeviceScope ds(device);
   DSB_CUDA(ds.err);
-  const int64_t total = batch * Tn * D;
-  const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count(device)) * 16));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (BWD)
+  if (BWD) {
+    const int64_t total = batch * Tn * D;
+    const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count(device)) * 16));
     delta_bwd_kernel<T><<<blocks, 256, 0, s>>>(static_cast<const T*>(in), static_cast<const T*>(win),
                                                static_cast<T*>(out), batch, Tn, D, Hn, W);
-  else
-    delta_kernel<T><<<blocks, 256, 0, s>>>(static_cast<const T*>(in), static_cast<const T*>(win),
-                                           static_cast<T*>(out), batch, Tn, D, Hn, W);
+  } else {
+    // frames per tile: ~16 KB of staged input rows, at least one frame, at most 128
+    int tt = static_cast<int>(std::min<int64_t>(128, std::max<int64_t>(1, 16384 / (static_cast<int64_t>(D) * sizeof(T)))));
+    if (tt > Tn) tt = static_cast<int>(Tn);
+    const size_t smem = (static_cast<size_t>(Hn) * W + static_cast<size_t>(tt + W - 1) * D +
+                         static_cast<size_t>(tt) * Hn * D) * sizeof(T);
+    if (smem > static_cast<size_t>(max_dynamic_smem(device)))
+      return fail(DSB200_E_UNSUPPORTED, "feature dimension %d is too large for the delta kernel's shared memory", D);
+    DSB_CUDA(cudaFuncSetAttribute(delta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    const int64_t tiles_per_utt = (Tn + tt - 1) / tt;
+    const int blocks = static_cast<int>(std::min<int64_t>(batch * tiles_per_utt, static_cast<int64_t>(sm_count(device)) * 8));
+    delta_kernel<T><<<blocks, 256, smem, s>>>(static_cast<const T*>(in), static_cast<const T*>(win),
+                                              static_cast<T*>(out), batch, Tn, D, Hn, W, tt, tiles_per_utt);
+  }
   return after_launch(BWD ? "delta_bwd_kernel" : "delta_kernel");
 }
 
