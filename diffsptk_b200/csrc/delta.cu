@@ -15,10 +15,12 @@ constexpr int kMaxTaps = 1024;   // H * W window coefficients kept in shared mem
 // A CTA owns a tile of `tt` consecutive frames of one utterance: the tt + W - 1 input rows it needs (clamped at the
 // utterance ends = replicate padding) are staged in shared memory with coalesced loads, and the tile's
 // tt x (H D) outputs, one contiguous span of y, are written with coalesced stores.
-template <typename T>
+// WC > 0: the window length is a compile-time constant (taps in registers, unrolled); WC == 0: any odd length.
+template <typename T, int WC>
 __global__ void __launch_bounds__(256) delta_kernel(const T* __restrict__ x, const T* __restrict__ win,
                                                     T* __restrict__ y, int64_t batch, int64_t Tn, int D, int Hn,
-                                                    int W, int tt, int64_t tiles_per_utt) {
+                                                    int Wrt, int tt, int64_t tiles_per_utt) {
+  const int W = WC > 0 ? WC : Wrt;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* ws = reinterpret_cast<T*>(smem_raw);      // [H W]
   T* xs = ws + Hn * W;                         // [tt + W - 1][D] staged input rows
@@ -47,10 +49,22 @@ __global__ void __launch_bounds__(256) delta_kernel(const T* __restrict__ x, con
     for (int i = threadIdx.x, r = r0, d = d0; i < nt * D; i += nthr) {
       const T* xp = xs + i;                    // tap w of frame r, feature d is xs[(r + w) D + d]
       T* yp = ys + r * HD + d;
-      for (int h = 0; h < Hn; ++h) {
-        T acc = 0;
-        for (int w = 0; w < W; ++w) acc = dfma(ws[h * W + w], xp[w * D], acc);
-        yp[h * D] = acc;
+      if constexpr (WC > 0) {
+        T tap[WC];
+#pragma unroll
+        for (int w = 0; w < WC; ++w) tap[w] = xp[w * D];
+        for (int h = 0; h < Hn; ++h) {
+          T acc = 0;
+#pragma unroll
+          for (int w = 0; w < WC; ++w) acc = dfma(ws[h * WC + w], tap[w], acc);
+          yp[h * D] = acc;
+        }
+      } else {
+        for (int h = 0; h < Hn; ++h) {
+          T acc = 0;
+          for (int w = 0; w < W; ++w) acc = dfma(ws[h * W + w], xp[w * D], acc);
+          yp[h * D] = acc;
+        }
       }
       r += step_r;
       d += step_d;
@@ -130,11 +144,24 @@ int delta_impl(const void* in, const void* win, void* out, int64_t batch, int64_
                          static_cast<size_t>(tt) * Hn * D) * sizeof(T);
     if (smem > static_cast<size_t>(max_dynamic_smem(device)))
       return fail(DSB200_E_UNSUPPORTED, "feature dimension %d is too large for the delta kernel's shared memory", D);
-    DSB_CUDA(cudaFuncSetAttribute(delta_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const int64_t tiles_per_utt = (Tn + tt - 1) / tt;
     const int blocks = static_cast<int>(std::min<int64_t>(batch * tiles_per_utt, static_cast<int64_t>(sm_count(device)) * 8));
-    delta_kernel<T><<<blocks, 256, smem, s>>>(static_cast<const T*>(in), static_cast<const T*>(win),
-                                              static_cast<T*>(out), batch, Tn, D, Hn, W, tt, tiles_per_utt);
+    auto launch = [&](auto kern) -> int {
+      DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      kern<<<blocks, 256, smem, s>>>(static_cast<const T*>(in), static_cast<const T*>(win), static_cast<T*>(out), batch,
+                                     Tn, D, Hn, W, tt, tiles_per_utt);
+      return DSB200_OK;
+    };
+    int rc;
+    switch (W) {
+      case 1: rc = launch(delta_kernel<T, 1>); break;
+      case 3: rc = launch(delta_kernel<T, 3>); break;
+      case 5: rc = launch(delta_kernel<T, 5>); break;
+      case 7: rc = launch(delta_kernel<T, 7>); break;
+      case 9: rc = launch(delta_kernel<T, 9>); break;
+      default: rc = launch(delta_kernel<T, 0>); break;
+    }
+    if (rc != DSB200_OK) return rc;
   }
   return after_launch(BWD ? "delta_bwd_kernel" : "delta_kernel");
 }
