@@ -11,6 +11,7 @@ namespace dsb200 {
 namespace {
 
 constexpr int kMaxTaps = 1024;   // H * W window coefficients kept in shared memory
+constexpr int kPF = 8;           // staged input elements per thread (256 threads): a tile holds <= 2048 of them
 
 // A CTA owns a tile of `tt` consecutive frames of one utterance: the tt + W - 1 input rows it needs (clamped at the
 // utterance ends = replicate padding) are staged in shared memory with coalesced loads, and the tile's
@@ -31,20 +32,37 @@ __global__ void __launch_bounds__(256) delta_kernel(const T* __restrict__ x, con
   const int nthr = blockDim.x, step_r = nthr / D, step_d = nthr - step_r * D;
   const int r0 = threadIdx.x / D, d0 = threadIdx.x - r0 * D;
   const int64_t n_tiles = batch * tiles_per_utt;
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // Software pipeline: the rows of the NEXT tile are fetched into registers (<= kPF elements per thread, the host
+  // sizes the tile accordingly) before the current tile is computed, so their HBM latency hides behind it.
+  T pf[kPF];
+  auto fetch = [&](int64_t tile) {
     const int64_t b = tile / tiles_per_utt;
     const int64_t t0 = (tile - b * tiles_per_utt) * tt;
     const int nt = static_cast<int>(Tn - t0 < tt ? Tn - t0 : tt);
     const T* xb = x + b * Tn * D;
-    __syncthreads();                           // previous tile's copy-out (and the window table) is done
-    for (int i = threadIdx.x, r = r0, d = d0; i < (nt + W - 1) * D; i += nthr) {
-      int64_t t = t0 + r - pad;
-      t = t < 0 ? 0 : (t > Tn - 1 ? Tn - 1 : t);
-      xs[i] = xb[t * D + d];
+    int r = r0, d = d0;
+#pragma unroll
+    for (int k = 0; k < kPF; ++k) {
+      if (threadIdx.x + k * nthr < (nt + W - 1) * D) {
+        int64_t t = t0 + r - pad;
+        t = t < 0 ? 0 : (t > Tn - 1 ? Tn - 1 : t);
+        pf[k] = xb[t * D + d];
+      }
       r += step_r;
       d += step_d;
       if (d >= D) { d -= D; ++r; }
     }
+  };
+  if (blockIdx.x < n_tiles) fetch(blockIdx.x);
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t b = tile / tiles_per_utt;
+    const int64_t t0 = (tile - b * tiles_per_utt) * tt;
+    const int nt = static_cast<int>(Tn - t0 < tt ? Tn - t0 : tt);
+    __syncthreads();                           // previous tile's copy-out (and the window table) is done
+#pragma unroll
+    for (int k = 0; k < kPF; ++k)
+      if (threadIdx.x + k * nthr < (nt + W - 1) * D) xs[threadIdx.x + k * nthr] = pf[k];
+    if (tile + gridDim.x < n_tiles) fetch(tile + gridDim.x);
     __syncthreads();
     for (int i = threadIdx.x, r = r0, d = d0; i < nt * D; i += nthr) {
       const T* xp = xs + i;                    // tap w of frame r, feature d is xs[(r + w) D + d]
@@ -73,6 +91,35 @@ __global__ void __launch_bounds__(256) delta_kernel(const T* __restrict__ x, con
     __syncthreads();
     T* yo = y + (b * Tn + t0) * HD;            // the tile's outputs are one contiguous span
     for (int o = threadIdx.x; o < nt * HD; o += nthr) yo[o] = ys[o];
+  }
+}
+
+// Fallback for feature dimensions too large for the tile kernel: one thread per (frame, feature) pair.
+template <typename T>
+__global__ void __launch_bounds__(256) delta_wide_kernel(const T* __restrict__ x, const T* __restrict__ win,
+                                                         T* __restrict__ y, int64_t batch, int64_t Tn, int D, int Hn,
+                                                         int W) {
+  __shared__ T ws[kMaxTaps];
+  for (int i = threadIdx.x; i < Hn * W; i += blockDim.x) ws[i] = win[i];
+  __syncthreads();
+  const int pad = (W - 1) / 2;
+  const int64_t total = batch * Tn * D;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t bt = i / D;
+    const int d = static_cast<int>(i - bt * D);
+    const int64_t b = bt / Tn, t = bt - b * Tn;
+    const T* xb = x + b * Tn * D + d;
+    T* yo = y + bt * (static_cast<int64_t>(Hn) * D) + d;
+    for (int h = 0; h < Hn; ++h) {
+      T acc = 0;
+      for (int w = 0; w < W; ++w) {
+        int64_t tt = t + w - pad;
+        tt = tt < 0 ? 0 : (tt > Tn - 1 ? Tn - 1 : tt);
+        acc = dfma(ws[h * W + w], xb[tt * D], acc);
+      }
+      yo[static_cast<int64_t>(h) * D] = acc;
+    }
   }
 }
 
@@ -137,8 +184,15 @@ int delta_impl(const void* in, const void* win, void* out, int64_t batch, int64_
     delta_bwd_kernel<T><<<blocks, 256, 0, s>>>(static_cast<const T*>(in), static_cast<const T*>(win),
                                                static_cast<T*>(out), batch, Tn, D, Hn, W);
   } else {
-    // frames per tile: ~16 KB of staged input rows, at least one frame, at most 128
-    int tt = static_cast<int>(std::min<int64_t>(128, std::max<int64_t>(1, 16384 / (static_cast<int64_t>(D) * sizeof(T)))));
+    // frames per tile: (tt + W - 1) D staged elements must fit the kPF x 256 register prefetch; at most 128 frames
+    if (static_cast<int64_t>(W) * D > kPF * 256) {   // a single frame's halo does not fit the tile kernel
+      const int64_t total = batch * Tn * D;
+      const int blocks = static_cast<int>(std::min<int64_t>((total + 255) / 256, static_cast<int64_t>(sm_count(device)) * 16));
+      delta_wide_kernel<T><<<blocks, 256, 0, s>>>(static_cast<const T*>(in), static_cast<const T*>(win),
+                                                  static_cast<T*>(out), batch, Tn, D, Hn, W);
+      return after_launch("delta_wide_kernel");
+    }
+    int tt = static_cast<int>(std::min<int64_t>(128, (kPF * 256) / D - (W - 1)));
     if (tt > Tn) tt = static_cast<int>(Tn);
     const size_t smem = (static_cast<size_t>(Hn) * W + static_cast<size_t>(tt + W - 1) * D +
                          static_cast<size_t>(tt) * Hn * D) * sizeof(T);

@@ -484,7 +484,8 @@ def test_delta_gradients():
     g = torch.Generator().manual_seed(41)
     for shape, seed, so in (((2, 9, 3), [[-0.5, 0, 0.5], [1, -2, 1]], True), ((7, 4), [3, 2], False),
                             ((3, 1, 5), [2, 2], True), ((2, 2, 6), [[1, -1, 2, 0.5, 3]], True),
-                            ((2, 20, 3), [5], True), ((1, 300, 40), [4, 3], True)):   # widths 11 and 9
+                            ((2, 20, 3), [5], True), ((1, 300, 40), [4, 3], True),     # widths 11 and 9
+                            ((2, 6, 700), [2], True)):                                # wide features: fallback kernel
         x = torch.randn(*shape, generator=g, dtype=torch.float64).to(d).requires_grad_(True)
         mod = B.Delta(seed, so, dtype=torch.float64).to(d)
 
