@@ -1,0 +1,165 @@
+// Per-frame coefficient converters on LPC / cepstral rows: one launch reads every
+// row once and writes it once -- HBM-bound at 2 * dim * sizeof(T) bytes per row.
+//
+//   DSB200_CONV_LPC2PAR  lpc2par.py:104-120   [K, a_1..a_M] -> [K, k_1..k_M]   (step-down recursion, gamma)
+//   DSB200_CONV_PAR2LPC  par2lpc.py:100-107   [K, k_1..k_M] -> [K, a_1..a_M] / gamma (step-up recursion)
+//   DSB200_CONV_GNORM    gnorm.py:101-112     gain normalisation of a generalized cepstrum (gamma)
+//   DSB200_CONV_IGNORM   ignorm.py:98-109     its inverse
+//   DSB200_CONV_NORM0    norm0.py:88-94       [K, a_1..a_M] -> [1/K, a_1/K..a_M/K]
+//
+// Mapping: a CTA stages a tile of 256 rows in shared memory with coalesced loads (row pitch odd, so that the
+// per-thread row walks below are bank-conflict free), ONE THREAD owns one row and runs the recursion in place --
+// the recursions are sequential in the order m and only O(M^2) flops on M + 1 values, far below the HBM time of
+// the row -- then the tile leaves with coalesced stores.
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dsb200 {
+namespace {
+
+constexpr int kThreads = 256;
+
+template <typename T>
+__device__ __forceinline__ void convert_row(T* a, int D, int op, T g) {
+  const int M = D - 1;
+  switch (op) {
+    case DSB200_CONV_LPC2PAR: {
+      // a[1 + i] <- gamma a_i; for m = M-1..1: k_m = a[m]; a[i] <- (a[i] - k_m a[m-1-i]) / (1 - k_m^2), i < m
+      T* c = a + 1;
+      for (int i = 0; i < M; ++i) c[i] *= g;
+      for (int m = M - 1; m >= 1; --m) {
+        const T km = c[m];
+        const T z = static_cast<T>(1) - km * km;
+        for (int i = 0, j = m - 1; i <= j; ++i, --j) {
+          const T ci = c[i], cj = c[j];
+          c[i] = (ci - km * cj) / z;
+          if (j != i) c[j] = (cj - km * ci) / z;
+        }
+      }
+      break;
+    }
+    case DSB200_CONV_PAR2LPC: {
+      // a <- k / gamma (the gain too, as the reference does); for m = 2..M: a[1..m) += k_m flip(a[1..m))
+      // k_m is the UNDIVIDED coefficient, so a[m] is divided only after it was used as k_m.
+      a[0] = a[0] / g;
+      if (M >= 1) a[1] = a[1] / g;
+      for (int m = 2; m <= M; ++m) {
+        const T km = a[m];
+        for (int i = 1, j = m - 1; i <= j; ++i, --j) {
+          const T ai = a[i], aj = a[j];
+          a[i] = ai + km * aj;
+          if (j != i) a[j] = aj + km * ai;
+        }
+        a[m] = km / g;
+      }
+      break;
+    }
+    case DSB200_CONV_GNORM: {
+      if (g == static_cast<T>(0)) {
+        a[0] = dexp(a[0]);
+      } else {
+        const T z = static_cast<T>(1) + g * a[0];
+        a[0] = dpow(z, static_cast<T>(1) / g);
+        for (int i = 1; i <= M; ++i) a[i] = a[i] / z;
+      }
+      break;
+    }
+    case DSB200_CONV_IGNORM: {
+      if (g == static_cast<T>(0)) {
+        a[0] = dlog(a[0]);
+      } else {
+        const T z = dpow(a[0], g);
+        a[0] = (z - static_cast<T>(1)) / g;
+        for (int i = 1; i <= M; ++i) a[i] = a[i] * z;
+      }
+      break;
+    }
+    default: {  // DSB200_CONV_NORM0
+      const T b0 = static_cast<T>(1) / a[0];
+      a[0] = b0;
+      for (int i = 1; i <= M; ++i) a[i] = a[i] * b0;
+      break;
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) rowconv_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows,
+                                                           int D, int pitch, int op, T g) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  T* tile = reinterpret_cast<T*>(smem_raw);   // [kThreads][pitch]
+  const int64_t n_tiles = (rows + kThreads - 1) / kThreads;
+  for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int64_t base = t * kThreads;
+    const int nr = static_cast<int>(rows - base < kThreads ? rows - base : kThreads);
+    const T* src = x + base * D;
+    T* dst = y + base * D;
+    // coalesced load: element e of the tile -> (row e / D, column e % D), walked incrementally
+    {
+      int r = threadIdx.x / D, c = threadIdx.x - r * D;
+      const int dr = kThreads / D, dc = kThreads - dr * D;
+      for (int e = threadIdx.x; e < nr * D; e += kThreads) {
+        tile[r * pitch + c] = src[e];
+        r += dr;
+        c += dc;
+        if (c >= D) { c -= D; ++r; }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < nr) convert_row<T>(tile + threadIdx.x * pitch, D, op, g);
+    __syncthreads();
+    {
+      int r = threadIdx.x / D, c = threadIdx.x - r * D;
+      const int dr = kThreads / D, dc = kThreads - dr * D;
+      for (int e = threadIdx.x; e < nr * D; e += kThreads) {
+        dst[e] = tile[r * pitch + c];
+        r += dr;
+        c += dc;
+        if (c >= D) { c -= D; ++r; }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+template <typename T>
+int rowconv_impl(const void* x, void* y, int64_t rows, int32_t dim, int32_t op, double param, int device, void* stream) {
+  DSB_REQUIRE(dim >= 1, "dim must be positive");
+  DSB_REQUIRE(rows >= 0, "rows must be non-negative");
+  DSB_REQUIRE(op >= DSB200_CONV_LPC2PAR && op <= DSB200_CONV_NORM0, "converter %d is not supported.", op);
+  if ((op == DSB200_CONV_LPC2PAR || op == DSB200_CONV_PAR2LPC || op == DSB200_CONV_GNORM || op == DSB200_CONV_IGNORM) &&
+      !(param >= -1.0 && param <= 1.0))
+    return fail(DSB200_E_BAD_PARAM, "gamma must be in [-1, 1].");
+  if (rows == 0) return DSB200_OK;
+  DSB_REQUIRE(x != nullptr && y != nullptr, "NULL data pointer");
+  DeviceScope ds(device);
+  DSB_CUDA(ds.err);
+  const int pitch = dim | 1;
+  const size_t smem = static_cast<size_t>(kThreads) * pitch * sizeof(T);
+  if (smem > static_cast<size_t>(max_dynamic_smem(device)))
+    return fail(DSB200_E_UNSUPPORTED, "row length %d does not fit in shared memory", dim);
+  DSB_CUDA(cudaFuncSetAttribute(rowconv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const int64_t n_tiles = (rows + kThreads - 1) / kThreads;
+  const int per_sm = std::max<int>(1, std::min<int>(8, static_cast<int>((200 * 1024) / std::max<size_t>(smem, 1))));
+  const int blocks = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count(device)) * per_sm));
+  rowconv_kernel<T><<<blocks, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const T*>(x), static_cast<T*>(y), rows, dim, pitch, op, static_cast<T>(param));
+  return after_launch("rowconv_kernel");
+}
+
+}  // namespace
+}  // namespace dsb200
+
+extern "C" {
+
+int dsb200_rowconv_f32(const void* x, void* y, int64_t rows, int32_t dim, int32_t op, double param, int device,
+                       void* stream) {
+  return dsb200::rowconv_impl<float>(x, y, rows, dim, op, param, device, stream);
+}
+int dsb200_rowconv_f64(const void* x, void* y, int64_t rows, int32_t dim, int32_t op, double param, int device,
+                       void* stream) {
+  return dsb200::rowconv_impl<double>(x, y, rows, dim, op, param, device, stream);
+}
+
+}  // extern "C"

@@ -45,6 +45,7 @@ constexpr int kWarpsSpectrum = 16;
 constexpr int kWarpsMfcc = 12;
 constexpr int kOutFloats = 4 * 257;                    // one quad of real-valued output rows
 constexpr int kDefaultBulkStore = 1;                   // see stft512_try (DSB200_STFT_STORE)
+constexpr int kDefaultVariant = 1;                     // see stft512_try (DSB200_STFT_V)
 
 struct Args {
   const float* x;
@@ -116,9 +117,23 @@ __device__ __forceinline__ void put_bin(float* rowA, float* rowB, bool vB, int k
   }
 }
 
-template <int NJ, bool MASK_ALL, int FMT, int W>
+// V (variant bits): 1 = a half-warp pairs frames (f, f + 2) instead of (f, f + 1): with 2 P = 32 kShift floats the
+// second frame's column j is the first frame's column j + kShift of the SAME lane, so a lane reads NJ + kShift
+// instead of 2 NJ sample pairs from shared memory (frame_period 80 only): -8 LDS.64 and -16 shared-memory
+// wavefronts per quad, 0.1946 -> 0.1926 ms at BASELINE config 2 (profiles/r1_stft512_v4_sweep.json).
+// Tried on the same sweep and dropped: staging spans / output rows at the 128-byte phase of their global address
+// (the bank conflicts ncu attributes to the bulk copies do not come from misalignment: no change), dropping the
+// proxy fence in front of the span copies (no change), and moving (re A, re B, im A, im B) through the transposes
+// as one 128-bit access (32 fewer LDS/STS but 60 more MOVs to build aligned register quads).
+constexpr int kVPair2 = 1;
+constexpr int kShift = 5;   // 2 * 80 / 32
+
+template <int NJ, bool MASK_ALL, int FMT, int W, int V = 0>
 __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   constexpr int kWarps = W, kThreads = W * 32;
+  constexpr bool PAIR2 = (V & kVPair2) != 0;
+  constexpr int kFB = PAIR2 ? 2 : 1;        // frame B = frame A + kFB
+  constexpr int kRowB = kFB * 257;          // its staged row
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -231,18 +246,30 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     __syncwarp();  // zero-fill / guarded stores of the other lanes
     const float* span = in0 + buf * A.in_floats;
 
-    const int fA = 4 * g + 2 * h;
+    const int hf = PAIR2 ? h : 2 * h;         // first frame of this half-warp's pair within the quad
+    const int fA = 4 * g + hf;
     const int rows = (A.n_frames - 4 * g) < 4 ? (A.n_frames - 4 * g) : 4;   // valid frames in the quad
-    const bool vA = fA < A.n_frames, vB = (fA + 1) < A.n_frames;
-    const float* pa = span + (2 * h) * A.P + 2 * l;
+    const bool vA = fA < A.n_frames, vB = (fA + kFB) < A.n_frames;
+    const float* pa = span + hf * A.P + 2 * l;
     const float* pb = pa + A.P;
 
     C2 a[16];
+    float2 raw[PAIR2 ? NJ + kShift : 1];
+    if (PAIR2) {
+#pragma unroll
+      for (int j = 0; j < NJ + kShift; ++j) raw[PAIR2 ? j : 0] = *reinterpret_cast<const float2*>(pa + 32 * j);
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       if (j < NJ) {
-        float2 xa = *reinterpret_cast<const float2*>(pa + 32 * j);
-        float2 xb2 = *reinterpret_cast<const float2*>(pb + 32 * j);
+        float2 xa, xb2;
+        if (PAIR2) {
+          xa = raw[PAIR2 ? j : 0];
+          xb2 = raw[PAIR2 ? j + kShift : 0];
+        } else {
+          xa = *reinterpret_cast<const float2*>(pa + 32 * j);
+          xb2 = *reinterpret_cast<const float2*>(pb + 32 * j);
+        }
         const float2 wv = *reinterpret_cast<const float2*>(win + 2 * l + 32 * j);
         if (MASK_ALL || j == NJ - 1) {  // never let samples past the frame end in (0 * inf = nan)
           const int p0 = 2 * l + 32 * j;
@@ -306,11 +333,11 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       rowA = ostage + h * (2 * kAmpPitch);   // float2 amp2[kAmpPitch] of this half-warp's frame pair
       rowB = rowA;
     } else if (staged) {
-      rowA = ostage + (2 * h) * 257;
-      rowB = rowA + 257;
+      rowA = ostage + hf * 257;
+      rowB = rowA + kRowB;
     } else {
-      rowA = A.y + (row0 + 2 * h) * kStride;
-      rowB = rowA + kStride;
+      rowA = A.y + (row0 + hf) * kStride;
+      rowB = rowA + kFB * kStride;
     }
 
     // X[k] and X[256 - k] (k = 16 k1 + l) of both frames from Z[k] = a[dig(k1)] and Z[256 - k] = r[7 - k1]
@@ -333,7 +360,9 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         // store of "bin 16 k1 + l" from both would always collide.  Bins are therefore written two k1 at a
         // time and the upper half-warp swaps which of the two it writes first (all lanes but the two whose
         // banks wrap around): every store instruction then touches 32 distinct banks.
-        const bool swF = h && (l < 14), swM = h && (l >= 2);
+        // (d = bank distance between the two half-warps' rows: 514 floats = 2 banks, or 257 = 1 with PAIR2)
+        constexpr int d = PAIR2 ? 1 : 2;
+        const bool swF = h && (l < 16 - d), swM = h && (l >= d);
         float* f1 = rowA + l + (swF ? 16 : 0);
         float* f2 = rowA + l - (swF ? 16 : 0);
         float* m1 = rowA + 256 - l - (swM ? 16 : 0);
@@ -351,16 +380,16 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
           const float2 F1 = fmt2(xr_, xi_), M1 = fmt2(mr, mi);
           float2 v = swF ? F1 : F0;
           f1[32 * u] = v.x;
-          f1[32 * u + 257] = v.y;
+          f1[32 * u + kRowB] = v.y;
           v = swF ? F0 : F1;
           f2[32 * u + 16] = v.x;
-          f2[32 * u + 16 + 257] = v.y;
+          f2[32 * u + 16 + kRowB] = v.y;
           v = swM ? M1 : M0;
           m1[-32 * u] = v.x;
-          m1[-32 * u + 257] = v.y;
+          m1[-32 * u + kRowB] = v.y;
           v = swM ? M0 : M1;
           m2[-32 * u - 16] = v.x;
-          m2[-32 * u - 16 + 257] = v.y;
+          m2[-32 * u - 16 + kRowB] = v.y;
         }
       } else {
 #pragma unroll
@@ -469,8 +498,8 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       __syncwarp();
       // DCT-II columns 0..M (lane l), the channel range split between the half-warps, then lifter and
       // y | yE | yc | ycE packing; half-warp h writes frames 2h, 2h + 1.
-      float* outA = A.y + (row0 + 2 * h) * A.mf_D;
-      float* outB = outA + A.mf_D;
+      float* outA = A.y + (row0 + hf) * A.mf_D;
+      float* outB = outA + kFB * A.mf_D;
       const int ch = (C + 1) >> 1, c0 = h * ch, c1 = (c0 + ch < C) ? c0 + ch : C;
       for (int m0 = 0; m0 < M1; m0 += 16) {
         const int m = m0 + l;
@@ -531,14 +560,14 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   if (store_pending && lane == 0) bulk_wait_read();
 }
 
-template <int NJ, bool MASK_ALL, int W>
+template <int NJ, bool MASK_ALL, int W, int V = 0>
 int launch_fmt(const Args& A, int fmt, size_t smem, int device, cudaStream_t stream) {
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + W - 1) / W, sm_count(device)));
 #define DSB_LAUNCH(F)                                                                                      \
   case F: {                                                                                                \
-    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<NJ, MASK_ALL, F, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+    DSB_CUDA(cudaFuncSetAttribute(stft512_kernel<NJ, MASK_ALL, F, W, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                   static_cast<int>(smem)));                                                \
-    stft512_kernel<NJ, MASK_ALL, F, W><<<blocks, W * 32, smem, stream>>>(A);                               \
+    stft512_kernel<NJ, MASK_ALL, F, W, V><<<blocks, W * 32, smem, stream>>>(A);                            \
     break;                                                                                                 \
   }
   switch (fmt) {
@@ -597,6 +626,15 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
   return DSB200_OK;
 }
 
+// DSB200_STFT_V=0|1 (tuning knob, read once): kernel variant bits, see stft512_kernel
+static int stft_variant_knob() {
+  static const int v = [] {
+    const char* e = getenv("DSB200_STFT_V");
+    return e != nullptr ? atoi(e) : kDefaultVariant;
+  }();
+  return v;
+}
+
 static size_t smem_bytes(const Args& A, int mf_floats, int kWarps) {
   return 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) + static_cast<size_t>(mf_floats) * 4 +
          static_cast<size_t>(kWarps) * (2 * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
@@ -620,7 +658,11 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
     return kDefaultBulkStore;
   }();
   A.bulk_out = store_mode && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-  if (NJ == 13) return launch_fmt<13, false, kWarpsSpectrum>(A, p->spec.out_format, smem, device, stream);
+  if (NJ == 13) {
+    if ((stft_variant_knob() & kVPair2) && A.P == 80)
+      return launch_fmt<13, false, kWarpsSpectrum, kVPair2>(A, p->spec.out_format, smem, device, stream);
+    return launch_fmt<13, false, kWarpsSpectrum, 0>(A, p->spec.out_format, smem, device, stream);
+  }
   return launch_fmt<16, true, kWarpsMfcc>(A, p->spec.out_format, smem, device, stream);
 }
 
@@ -665,8 +707,10 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
     kern<<<blocks, kWarps * 32, smem, stream>>>(A);
     return DSB200_OK;
   };
+  const bool pair2 = (stft_variant_knob() & kVPair2) && A.P == 80;
   int rc;
-  if (w16) rc = launch(stft512_kernel<13, false, kFmtMfcc, kWarpsSpectrum>);
+  if (w16) rc = pair2 ? launch(stft512_kernel<13, false, kFmtMfcc, kWarpsSpectrum, kVPair2>)
+                      : launch(stft512_kernel<13, false, kFmtMfcc, kWarpsSpectrum, 0>);
   else if (NJ == 13) rc = launch(stft512_kernel<13, false, kFmtMfcc, kWarpsMfcc>);
   else rc = launch(stft512_kernel<16, true, kFmtMfcc, kWarpsMfcc>);
   if (rc != DSB200_OK) return rc;

@@ -61,6 +61,8 @@ enum { DSB200_SPEC_DB = 0, DSB200_SPEC_LOGMAG = 1, DSB200_SPEC_MAGNITUDE = 2, DS
 enum { DSB200_ACORR_NAIVE = 0, DSB200_ACORR_NORMALIZED = 1, DSB200_ACORR_BIASED = 2, DSB200_ACORR_UNBIASED = 3 };
 /* mfcc output packing, diffsptk/modules/mfcc.py:188-197. */
 enum { DSB200_MFCC_Y = 0, DSB200_MFCC_YE = 1, DSB200_MFCC_YC = 2, DSB200_MFCC_YCE = 3 };
+/* per-row coefficient converters of dsb200_rowconv */
+enum { DSB200_CONV_LPC2PAR = 0, DSB200_CONV_PAR2LPC = 1, DSB200_CONV_GNORM = 2, DSB200_CONV_IGNORM = 3, DSB200_CONV_NORM0 = 4 };
 
 typedef struct dsb200_frame_params {
   int32_t frame_length;  /* L >= 1 */
@@ -252,6 +254,15 @@ DSB200_DECL2(dsb200_delta, (const void* x, const void* window, void* y, int64_t 
 DSB200_DECL2(dsb200_delta_backward, (const void* gy, const void* window, void* gx, int64_t batch,
                                      int64_t n_frames, int32_t dim, int32_t n_windows, int32_t width, int device,
                                      void* stream))
+
+/* Per-row converters on coefficient vectors x[rows, dim] -> y[rows, dim] (y may alias x); `param` is gamma:
+ *   DSB200_CONV_LPC2PAR  LinearPredictiveCoefficientsToParcorCoefficients._forward, diffsptk/modules/lpc2par.py:104-120
+ *   DSB200_CONV_PAR2LPC  ParcorCoefficientsToLinearPredictiveCoefficients._forward, diffsptk/modules/par2lpc.py:100-107
+ *   DSB200_CONV_GNORM    GeneralizedCepstrumGainNormalization._forward, diffsptk/modules/gnorm.py:101-112
+ *   DSB200_CONV_IGNORM   GeneralizedCepstrumInverseGainNormalization._forward, diffsptk/modules/ignorm.py:98-109
+ *   DSB200_CONV_NORM0    AllPoleToAllZeroDigitalFilterCoefficients._forward, diffsptk/modules/norm0.py:88-94 (param unused) */
+DSB200_DECL2(dsb200_rowconv, (const void* x, void* y, int64_t rows, int32_t dim, int32_t op, double param,
+                              int device, void* stream))
 
 /* ---- host-buffer pipeline (the end-to-end path: pinned host -> device -> kernel -> host) -------------
  * One object owns two device staging slots and three streams (H2D, compute, D2H) and runs

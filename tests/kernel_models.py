@@ -190,3 +190,45 @@ def overlap_add_ranges_model(L, P, N, s, T_out, tile, threads=256):
                 if r >= P:
                     r, ne = r - P, ne + 1
                 i += threads
+
+
+# stft512.cu, variant kVPair2: index model of the (f, f + 2) frame pairing and of the staged-row store order.
+def stft512_pair2_columns(P=80, L=400, NJ=13, shift=5):
+    """For every half-warp h, lane l and column j: the span offsets the kernel reads for frames A = h and B = h + 2
+    (as raw[j] and raw[j + shift] of the SAME lane) next to the offsets the frames really start at."""
+    out = []
+    for h in range(2):
+        for l in range(16):
+            base = h * P + 2 * l                      # pa = span + hf * P + 2 * l
+            for j in range(NJ):
+                read_a = base + 32 * j                # raw[j]
+                read_b = base + 32 * (j + shift)      # raw[j + shift]
+                want_a = h * P + 2 * l + 32 * j       # sample 2 l + 32 j of frame h
+                want_b = (h + 2) * P + 2 * l + 32 * j  # the same sample of frame h + 2
+                out.append((read_a, want_a, read_b, want_b))
+    return out
+
+
+def stft512_staged_store_banks(d):
+    """Banks touched by each of the four store instructions of one `u` step of the staged split (stft512.cu):
+    d = bank distance between the two half-warps' rows (2: frames (2h, 2h+1); 1: frames (h, h+2))."""
+    rows = []
+    for u in range(4):
+        for which in range(4):
+            banks = []
+            for h in range(2):
+                for l in range(16):
+                    rowA = h * (257 * (2 if d == 2 else 1))
+                    swF = bool(h) and l < 16 - d
+                    swM = bool(h) and l >= d
+                    if which == 0:
+                        addr = rowA + l + (16 if swF else 0) + 32 * u
+                    elif which == 1:
+                        addr = rowA + l - (16 if swF else 0) + 32 * u + 16
+                    elif which == 2:
+                        addr = rowA + 256 - l - (16 if swM else 0) - 32 * u
+                    else:
+                        addr = rowA + 256 - l + (16 if swM else 0) - 32 * u - 16
+                    banks.append(addr % 32)
+            rows.append(banks)
+    return rows

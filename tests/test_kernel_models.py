@@ -60,3 +60,15 @@ def test_overlap_add_incremental_indexing():
         for q, na, nb, j in KM.overlap_add_ranges_model(L, P, N, s, T_out, tile):
             a_ref = 0 if q - L + 1 <= 0 else (q - L + P) // P
             assert (na, nb) == (a_ref, min(q // P, N - 1)) and j == q - na * P
+
+
+def test_stft512_pair2_reads_the_right_samples():
+    # frame f + 2 starts 2 P = 160 floats = 5 columns of 32 floats after frame f: same lane, column j + 5
+    for read_a, want_a, read_b, want_b in KM.stft512_pair2_columns():
+        assert read_a == want_a and read_b == want_b
+
+
+def test_stft512_staged_stores_are_bank_conflict_free():
+    for d in (1, 2):
+        for banks in KM.stft512_staged_store_banks(d):
+            assert len(set(banks)) == 32, (d, sorted(banks))
