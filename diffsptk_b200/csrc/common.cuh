@@ -72,20 +72,20 @@ template <typename C> __device__ __forceinline__ C cmul(C a, C b) {
   return r;
 }
 
-__device__ __forceinline__ float dsqrt(float x) { return sqrtf(x); }
-__device__ __forceinline__ double dsqrt(double x) { return sqrt(x); }
-__device__ __forceinline__ float dlog(float x) { return logf(x); }
-__device__ __forceinline__ double dlog(double x) { return log(x); }
-__device__ __forceinline__ float dlog10(float x) { return log10f(x); }
-__device__ __forceinline__ double dlog10(double x) { return log10(x); }
-__device__ __forceinline__ float dexp(float x) { return expf(x); }
-__device__ __forceinline__ double dexp(double x) { return exp(x); }
-__device__ __forceinline__ float dpow(float x, float y) { return powf(x, y); }
-__device__ __forceinline__ double dpow(double x, double y) { return pow(x, y); }
-__device__ __forceinline__ float dmax(float a, float b) { return fmaxf(a, b); }
-__device__ __forceinline__ double dmax(double a, double b) { return fmax(a, b); }
-__device__ __forceinline__ float dfma(float a, float b, float c) { return fmaf(a, b, c); }
-__device__ __forceinline__ double dfma(double a, double b, double c) { return fma(a, b, c); }
+__host__ __device__ __forceinline__ float dsqrt(float x) { return sqrtf(x); }
+__host__ __device__ __forceinline__ double dsqrt(double x) { return sqrt(x); }
+__host__ __device__ __forceinline__ float dlog(float x) { return logf(x); }
+__host__ __device__ __forceinline__ double dlog(double x) { return log(x); }
+__host__ __device__ __forceinline__ float dlog10(float x) { return log10f(x); }
+__host__ __device__ __forceinline__ double dlog10(double x) { return log10(x); }
+__host__ __device__ __forceinline__ float dexp(float x) { return expf(x); }
+__host__ __device__ __forceinline__ double dexp(double x) { return exp(x); }
+__host__ __device__ __forceinline__ float dpow(float x, float y) { return powf(x, y); }
+__host__ __device__ __forceinline__ double dpow(double x, double y) { return pow(x, y); }
+__host__ __device__ __forceinline__ float dmax(float a, float b) { return fmaxf(a, b); }
+__host__ __device__ __forceinline__ double dmax(double a, double b) { return fmax(a, b); }
+__host__ __device__ __forceinline__ float dfma(float a, float b, float c) { return fmaf(a, b, c); }
+__host__ __device__ __forceinline__ double dfma(double a, double b, double c) { return fma(a, b, c); }
 
 template <typename T> __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -14,75 +14,12 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "convert_row.cuh"
 
 namespace dsb200 {
 namespace {
 
 constexpr int kThreads = 256;
-
-template <typename T>
-__device__ __forceinline__ void convert_row(T* a, int D, int op, T g) {
-  const int M = D - 1;
-  switch (op) {
-    case DSB200_CONV_LPC2PAR: {
-      // a[1 + i] <- gamma a_i; for m = M-1..1: k_m = a[m]; a[i] <- (a[i] - k_m a[m-1-i]) / (1 - k_m^2), i < m
-      T* c = a + 1;
-      for (int i = 0; i < M; ++i) c[i] *= g;
-      for (int m = M - 1; m >= 1; --m) {
-        const T km = c[m];
-        const T z = static_cast<T>(1) - km * km;
-        for (int i = 0, j = m - 1; i <= j; ++i, --j) {
-          const T ci = c[i], cj = c[j];
-          c[i] = (ci - km * cj) / z;
-          if (j != i) c[j] = (cj - km * ci) / z;
-        }
-      }
-      break;
-    }
-    case DSB200_CONV_PAR2LPC: {
-      // a <- k / gamma (the gain too, as the reference does); for m = 2..M: a[1..m) += k_m flip(a[1..m))
-      // k_m is the UNDIVIDED coefficient, so a[m] is divided only after it was used as k_m.
-      a[0] = a[0] / g;
-      if (M >= 1) a[1] = a[1] / g;
-      for (int m = 2; m <= M; ++m) {
-        const T km = a[m];
-        for (int i = 1, j = m - 1; i <= j; ++i, --j) {
-          const T ai = a[i], aj = a[j];
-          a[i] = ai + km * aj;
-          if (j != i) a[j] = aj + km * ai;
-        }
-        a[m] = km / g;
-      }
-      break;
-    }
-    case DSB200_CONV_GNORM: {
-      if (g == static_cast<T>(0)) {
-        a[0] = dexp(a[0]);
-      } else {
-        const T z = static_cast<T>(1) + g * a[0];
-        a[0] = dpow(z, static_cast<T>(1) / g);
-        for (int i = 1; i <= M; ++i) a[i] = a[i] / z;
-      }
-      break;
-    }
-    case DSB200_CONV_IGNORM: {
-      if (g == static_cast<T>(0)) {
-        a[0] = dlog(a[0]);
-      } else {
-        const T z = dpow(a[0], g);
-        a[0] = (z - static_cast<T>(1)) / g;
-        for (int i = 1; i <= M; ++i) a[i] = a[i] * z;
-      }
-      break;
-    }
-    default: {  // DSB200_CONV_NORM0
-      const T b0 = static_cast<T>(1) / a[0];
-      a[0] = b0;
-      for (int i = 1; i <= M; ++i) a[i] = a[i] * b0;
-      break;
-    }
-  }
-}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads) rowconv_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows,

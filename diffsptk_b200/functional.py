@@ -105,6 +105,41 @@ def delta(x: Tensor, seed=[[-0.5, 0, 0.5]], static_out: bool = True) -> Tensor: 
     return nn.Delta._func(x, seed, static_out=static_out)
 
 
+def b2mc(b: Tensor, alpha: float = 0) -> Tensor:
+    """MLSA filter coefficients to mel-cepstrum ``(..., M+1) -> (..., M+1)``."""
+    return nn.MLSADigitalFilterCoefficientsToMelCepstrum._func(b, alpha=alpha)
+
+
+def mc2b(mc: Tensor, alpha: float = 0) -> Tensor:
+    """Mel-cepstrum to MLSA filter coefficients ``(..., M+1) -> (..., M+1)``."""
+    return nn.MelCepstrumToMLSADigitalFilterCoefficients._func(mc, alpha=alpha)
+
+
+def gnorm(x: Tensor, gamma: float = 0, c: int | None = None) -> Tensor:
+    """Gain normalisation of a generalized cepstrum ``(..., M+1) -> (..., M+1)``."""
+    return nn.GeneralizedCepstrumGainNormalization._func(x, gamma=gamma, c=c)
+
+
+def ignorm(y: Tensor, gamma: float = 0, c: int | None = None) -> Tensor:
+    """Inverse gain normalisation ``(..., M+1) -> (..., M+1)``."""
+    return nn.GeneralizedCepstrumInverseGainNormalization._func(y, gamma=gamma, c=c)
+
+
+def lpc2par(a: Tensor, gamma: float = 1, c: int | None = None) -> Tensor:
+    """LPC to PARCOR coefficients ``(..., M+1) -> (..., M+1)``."""
+    return nn.LinearPredictiveCoefficientsToParcorCoefficients._func(a, gamma=gamma, c=c)
+
+
+def par2lpc(k: Tensor, gamma: float = 1, c: int | None = None) -> Tensor:
+    """PARCOR to LPC coefficients ``(..., M+1) -> (..., M+1)``."""
+    return nn.ParcorCoefficientsToLinearPredictiveCoefficients._func(k, gamma=gamma, c=c)
+
+
+def norm0(a: Tensor) -> Tensor:
+    """All-pole to all-zero filter coefficients ``(..., M+1) -> (..., M+1)``."""
+    return nn.AllPoleToAllZeroDigitalFilterCoefficients._func(a)
+
+
 def fftcep(x: Tensor, cep_order: int, accel: float = 0, n_iter: int = 0) -> Tensor:
     """Cepstral analysis ``(..., L/2+1) -> (..., M+1)`` (improved cepstral method)."""
     return nn.CepstralAnalysis._func(x, cep_order=cep_order, accel=accel, n_iter=n_iter)

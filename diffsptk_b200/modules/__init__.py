@@ -2,6 +2,7 @@
 diffsptk/modules/__init__.py:17-175)."""
 
 from .acorr import Autocorrelation
+from .b2mc import MLSADigitalFilterCoefficientsToMelCepstrum
 from .dct import DiscreteCosineTransform
 from .dct import DiscreteCosineTransform as DCT
 from .delta import Delta
@@ -14,12 +15,18 @@ from .ifftr import RealValuedInverseFastFourierTransform
 from .istft import InverseShortTimeFourierTransform
 from .istft import InverseShortTimeFourierTransform as ISTFT
 from .freqt import FrequencyTransform
+from .gnorm import GeneralizedCepstrumGainNormalization
+from .ignorm import GeneralizedCepstrumInverseGainNormalization
 from .levdur import LevinsonDurbin
 from .lpc import LinearPredictiveCodingAnalysis
 from .lpc import LinearPredictiveCodingAnalysis as LPC
+from .lpc2par import LinearPredictiveCoefficientsToParcorCoefficients
+from .mc2b import MelCepstrumToMLSADigitalFilterCoefficients
 from .mcep import MelCepstralAnalysis
 from .mfcc import MelFrequencyCepstralCoefficientsAnalysis
 from .mfcc import MelFrequencyCepstralCoefficientsAnalysis as MFCC
+from .norm0 import AllPoleToAllZeroDigitalFilterCoefficients
+from .par2lpc import ParcorCoefficientsToLinearPredictiveCoefficients
 from .spec import Spectrum
 from .stft import ShortTimeFourierTransform
 from .stft import ShortTimeFourierTransform as STFT
@@ -32,4 +39,8 @@ __all__ = [
     "LinearPredictiveCodingAnalysis", "LPC", "MelCepstralAnalysis",
     "MelFrequencyCepstralCoefficientsAnalysis", "MFCC", "Spectrum", "ShortTimeFourierTransform", "STFT",
     "Window", "RealValuedInverseFastFourierTransform", "Unframe", "InverseShortTimeFourierTransform", "ISTFT", "CepstralAnalysis", "Delta",
+    "MLSADigitalFilterCoefficientsToMelCepstrum", "MelCepstrumToMLSADigitalFilterCoefficients",
+    "GeneralizedCepstrumGainNormalization", "GeneralizedCepstrumInverseGainNormalization",
+    "LinearPredictiveCoefficientsToParcorCoefficients", "ParcorCoefficientsToLinearPredictiveCoefficients",
+    "AllPoleToAllZeroDigitalFilterCoefficients",
 ]

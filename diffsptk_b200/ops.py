@@ -1059,3 +1059,82 @@ def _delta_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{_NS}::delta", _delta_bwd, setup_context=_delta_setup)
+
+
+# ------------------------------------------------------------------ per-row converters (section 8f rank 4)
+CONV_LPC2PAR, CONV_PAR2LPC, CONV_GNORM, CONV_IGNORM, CONV_NORM0 = range(5)
+
+
+@torch.library.custom_op(f"{_NS}::rowconv", mutates_args=(), device_types="cuda")
+def rowconv(x: Tensor, op: int, param: float) -> Tensor:
+    """``(..., D) -> (..., D)``: lpc2par / par2lpc / gnorm / ignorm / norm0 on every row (``dsb200_rowconv``)."""
+    dt = _native_dtype(x)
+    xc = _prep(x, dt)
+    D = xc.shape[-1]
+    rows = xc.numel() // max(D, 1)
+    y = torch.empty_like(xc)
+    N.check(N.typed("dsb200_rowconv", dt == torch.float64)(_ptr(xc), _ptr(y), rows, D, int(op), float(param), _dev(x),
+                                                           _stream(x)))
+    return y
+
+
+@rowconv.register_fake
+def _(x, op, param):
+    return x.new_empty(x.shape, dtype=_native_dtype(x))
+
+
+def rowconv_composite(x: Tensor, op: int, g: float) -> Tensor:
+    """The same five converters as differentiable torch expressions on the device: used by the backward of
+    ``rowconv`` only (recompute + torch.autograd), never by a forward call."""
+    M = x.shape[-1] - 1
+    K, a = torch.split(x, [1, M], dim=-1)
+    if op == CONV_LPC2PAR:          # lpc2par.py:104-120
+        ks = []
+        a = a * g
+        for m in reversed(range(M)):
+            km = a[..., m:m + 1]
+            ks.append(km)
+            if m == 0:
+                break
+            k = a[..., :-1]
+            a = (k - km * k.flip(-1)) / (1 - km * km)
+        ks.append(K)
+        return torch.cat(ks[::-1], dim=-1)
+    if op == CONV_PAR2LPC:          # par2lpc.py:100-107
+        cols = [x[..., i:i + 1] / g for i in range(min(2, M + 1))]
+        for m in range(2, M + 1):
+            km = x[..., m:m + 1]
+            am = torch.cat(cols[1:m], dim=-1)
+            am = am + km * am.flip(-1)
+            cols = cols[:1] + list(torch.split(am, 1, dim=-1)) + [km / g]
+        return torch.cat(cols, dim=-1)
+    if op == CONV_GNORM:            # gnorm.py:101-112
+        if g == 0:
+            return torch.cat((torch.exp(K), a), dim=-1)
+        z = 1 + g * K
+        return torch.cat((torch.pow(z, 1 / g), a / z), dim=-1)
+    if op == CONV_IGNORM:           # ignorm.py:98-109
+        if g == 0:
+            return torch.cat((torch.log(K), a), dim=-1)
+        z = torch.pow(K, g)
+        return torch.cat(((z - 1) / g, a * z), dim=-1)
+    b0 = torch.reciprocal(K)        # norm0.py:88-94
+    return torch.cat((b0, a * b0), dim=-1)
+
+
+def _rowconv_setup(ctx, inputs, output):
+    x, op, param = inputs
+    ctx.save_for_backward(x)
+    ctx.op, ctx.param = op, param
+
+
+def _rowconv_bwd(ctx, g):
+    (x,) = ctx.saved_tensors
+    with torch.enable_grad():
+        xd = x.detach().to(_native_dtype(x)).requires_grad_(True)
+        y = rowconv_composite(xd, ctx.op, ctx.param)
+        (gx,) = torch.autograd.grad(y, xd, g.to(y.dtype))
+    return _like_input(gx, x), None, None
+
+
+torch.library.register_autograd(f"{_NS}::rowconv", _rowconv_bwd, setup_context=_rowconv_setup)

@@ -341,3 +341,21 @@ def make_delta_window(seed, static_out: bool = True, device=None, dtype=None) ->
         raise ValueError("seed must be tuple or list.")
     key = tuple(tuple(s) if isinstance(s, (tuple, list)) else s for s in seed)
     return _delta_window_cached(key, bool(static_out), _dev_key(device), dtype).clone()
+
+
+# ------------------------------------------------------------------------- mc2b / b2mc (section 8f rank 4)
+def make_mc2b_matrix(cep_order, alpha, device=None, dtype=None):
+    """``A`` of mc2b.py:107-119 (stored transposed): ``b = mc @ A``, ``A[m + d, m] = (-alpha)^d``."""
+    a = 1
+    A = torch.eye(int(cep_order) + 1, dtype=torch.double)
+    for m in range(1, len(A)):
+        a *= -alpha
+        A[:, m:].fill_diagonal_(a)
+    return _cast(A.T.contiguous(), device, dtype)
+
+
+def make_b2mc_matrix(cep_order, alpha, device=None, dtype=None):
+    """``A`` of b2mc.py:104-115 (stored transposed): ``mc = b @ A``, ones on the diagonal, alpha below it."""
+    A = torch.eye(int(cep_order) + 1, dtype=torch.double)
+    A[:, 1:].fill_diagonal_(alpha)
+    return _cast(A.T.contiguous(), device, dtype)

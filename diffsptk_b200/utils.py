@@ -45,3 +45,12 @@ def pad_mode_id(mode: str) -> int:
         return PAD_MODE_IDS[mode]
     except KeyError:
         raise ValueError(f"mode {mode} is not supported.") from None
+
+
+def get_gamma(gamma: float, c: int | None) -> float:
+    """``gamma`` itself, or ``-1 / c`` when the integer ``c`` is given (diffsptk/utils/private.py:233-238)."""
+    if c is None or c == 0:
+        return gamma
+    if not 1 <= c:
+        raise ValueError("c must be an integer greater than or equal to 1.")
+    return -1 / c

@@ -706,3 +706,114 @@ def mfcc(x, mfcc_order, n_channel, sample_rate, lifter=1, f_min=0.0, f_max=None,
     if out_format in (3, "ycE"):
         return np.concatenate([y, c, E], axis=-1)
     raise ValueError(f"out_format {out_format} is not supported.")
+
+
+# ----------------------------------------------------------------------------- per-row converters (8f rank 4)
+def _get_gamma(gamma, c):
+    """diffsptk/utils/private.py:233-238."""
+    if c is None or c == 0:
+        return gamma
+    if not 1 <= c:
+        raise ValueError("c must be an integer greater than or equal to 1.")
+    return -1 / c
+
+
+def _check_gamma(order, gamma, c, what):
+    if order < 0:
+        raise ValueError(f"{what} must be non-negative.")
+    if 1 < abs(gamma):
+        raise ValueError("gamma must be in [-1, 1].")
+    if c is not None and c < 1:
+        raise ValueError("c must be greater than or equal to 1.")
+
+
+def lpc2par(a, gamma=1, c=None):
+    """Step-down recursion [K, a_1..a_M] -> [K, k_1..k_M].  diffsptk/modules/lpc2par.py:104-120."""
+    a = _as_float(a)
+    M = a.shape[-1] - 1
+    _check_gamma(M, gamma, c, "lpc_order")
+    g = a.dtype.type(_get_gamma(gamma, c))
+    K, a = a[..., :1], a[..., 1:]
+    ks = []
+    a = a * g
+    for m in reversed(range(M)):
+        km = a[..., m:m + 1]
+        ks.append(km)
+        if m == 0:
+            break
+        z = 1 - km * km
+        k = a[..., :-1]
+        a = (k - km * k[..., ::-1]) / z
+    ks.append(K)
+    return np.concatenate(ks[::-1], axis=-1)
+
+
+def par2lpc(k, gamma=1, c=None):
+    """Step-up recursion [K, k_1..k_M] -> [K, a_1..a_M] / gamma.  diffsptk/modules/par2lpc.py:100-107."""
+    k = _as_float(k)
+    _check_gamma(k.shape[-1] - 1, gamma, c, "lpc_order")
+    g = k.dtype.type(_get_gamma(gamma, c))
+    a = k / g
+    for m in range(2, k.shape[-1]):
+        km = k[..., m:m + 1]
+        am = a[..., 1:m].copy()
+        a[..., 1:m] = am + km * am[..., ::-1]
+    return a
+
+
+def gnorm(x, gamma=0, c=None):
+    """Gain normalisation.  diffsptk/modules/gnorm.py:101-112."""
+    x = _as_float(x)
+    _check_gamma(x.shape[-1] - 1, gamma, c, "cep_order")
+    g = _get_gamma(gamma, c)
+    x0, x1 = x[..., :1], x[..., 1:]
+    if g == 0:
+        K, y = np.exp(x0), x1
+    else:
+        z = 1 + x.dtype.type(g) * x0
+        K, y = np.power(z, x.dtype.type(1 / g)), x1 / z
+    return np.concatenate([K, y], axis=-1)
+
+
+def ignorm(y, gamma=0, c=None):
+    """Inverse gain normalisation.  diffsptk/modules/ignorm.py:98-109."""
+    y = _as_float(y)
+    _check_gamma(y.shape[-1] - 1, gamma, c, "cep_order")
+    g = _get_gamma(gamma, c)
+    K, y1 = y[..., :1], y[..., 1:]
+    if g == 0:
+        x0, x1 = np.log(K), y1
+    else:
+        z = np.power(K, y.dtype.type(g))
+        x0, x1 = (z - 1) / y.dtype.type(g), y1 * z
+    return np.concatenate([x0, x1], axis=-1)
+
+
+def norm0(a):
+    """[K, a_1..a_M] -> [1/K, a_1/K..a_M/K].  diffsptk/modules/norm0.py:88-94."""
+    a = _as_float(a)
+    b0 = 1 / a[..., :1]
+    return np.concatenate([b0, a[..., 1:] * b0], axis=-1)
+
+
+def mc2b(mc, alpha=0):
+    """b_M = mc_M, b_m = mc_m - alpha b_{m+1}.  diffsptk/modules/mc2b.py:93-101."""
+    mc = _as_float(mc)
+    if 1 <= abs(alpha):
+        raise ValueError("alpha must be in (-1, 1).")
+    M = mc.shape[-1] - 1
+    b = np.zeros_like(mc)
+    b[..., M] = mc[..., M]
+    for m in reversed(range(M)):
+        b[..., m] = mc[..., m] - mc.dtype.type(alpha) * b[..., m + 1]
+    return b
+
+
+def b2mc(b, alpha=0):
+    """mc_m = b_m + alpha b_{m+1}.  diffsptk/modules/b2mc.py:92-95."""
+    b = _as_float(b)
+    if 1 <= abs(alpha):
+        raise ValueError("alpha must be in (-1, 1).")
+    mc = b.copy()
+    mc[..., :-1] += b.dtype.type(alpha) * b[..., 1:]
+    return mc

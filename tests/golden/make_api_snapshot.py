@@ -1,7 +1,7 @@
 """Snapshot the reference's public signatures for the hot path (run in the build container).
 
 Writes ``tests/golden/api_signatures.json``: constructor / functional parameter names, kinds and
-defaults of the 24 exported classes (incl. aliases) and 18 functional delegates, plus the
+defaults of the 31 exported classes (incl. aliases) and 25 functional delegates, plus the
 ``_takes_input_size`` flags -- the drop-in contract of SURVEY.md section 8(b).
 """
 
@@ -18,9 +18,14 @@ CLASSES = ["Autocorrelation", "DiscreteCosineTransform", "DCT", "MelFilterBankAn
            "LinearPredictiveCodingAnalysis", "LPC", "MelCepstralAnalysis",
            "MelFrequencyCepstralCoefficientsAnalysis", "MFCC", "Spectrum", "ShortTimeFourierTransform", "STFT",
            "Window", "RealValuedInverseFastFourierTransform", "Unframe", "InverseShortTimeFourierTransform",
-           "ISTFT", "CepstralAnalysis", "Delta"]
+           "ISTFT", "CepstralAnalysis", "Delta",
+           "MLSADigitalFilterCoefficientsToMelCepstrum", "MelCepstrumToMLSADigitalFilterCoefficients",
+           "GeneralizedCepstrumGainNormalization", "GeneralizedCepstrumInverseGainNormalization",
+           "LinearPredictiveCoefficientsToParcorCoefficients", "ParcorCoefficientsToLinearPredictiveCoefficients",
+           "AllPoleToAllZeroDigitalFilterCoefficients"]
 FUNCTIONS = ["acorr", "dct", "fbank", "fftr", "frame", "freqt", "levdur", "lpc", "mcep", "mfcc", "spec", "stft",
-             "window", "ifftr", "unframe", "istft", "fftcep", "delta"]
+             "window", "ifftr", "unframe", "istft", "fftcep", "delta", "b2mc", "mc2b", "gnorm", "ignorm", "lpc2par",
+             "par2lpc", "norm0"]
 
 
 def describe(fn):

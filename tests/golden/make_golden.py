@@ -226,6 +226,45 @@ def cases():
     yield ("delta_one_frame", "delta", dict(seed=[2, 2], static_out=True), [ri.standard_normal((3, 1, 5))])
     yield ("delta_mfcc_like", "delta", dict(seed=[2, 2], static_out=True), [ri.standard_normal((4, 200, 13))])
     yield ("fftcep_512_m24_i5", "fftcep", dict(cep_order=24, accel=1.0, n_iter=5), [P257])
+    # ---- per-row converters, section 8(f) rank 4 (tests/test_lpc2par.py, test_par2lpc.py, test_gnorm.py,
+    #      test_ignorm.py, test_norm0.py, test_mc2b.py, test_b2mc.py) ------------------------------------------
+    rc = _rng(99)
+    # stable LPC rows: step-up recursion from random PARCOR coefficients in (-0.9, 0.9), gain > 0
+    def lpc_rows(shape, M):
+        k = rc.uniform(-0.9, 0.9, (*shape, M))
+        a = np.zeros((*shape, M))
+        for m in range(M):
+            km = k[..., m:m + 1]
+            prev = a[..., :m].copy()
+            a[..., :m] = prev + km * prev[..., ::-1]
+            a[..., m] = km[..., 0]
+        return np.concatenate([rc.uniform(0.5, 2.0, (*shape, 1)), a], axis=-1)
+    for M in (0, 1, 2, 7, 24):
+        yield (f"lpc2par_m{M}", "lpc2par", dict(gamma=1, c=None), [lpc_rows((3, 5), M)])
+        yield (f"par2lpc_m{M}", "par2lpc", dict(gamma=1, c=None),
+               [np.concatenate([rc.uniform(0.5, 2.0, (3, 5, 1)), rc.uniform(-0.9, 0.9, (3, 5, M))], axis=-1)])
+    yield ("lpc2par_g05", "lpc2par", dict(gamma=0.5, c=None), [lpc_rows((40,), 12)])
+    yield ("lpc2par_c2", "lpc2par", dict(gamma=1, c=2), [lpc_rows((40,), 12)])
+    yield ("par2lpc_g05", "par2lpc", dict(gamma=0.5, c=None),
+           [np.concatenate([rc.uniform(0.5, 2.0, (40, 1)), rc.uniform(-0.9, 0.9, (40, 12))], axis=-1)])
+    yield ("par2lpc_c3", "par2lpc", dict(gamma=1, c=3),
+           [np.concatenate([rc.uniform(0.5, 2.0, (40, 1)), rc.uniform(-0.9, 0.9, (40, 12))], axis=-1)])
+    yield ("lpc2par_many", "lpc2par", dict(gamma=1, c=None), [lpc_rows((700,), 24)])
+    cep = 0.3 * rc.standard_normal((3, 50, 25))
+    cep[..., 0] = rc.uniform(0.1, 1.5, (3, 50))
+    for g, c in ((0, None), (0.5, None), (-0.5, None), (-1, None), (1, None), (0, 2), (0, 4)):
+        tag = f"g{g}_c{c}".replace("-", "m").replace(".", "")
+        yield (f"gnorm_{tag}", "gnorm", dict(gamma=g, c=c), [cep])
+        gain = np.concatenate([rc.uniform(0.3, 3.0, (3, 50, 1)), cep[..., 1:]], axis=-1)
+        yield (f"ignorm_{tag}", "ignorm", dict(gamma=g, c=c), [gain])
+    yield ("gnorm_m0", "gnorm", dict(gamma=-0.5, c=None), [rc.uniform(0.1, 1.0, (7, 1))])
+    yield ("norm0_m24", "norm0", dict(), [lpc_rows((3, 50), 24)])
+    yield ("norm0_m0", "norm0", dict(), [rc.uniform(0.5, 2.0, (9, 1))])
+    for M in (0, 1, 4, 24):
+        for alpha in (0.0, 0.42, -0.3):
+            tag = f"m{M}_a{alpha}".replace("-", "m").replace(".", "")
+            yield (f"mc2b_{tag}", "mc2b", dict(alpha=alpha), [rc.standard_normal((2, 6, M + 1))])
+            yield (f"b2mc_{tag}", "b2mc", dict(alpha=alpha), [rc.standard_normal((2, 6, M + 1))])
 
 
 def main():

@@ -501,3 +501,38 @@ def test_delta_gradients():
         (rx,) = _ref_vjp(ref, (x,), ws)
         assert torch.allclose(mod(x), ref(x), rtol=1e-12, atol=1e-12), (shape, seed)
         assert torch.allclose(gx, rx, rtol=1e-10, atol=1e-12), (shape, seed)
+
+
+def test_converter_gradients():
+    """lpc2par / par2lpc / gnorm / ignorm / norm0 / mc2b / b2mc: gradients against torch.autograd.gradcheck-style
+    finite differences of the kernels themselves (float64) -- the backward recomputes a torch composite, so a
+    mismatch between kernel and composite shows up here."""
+    import diffsptk_b200.functional as F
+    d = dev()
+    g = torch.Generator().manual_seed(5)
+    k = torch.empty(6, 9, dtype=torch.float64).uniform_(-0.8, 0.8, generator=g)
+    k[:, 0] = torch.empty(6, dtype=torch.float64).uniform_(0.5, 2.0, generator=g)
+    k = k.to(d)
+    with torch.no_grad():
+        a = F.par2lpc(k)
+    cep = (0.3 * torch.randn(6, 9, generator=g, dtype=torch.float64)).to(d)
+    cep[:, 0] = cep[:, 0].abs() + 0.2
+    fns = [("lpc2par", lambda t: F.lpc2par(t), a), ("lpc2par_g", lambda t: F.lpc2par(t, gamma=0.5), a),
+           ("par2lpc", lambda t: F.par2lpc(t), k), ("par2lpc_c", lambda t: F.par2lpc(t, c=2), k),
+           ("gnorm0", lambda t: F.gnorm(t), cep), ("gnorm", lambda t: F.gnorm(t, gamma=-0.5), cep),
+           ("ignorm0", lambda t: F.ignorm(t), cep), ("ignorm", lambda t: F.ignorm(t, gamma=0.5), cep),
+           ("norm0", lambda t: F.norm0(t), a), ("mc2b", lambda t: F.mc2b(t, 0.42), cep),
+           ("b2mc", lambda t: F.b2mc(t, 0.42), cep)]
+    for name, fn, x0 in fns:
+        x = x0.clone().requires_grad_(True)
+        y = fn(x)
+        w = torch.randn(y.shape, generator=g, dtype=torch.float64).to(d)
+        (gx,) = torch.autograd.grad((y * w).sum(), x)
+        num = torch.zeros_like(x0)
+        h = 1e-6
+        with torch.no_grad():
+            for j in range(x0.shape[-1]):
+                e = torch.zeros_like(x0)
+                e[:, j] = h
+                num[:, j] = ((fn(x0 + e) - fn(x0 - e)) * w).sum(-1) / (2 * h)
+        assert torch.allclose(gx, num, rtol=1e-5, atol=1e-6), name

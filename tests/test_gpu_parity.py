@@ -102,6 +102,20 @@ def build_module(op, params, ins, prec):
         return B.CepstralAnalysis(fft_length=2 * n - 2, **p)
     if op == "delta":
         return B.Delta(**p, device=d, dtype=dt)
+    if op == "lpc2par":
+        return B.LinearPredictiveCoefficientsToParcorCoefficients(n - 1, **p)
+    if op == "par2lpc":
+        return B.ParcorCoefficientsToLinearPredictiveCoefficients(n - 1, **p)
+    if op == "gnorm":
+        return B.GeneralizedCepstrumGainNormalization(n - 1, **p)
+    if op == "ignorm":
+        return B.GeneralizedCepstrumInverseGainNormalization(n - 1, **p)
+    if op == "norm0":
+        return B.AllPoleToAllZeroDigitalFilterCoefficients(n - 1)
+    if op == "mc2b":
+        return B.MelCepstrumToMLSADigitalFilterCoefficients(n - 1, **p, device=d, dtype=dt)
+    if op == "b2mc":
+        return B.MLSADigitalFilterCoefficientsToMelCepstrum(n - 1, **p, device=d, dtype=dt)
     if op == "ifftr":
         return B.RealValuedInverseFastFourierTransform(2 * n - 2, p.pop("out_length"), device=d, dtype=dt)
     if op == "unframe":
