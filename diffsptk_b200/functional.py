@@ -135,6 +135,32 @@ def par2lpc(k: Tensor, gamma: float = 1, c: int | None = None) -> Tensor:
     return nn.ParcorCoefficientsToLinearPredictiveCoefficients._func(k, gamma=gamma, c=c)
 
 
+def mgc2mgc(mc: Tensor, out_order: int, in_alpha: float = 0, out_alpha: float = 0, in_gamma: float = 0,
+            out_gamma: float = 0, in_norm: bool = False, out_norm: bool = False, in_mul: bool = False,
+            out_mul: bool = False, n_fft: int = 512) -> Tensor:
+    """Mel-generalized cepstrum conversion ``(..., M1+1) -> (..., M2+1)``."""
+    return nn.MelGeneralizedCepstrumToMelGeneralizedCepstrum._func(
+        mc, out_order=out_order, in_alpha=in_alpha, out_alpha=out_alpha, in_gamma=in_gamma, out_gamma=out_gamma,
+        in_norm=in_norm, out_norm=out_norm, in_mul=in_mul, out_mul=out_mul, n_fft=n_fft)
+
+
+def mgc2sp(mc: Tensor, fft_length: int, alpha: float = 0, gamma: float = 0, norm: bool = False, mul: bool = False,
+           n_fft: int = 512, out_format: str = "power") -> Tensor:
+    """Mel-generalized cepstrum to spectrum ``(..., M+1) -> (..., L/2+1)``."""
+    return nn.MelGeneralizedCepstrumToSpectrum._func(mc, fft_length=fft_length, alpha=alpha, gamma=gamma, norm=norm,
+                                                     mul=mul, n_fft=n_fft, out_format=out_format)
+
+
+def plp(x: Tensor, plp_order: int, n_channel: int, sample_rate: int, compression_factor: float = 0.33,
+        lifter: int = 1, f_min: float = 0, f_max: float | None = None, floor: float = 1e-5, gamma: float = 0,
+        scale: str = "htk", erb_factor: float | None = None, n_fft: int = 512, out_format: str = "y") -> Tensor:
+    """PLP analysis of a power spectrum ``(..., L/2+1) -> (..., M)`` [+ c0] [+ energy]."""
+    return nn.PerceptualLinearPredictiveCoefficientsAnalysis._func(
+        x, plp_order=plp_order, n_channel=n_channel, sample_rate=sample_rate,
+        compression_factor=compression_factor, lifter=lifter, f_min=f_min, f_max=f_max, floor=floor, gamma=gamma,
+        scale=scale, erb_factor=erb_factor, n_fft=n_fft, out_format=out_format)
+
+
 def norm0(a: Tensor) -> Tensor:
     """All-pole to all-zero filter coefficients ``(..., M+1) -> (..., M+1)``."""
     return nn.AllPoleToAllZeroDigitalFilterCoefficients._func(a)

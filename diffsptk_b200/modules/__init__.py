@@ -24,6 +24,10 @@ from .lpc2par import LinearPredictiveCoefficientsToParcorCoefficients
 from .mc2b import MelCepstrumToMLSADigitalFilterCoefficients
 from .mcep import MelCepstralAnalysis
 from .mfcc import MelFrequencyCepstralCoefficientsAnalysis
+from .mgc2mgc import MelGeneralizedCepstrumToMelGeneralizedCepstrum
+from .mgc2sp import MelGeneralizedCepstrumToSpectrum
+from .plp import PerceptualLinearPredictiveCoefficientsAnalysis
+from .plp import PerceptualLinearPredictiveCoefficientsAnalysis as PLP
 from .mfcc import MelFrequencyCepstralCoefficientsAnalysis as MFCC
 from .norm0 import AllPoleToAllZeroDigitalFilterCoefficients
 from .par2lpc import ParcorCoefficientsToLinearPredictiveCoefficients
@@ -42,5 +46,6 @@ __all__ = [
     "MLSADigitalFilterCoefficientsToMelCepstrum", "MelCepstrumToMLSADigitalFilterCoefficients",
     "GeneralizedCepstrumGainNormalization", "GeneralizedCepstrumInverseGainNormalization",
     "LinearPredictiveCoefficientsToParcorCoefficients", "ParcorCoefficientsToLinearPredictiveCoefficients",
-    "AllPoleToAllZeroDigitalFilterCoefficients",
+    "AllPoleToAllZeroDigitalFilterCoefficients", "MelGeneralizedCepstrumToMelGeneralizedCepstrum",
+    "MelGeneralizedCepstrumToSpectrum", "PerceptualLinearPredictiveCoefficientsAnalysis", "PLP",
 ]

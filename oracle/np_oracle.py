@@ -817,3 +817,155 @@ def b2mc(b, alpha=0):
     mc = b.copy()
     mc[..., :-1] += b.dtype.type(alpha) * b[..., 1:]
     return mc
+
+
+# ----------------------------------------------------------------------------- mgc2mgc / mgc2sp / plp (8f rank 3)
+def _gc2gc(c1, out_order, in_gamma, out_gamma, n_fft):
+    """Gamma conversion in the spectral domain.  diffsptk/modules/mgc2mgc.py:327-364."""
+    c01 = np.concatenate([np.zeros_like(c1[..., :1]), c1[..., 1:]], axis=-1)
+    C1 = np.fft.fft(c01.astype(np.float64), n=n_fft, axis=-1)
+    if in_gamma == 0:
+        sC1 = np.exp(C1.real) * np.exp(1j * C1.imag)
+    else:
+        C1 = C1 * in_gamma
+        C1 = C1 + 1
+        sC1 = (np.abs(C1) ** (1 / in_gamma)) * np.exp(1j * (np.angle(C1) / in_gamma))
+    if out_gamma == 0:
+        C2 = np.log(np.abs(sC1))
+    else:
+        C2 = ((np.abs(sC1) ** out_gamma) * np.cos(np.angle(sC1) * out_gamma) - 1) / out_gamma
+    c02 = np.fft.ifft(C2, axis=-1).real[..., : out_order + 1]
+    return np.concatenate([c1[..., :1], (2 * c02[..., 1:]).astype(c1.dtype)], axis=-1)
+
+
+def mgc2mgc(mc, out_order, in_alpha=0, out_alpha=0, in_gamma=0, out_gamma=0, in_norm=False, out_norm=False,
+            in_mul=False, out_mul=False, n_fft=512):
+    """The reference's step sequence.  diffsptk/modules/mgc2mgc.py:209-297 (the FFTs of the gamma conversion run
+    in float64 here; the reference's run in the input dtype)."""
+    mc = _as_float(mc)
+    in_order = mc.shape[-1] - 1
+    if in_order < 0 or out_order < 0:
+        raise ValueError("order must be non-negative.")
+    if 1 <= abs(in_alpha) or 1 <= abs(out_alpha):
+        raise ValueError("alpha must be in (-1, 1).")
+    if 1 < abs(in_gamma) or 1 < abs(out_gamma):
+        raise ValueError("gamma must be in [-1, 1].")
+    if n_fft <= max(in_order, out_order) + 1:
+        raise ValueError("n_fft must be much larger than order of cepstrum.")
+    if 0 == in_gamma and in_mul:
+        raise ValueError("Invalid combination of in_gamma and in_mul.")
+    t = mc.dtype.type
+    tail = lambda c, f: np.concatenate([c[..., :1], f(c[..., 1:])], axis=-1)      # noqa: E731
+    head = lambda c, f: np.concatenate([f(c[..., :1]), c[..., 1:]], axis=-1)      # noqa: E731
+    c = mc
+    if not in_norm and in_mul:
+        c = head(c, lambda v: (v - 1) / t(in_gamma))
+    alpha = (out_alpha - in_alpha) / (1 - in_alpha * out_alpha)
+    if 0 == alpha:
+        if in_order == out_order and in_gamma == out_gamma:
+            if not in_mul and out_mul:
+                c = tail(c, lambda v: v * t(in_gamma))
+            if not in_norm and out_norm:
+                c = gnorm(c, in_gamma)
+            if in_norm and not out_norm:
+                c = ignorm(c, out_gamma)
+            if in_mul and not out_mul:
+                c = tail(c, lambda v: v / t(out_gamma))
+        else:
+            if in_mul:
+                c = tail(c, lambda v: v / t(in_gamma))
+            if not in_norm:
+                c = gnorm(c, in_gamma)
+            c = _gc2gc(c, out_order, in_gamma, out_gamma, n_fft)
+            if not out_norm:
+                c = ignorm(c, out_gamma)
+            if out_mul:
+                c = tail(c, lambda v: v * t(out_gamma))
+    else:
+        if in_mul:
+            c = tail(c, lambda v: v / t(in_gamma))
+        if in_norm:
+            c = ignorm(c, in_gamma)
+        c = freqt(c, out_order, alpha)
+        if out_norm or in_gamma != out_gamma:
+            c = gnorm(c, in_gamma)
+        if in_gamma != out_gamma:
+            c = _gc2gc(c, out_order, in_gamma, out_gamma, n_fft)
+        if not out_norm and in_gamma != out_gamma:
+            c = ignorm(c, out_gamma)
+        if out_mul:
+            c = tail(c, lambda v: v * t(out_gamma))
+    if not out_norm and out_mul:
+        c = head(c, lambda v: v * t(out_gamma) + 1)
+    return c
+
+
+def mgc2sp(mc, fft_length, alpha=0, gamma=0, norm=False, mul=False, n_fft=512, out_format="power"):
+    """mgc2mgc to a plain cepstrum of order L/2, rfft, formatter.  diffsptk/modules/mgc2sp.py:131-202."""
+    mc = _as_float(mc)
+    c = mgc2mgc(mc, fft_length // 2, in_alpha=alpha, out_alpha=0, in_gamma=gamma, out_gamma=0, in_norm=norm,
+                out_norm=False, in_mul=mul, out_mul=False, n_fft=n_fft)
+    sp = np.fft.rfft(c.astype(np.float64), n=(c.shape[-1] - 1) * 2, axis=-1)
+    if out_format in (0, "db"):
+        out = sp.real * (20 / math.log(10))
+    elif out_format in (1, "log-magnitude"):
+        out = sp.real
+    elif out_format in (2, "magnitude"):
+        out = np.exp(sp.real)
+    elif out_format in (3, "power"):
+        out = np.exp(2 * sp.real)
+    elif out_format in (4, "cycle"):
+        out = sp.imag / math.pi
+    elif out_format in (5, "radian"):
+        out = sp.imag
+    elif out_format in (6, "degree"):
+        out = sp.imag * (180 / math.pi)
+    elif out_format == "complex":
+        return (np.exp(sp.real) * np.exp(1j * sp.imag)).astype(np.complex64 if mc.dtype == np.float32 else np.complex128)
+    else:
+        raise ValueError(f"out_format {out_format} is not supported.")
+    return out.astype(mc.dtype)
+
+
+def plp(x, plp_order, n_channel, sample_rate, compression_factor=0.33, lifter=1, f_min=0.0, f_max=None, floor=1e-5,
+        gamma=0.0, scale="htk", erb_factor=None, n_fft=512, out_format="y"):
+    """fbank (power) -> equal loudness -> compression -> inverse DFT -> levdur -> LPC cepstrum -> lifter.
+    diffsptk/modules/plp.py:192-320."""
+    x = _as_float(x)
+    if plp_order < 0:
+        raise ValueError("plp_order must be non-negative.")
+    if n_channel <= plp_order:
+        raise ValueError("plp_order must be less than n_channel.")
+    if compression_factor <= 0:
+        raise ValueError("compression_factor must be positive.")
+    if lifter < 0:
+        raise ValueError("lifter must be non-negative.")
+    y, E = fbank(x, n_channel, sample_rate, f_min, f_max, floor, gamma, scale, erb_factor, use_power=True,
+                 out_format="y,E")
+    fmax = sample_rate / 2 if f_max is None else f_max
+    mel_min = _hz_to_auditory(np.asarray(f_min, dtype=np.float64), scale)
+    mel_max = _hz_to_auditory(np.asarray(fmax, dtype=np.float64), scale)
+    centre = (mel_max - mel_min) / (n_channel + 1) * np.arange(1, n_channel + 2) + mel_min
+    f = _auditory_to_hz(centre, scale)[:-1] ** 2
+    elc = ((f / (f + 1.6e5)) ** 2 * (f + 1.44e6) / (f + 9.61e6)).astype(x.dtype)
+    y = (np.exp(y) * elc) ** x.dtype.type(compression_factor)
+    y = np.concatenate([y[..., :1], y, y[..., -1:]], axis=-1)
+    r = np.fft.hfft(y.astype(np.float64), norm="forward", axis=-1).real[..., : plp_order + 1].astype(x.dtype)
+    a = levdur(r, eps=0)
+    c = mgc2mgc(a, plp_order, in_alpha=0, out_alpha=0, in_gamma=-1, out_gamma=0, in_norm=True, out_norm=False,
+                in_mul=True, out_mul=False, n_fft=n_fft)
+    ramp = np.arange(plp_order + 1, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lv = 1 + (lifter / 2) * np.sin((math.pi / lifter) * ramp)
+    lv[0] = 2
+    c = c * lv.astype(x.dtype)
+    c0, y = c[..., :1], c[..., 1:]
+    if out_format in (0, "y"):
+        return y
+    if out_format in (1, "yE"):
+        return np.concatenate([y, E], axis=-1)
+    if out_format in (2, "yc"):
+        return np.concatenate([y, c0], axis=-1)
+    if out_format in (3, "ycE"):
+        return np.concatenate([y, c0, E], axis=-1)
+    raise ValueError(f"out_format {out_format} is not supported.")

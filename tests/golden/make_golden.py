@@ -265,6 +265,58 @@ def cases():
             tag = f"m{M}_a{alpha}".replace("-", "m").replace(".", "")
             yield (f"mc2b_{tag}", "mc2b", dict(alpha=alpha), [rc.standard_normal((2, 6, M + 1))])
             yield (f"b2mc_{tag}", "b2mc", dict(alpha=alpha), [rc.standard_normal((2, 6, M + 1))])
+    # ---- mgc2mgc / mgc2sp / plp, section 8(f) rank 3 (tests/test_mgc2mgc.py:23-100, test_mgc2sp.py:23-51,
+    #      test_plp.py:23-70) -- inputs are valid (normalised / multiplied) cepstra made from a small random one
+    rm = _rng(2024)
+    base = 0.2 * rm.standard_normal((2, 6, 5))
+    base[..., 0] = rm.uniform(0.2, 1.0, (2, 6))
+
+    def shaped(c, g, norm, mul):
+        """A gamma-g cepstrum in the (normalised, multiplied) form the flags announce."""
+        c = c.copy()
+        if norm:
+            z = 1 + g * c[..., :1]
+            c = np.concatenate([z ** (1 / g), c[..., 1:] / z], axis=-1)
+        if mul:
+            c = np.concatenate([c[..., :1], c[..., 1:] * g], axis=-1)
+            if not norm:
+                c = np.concatenate([c[..., :1] * g + 1, c[..., 1:]], axis=-1)
+        return c
+    i = 0
+    for (M, A, G) in ((4, 0, 0.1), (4, 0, -0.1), (2, 0.1, 0.1), (6, 0.1, 0.2)):
+        for in_norm in (False, True):
+            for out_norm in (False, True):
+                for in_mul in (False, True):
+                    for out_mul in (False, True):
+                        i += 1
+                        yield (f"mgc2mgc_{i:02d}", "mgc2mgc",
+                               dict(out_order=M, in_alpha=0, out_alpha=A, in_gamma=0.1, out_gamma=G, in_norm=in_norm,
+                                    out_norm=out_norm, in_mul=in_mul, out_mul=out_mul, n_fft=256),
+                               [shaped(base, 0.1, in_norm, in_mul)])
+    mc25 = 0.1 * rm.standard_normal((3, 40, 25))
+    mc25[..., 0] = rm.uniform(-2.0, 1.0, (3, 40))
+    yield ("mgc2mgc_mc2c", "mgc2mgc", dict(out_order=40, in_alpha=0.42, out_alpha=0, n_fft=512), [mc25])
+    yield ("mgc2mgc_to_lsp_domain", "mgc2mgc", dict(out_order=24, in_alpha=0.42, out_alpha=0.42, in_gamma=0,
+                                                      out_gamma=-0.5, n_fft=512), [mc25])
+    yield ("mgc2mgc_lpc2c", "mgc2mgc", dict(out_order=12, in_gamma=-1, out_gamma=0, in_norm=True, in_mul=True,
+                                              n_fft=512), [shaped(0.5 * base, -1.0, True, True)])
+    c8 = 0.3 * rm.standard_normal((2, 8))
+    for fmt in (0, 1, 2, 3, 4, 5, 6, "complex"):
+        yield (f"mgc2sp_16_o{fmt}", "mgc2sp", dict(fft_length=16, out_format=fmt), [c8])
+    yield ("mgc2sp_mcep_512", "mgc2sp", dict(fft_length=512, alpha=0.42), [mc25])
+    yield ("mgc2sp_mgc_512", "mgc2sp", dict(fft_length=512, alpha=0.42, gamma=-0.5, n_fft=1024),
+           [np.concatenate([mc25[..., :1] * 0.2, mc25[..., 1:]], axis=-1)])
+    yield ("mgc2sp_lpc_like", "mgc2sp", dict(fft_length=64, gamma=-1, norm=True, mul=True, n_fft=256, out_format=1),
+           [shaped(0.5 * base, -1.0, True, True)])
+    P17 = rm.standard_normal((2, 4, 32))
+    P17 = np.abs(np.fft.rfft(P17, axis=-1)) ** 2
+    for fmt in (0, 1, 2, 3):
+        yield (f"plp_32_o{fmt}", "plp", dict(plp_order=4, n_channel=10, sample_rate=8000, compression_factor=0.3,
+                                              lifter=20, floor=1, out_format=fmt), [P17])
+    Pw = np.abs(np.fft.rfft(rm.standard_normal((2, 30, 400)) * np.hanning(400), n=512, axis=-1)) ** 2 + 1e-9
+    yield ("plp_512_m12", "plp", dict(plp_order=12, n_channel=40, sample_rate=16000), [Pw])
+    yield ("plp_512_bark", "plp", dict(plp_order=8, n_channel=20, sample_rate=16000, f_min=100, f_max=7000,
+                                        scale="bark", lifter=22, out_format="ycE"), [Pw])
 
 
 def main():

@@ -1,0 +1,79 @@
+"""Host logic of the composite modules (mgc2mgc / mgc2sp / plp) on the CPU.
+
+The composites chain this package's kernels with a few elementwise torch ops.  Here every kernel entry in
+``diffsptk_b200.ops`` is replaced by a plain torch stand-in of the same contract (TEST ONLY -- the product has no
+CPU path), so the step sequences, table construction, flag handling and output packing are checked against the
+reference's golden vectors without a GPU; the GPU parity tests then run the same cases on the real kernels.
+"""
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+
+
+def _rfft(x, fft_length, out_format):
+    X = torch.fft.rfft(x[..., :fft_length], n=fft_length)
+    return torch.view_as_real(X).contiguous() if out_format == 0 else X.real
+
+
+def _ifftr(y, out_length):
+    return torch.fft.irfft(y, n=2 * (y.shape[-1] - 1))[..., :out_length]
+
+
+def _fbank(x, Hm, cb, ce, floor, gamma, use_power, want_energy):
+    a = x if use_power else torch.sqrt(x)
+    y = torch.clip(a @ Hm, min=floor)
+    y = torch.log(y) if gamma == 0 else (y ** gamma - 1) / gamma
+    E = torch.log((2 * x[..., 1:-1].sum(-1) + x[..., 0] + x[..., -1]) / (2 * (x.shape[-1] - 1))).unsqueeze(-1)
+    return y, (E if want_energy else x.new_empty(0))
+
+
+def _levdur(r, eps):
+    M = r.shape[-1] - 1
+    idx = (torch.arange(M)[:, None] - torch.arange(M)[None, :]).abs()
+    R = r[..., :-1][..., idx] + eps * torch.eye(M, dtype=r.dtype)
+    a = torch.linalg.solve(R, -r[..., 1:].unsqueeze(-1)).squeeze(-1)
+    K = torch.sqrt((r[..., 1:] * a).sum(-1, keepdim=True) + r[..., :1])
+    return torch.cat((K, a), dim=-1)
+
+
+@pytest.fixture()
+def host_ops(monkeypatch):
+    from diffsptk_b200 import ops
+    monkeypatch.setattr(ops, "rfft", _rfft)
+    monkeypatch.setattr(ops, "ifftr", _ifftr)
+    monkeypatch.setattr(ops, "rowmat", lambda x, W: x @ W.to(x.dtype))
+    monkeypatch.setattr(ops, "rowconv", lambda x, op, g: ops.rowconv_composite(x, op, g))
+    monkeypatch.setattr(ops, "fbank", _fbank)
+    monkeypatch.setattr(ops, "levdur", _levdur)
+    return ops
+
+
+CASES = H.case_names(["mgc2mgc", "mgc2sp", "plp"])
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", CASES)
+def test_functional_host_logic_matches_reference(host_ops, name, prec):
+    import diffsptk_b200.functional as F
+    op, params, ins, outs = H.load_case(name, prec)
+    got = getattr(F, op)(*[torch.from_numpy(np.ascontiguousarray(a)) for a in ins], **params)
+    H.assert_close(got.numpy(), outs[0], prec, what=f"{name}[{prec}]", scale_atol=True)
+
+
+@pytest.mark.parametrize("name", CASES[::3])
+def test_module_host_logic_matches_reference(host_ops, name):
+    import diffsptk_b200 as B
+    op, params, ins, outs = H.load_case(name, "f64")
+    n = ins[0].shape[-1]
+    p = dict(params)
+    if op == "mgc2mgc":
+        mod = B.MelGeneralizedCepstrumToMelGeneralizedCepstrum(n - 1, **p, dtype=torch.float64)
+    elif op == "mgc2sp":
+        mod = B.MelGeneralizedCepstrumToSpectrum(n - 1, p.pop("fft_length"), **p, dtype=torch.float64)
+    else:
+        mod = B.PLP(fft_length=2 * n - 2, **p, dtype=torch.float64)
+    got = mod(torch.from_numpy(np.ascontiguousarray(ins[0])))
+    H.assert_close(got.numpy(), outs[0], "f64", what=name, scale_atol=True)

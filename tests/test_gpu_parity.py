@@ -15,7 +15,7 @@ import helpers as H
 
 pytestmark = pytest.mark.gpu
 
-ILL = {"levdur", "lpc", "mcep"}
+ILL = {"levdur", "lpc", "mcep", "plp"}   # plp contains levdur (eps = 0)
 TD = {"f32": torch.float32, "f64": torch.float64}
 
 
@@ -114,6 +114,12 @@ def build_module(op, params, ins, prec):
         return B.AllPoleToAllZeroDigitalFilterCoefficients(n - 1)
     if op == "mc2b":
         return B.MelCepstrumToMLSADigitalFilterCoefficients(n - 1, **p, device=d, dtype=dt)
+    if op == "mgc2mgc":
+        return B.MelGeneralizedCepstrumToMelGeneralizedCepstrum(n - 1, **p, device=d, dtype=dt)
+    if op == "mgc2sp":
+        return B.MelGeneralizedCepstrumToSpectrum(n - 1, p.pop("fft_length"), **p, device=d, dtype=dt)
+    if op == "plp":
+        return B.PLP(fft_length=2 * n - 2, **p, device=d, dtype=dt)
     if op == "b2mc":
         return B.MLSADigitalFilterCoefficientsToMelCepstrum(n - 1, **p, device=d, dtype=dt)
     if op == "ifftr":
