@@ -38,6 +38,8 @@ WORKLOADS = {
                   320 + 1028 + 320, 1028 + 320),
     "delta": ("Delta + delta-delta features (widths 2, 2) of 13-dim cepstra: 4096 utt x 2001 frames", 4096, 160000,
               52, 156),
+    "lpc2par": ("LPC -> PARCOR (step-down recursion, M=24) on the LPC rows of config 3: 1024 utt x 5 s", 1024, 80000,
+                100, 100),
     "istft": ("Inverse STFT (ifftr -> window -> overlap-add, one kernel): 256 utt x 10 s of complex spectra", 256,
               160000, 2056, 320),
 }
@@ -135,6 +137,8 @@ def _cpu_task(args):
         y = O.istft(x)
     elif workload == "delta":  # x holds 13-dim features
         y = O.delta(x, [2, 2], True)
+    elif workload == "lpc2par":  # x holds LPC rows
+        y = O.lpc2par(x)
     elif workload == "stft_grad":  # the oracle has no autograd: forward only (a lower bound on the CPU cost)
         y = O.stft(x)
     else:  # mcep: x holds power spectra
@@ -160,6 +164,10 @@ def cpu_oracle_throughput(workload, utterances, T, steps, warmup, budget_s=25.0)
         _CPU_X = O.stft(rng.standard_normal((utterances, T)).astype(np.float32), out_format="complex")
     elif workload == "delta":
         _CPU_X = rng.standard_normal((utterances, n_frames(T), 13)).astype(np.float32)
+    elif workload == "lpc2par":
+        from oracle import np_oracle as O
+        k = rng.uniform(-0.9, 0.9, (utterances, n_frames(T), 25)).astype(np.float32)
+        _CPU_X = O.par2lpc(k)
     else:
         _CPU_X = rng.standard_normal((utterances, T)).astype(np.float32)
     per = max(1, utterances // (cores * 2))
@@ -219,6 +227,11 @@ def make_step(workload, B, T, dev):
         dl = D.Delta([2, 2], True).to(dev)
         xs = [torch.randn(B, n_frames(T), 13, generator=g, device=dev) for _ in range(2)]
         return xs, lambda i: dl(xs[i & 1])
+    if workload == "lpc2par":
+        with torch.no_grad():   # stable LPC rows: step-up recursion from random PARCOR coefficients
+            xs = [F.par2lpc(torch.empty(B, n_frames(T), 25, device=dev).uniform_(-0.9, 0.9, generator=g))
+                  for _ in range(2)]
+        return xs, lambda i: F.lpc2par(xs[i & 1])
     if workload == "istft":
         stft = D.STFT(FL, FP, NFFT, out_format="complex").to(dev)
         istft = D.ISTFT(FL, FP, NFFT).to(dev)
