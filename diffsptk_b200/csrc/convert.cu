@@ -12,6 +12,7 @@
 // the recursions are sequential in the order m and only O(M^2) flops on M + 1 values, far below the HBM time of
 // the row -- then the tile leaves with coalesced stores.
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "convert_row.cuh"
@@ -21,7 +22,8 @@ namespace {
 
 constexpr int kThreads = 256;
 
-template <typename T>
+// DF > 0: the row length is the compile-time DF and the O(M^2) recursions run in registers.
+template <typename T, int DF>
 __global__ void __launch_bounds__(kThreads) rowconv_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows,
                                                            int D, int pitch, int op, T g) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -44,7 +46,10 @@ __global__ void __launch_bounds__(kThreads) rowconv_kernel(const T* __restrict__
       }
     }
     __syncthreads();
-    if (threadIdx.x < nr) convert_row<T>(tile + threadIdx.x * pitch, D, op, g);
+    if (threadIdx.x < nr) {
+      if (DF > 0) convert_row_fixed<T, (DF > 0 ? DF : 1)>(tile + threadIdx.x * pitch, op, g);
+      else convert_row<T>(tile + threadIdx.x * pitch, D, op, g);
+    }
     __syncthreads();
     {
       int r = threadIdx.x / D, c = threadIdx.x - r * D;
@@ -76,12 +81,25 @@ int rowconv_impl(const void* x, void* y, int64_t rows, int32_t dim, int32_t op, 
   const size_t smem = static_cast<size_t>(kThreads) * pitch * sizeof(T);
   if (smem > static_cast<size_t>(max_dynamic_smem(device)))
     return fail(DSB200_E_UNSUPPORTED, "row length %d does not fit in shared memory", dim);
-  DSB_CUDA(cudaFuncSetAttribute(rowconv_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int64_t n_tiles = (rows + kThreads - 1) / kThreads;
   const int per_sm = std::max<int>(1, std::min<int>(8, static_cast<int>((200 * 1024) / std::max<size_t>(smem, 1))));
   const int blocks = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count(device)) * per_sm));
-  rowconv_kernel<T><<<blocks, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const T*>(x), static_cast<T*>(y), rows, dim, pitch, op, static_cast<T>(param));
+  auto launch = [&](auto kern) -> int {
+    DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<blocks, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const T*>(x), static_cast<T*>(y), rows, dim, pitch, op, static_cast<T>(param));
+    return DSB200_OK;
+  };
+  // register-resident recursions for the usual LPC orders 12 / 16 / 20 / 24 (DSB200_ROWCONV_GENERIC=1: A/B knob)
+  static const bool generic_only = getenv("DSB200_ROWCONV_GENERIC") != nullptr;
+  const bool quad = (op == DSB200_CONV_LPC2PAR || op == DSB200_CONV_PAR2LPC) && !generic_only;
+  int rc;
+  if (quad && dim == 13) rc = launch(rowconv_kernel<T, 13>);
+  else if (quad && dim == 17) rc = launch(rowconv_kernel<T, 17>);
+  else if (quad && dim == 21) rc = launch(rowconv_kernel<T, 21>);
+  else if (quad && dim == 25) rc = launch(rowconv_kernel<T, 25>);
+  else rc = launch(rowconv_kernel<T, 0>);
+  if (rc != DSB200_OK) return rc;
   return after_launch("rowconv_kernel");
 }
 

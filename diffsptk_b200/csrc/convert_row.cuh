@@ -17,7 +17,7 @@ __host__ __device__ __forceinline__ void convert_row(T* a, int D, int op, T g) {
       for (int m = M - 1; m >= 1; --m) {
         const T km = c[m];
         const T z = static_cast<T>(1) - km * km;
-        for (int i = 0, j = m - 1; i <= j; ++i, --j) {
+        for (int i = 0, j = m - 1; i <= j; ++i, --j) {   // true divisions: the recursion amplifies every rounding
           const T ci = c[i], cj = c[j];
           c[i] = (ci - km * cj) / z;
           if (j != i) c[j] = (cj - km * ci) / z;
@@ -46,8 +46,9 @@ __host__ __device__ __forceinline__ void convert_row(T* a, int D, int op, T g) {
         a[0] = dexp(a[0]);
       } else {
         const T z = static_cast<T>(1) + g * a[0];
+        const T rz = static_cast<T>(1) / z;
         a[0] = dpow(z, static_cast<T>(1) / g);
-        for (int i = 1; i <= M; ++i) a[i] = a[i] / z;
+        for (int i = 1; i <= M; ++i) a[i] = a[i] * rz;
       }
       break;
     }
@@ -68,6 +69,54 @@ __host__ __device__ __forceinline__ void convert_row(T* a, int D, int op, T g) {
       break;
     }
   }
+}
+
+// The two O(M^2) recursions with the row in REGISTERS (compile-time length, fully unrolled): the shared-memory
+// version above costs ~2 M^2 shared-memory accesses and M^2 / 2 divisions per row, 4-5x the HBM time of the row at
+// M = 24.  The state is float64 for float32 rows too (like the Levinson kernels): the step-down recursion
+// amplifies each rounding by 1 / (1 - k^2) per order, and with a float64 state one reciprocal per order can
+// replace the per-element divisions without leaving the reference's own float32 error band.
+template <typename T, int D>
+__host__ __device__ __forceinline__ void convert_row_fixed(T* a, int op, T g_) {
+  constexpr int M = D - 1;
+  const double g = static_cast<double>(g_);
+  double c[D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) c[i] = static_cast<double>(a[i]);
+  if (op == DSB200_CONV_LPC2PAR) {
+#pragma unroll
+    for (int i = 1; i <= M; ++i) c[i] *= g;
+#pragma unroll
+    for (int m = M - 1; m >= 1; --m) {
+      const double km = c[1 + m];
+      const double rz = 1.0 / (1.0 - km * km);
+#pragma unroll
+      for (int i = 0; i <= (m - 1) / 2; ++i) {
+        const int j = m - 1 - i;
+        const double ci = c[1 + i], cj = c[1 + j];
+        c[1 + i] = (ci - km * cj) * rz;
+        if (j != i) c[1 + j] = (cj - km * ci) * rz;
+      }
+    }
+  } else {  // DSB200_CONV_PAR2LPC
+    const double rg = 1.0 / g;
+    c[0] *= rg;
+    if (M >= 1) c[M >= 1 ? 1 : 0] *= rg;
+#pragma unroll
+    for (int m = 2; m <= M; ++m) {
+      const double km = c[m];
+#pragma unroll
+      for (int i = 1; i <= m / 2; ++i) {
+        const int j = m - i;
+        const double ai = c[i], aj = c[j];
+        c[i] = ai + km * aj;
+        if (j != i) c[j] = aj + km * ai;
+      }
+      c[m] = km * rg;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < D; ++i) a[i] = static_cast<T>(c[i]);
 }
 
 }  // namespace dsb200

@@ -45,6 +45,7 @@ constexpr int kWarpsSpectrum = 16;
 constexpr int kWarpsMfcc = 12;
 constexpr int kOutFloats = 4 * 257;                    // one quad of real-valued output rows
 constexpr int kDefaultBulkStore = 1;                   // see stft512_try (DSB200_STFT_STORE)
+constexpr int kDefaultStaggerNs = 0;                   // see setup_args (DSB200_STFT_STAGGER)
 constexpr int kDefaultVariant = 1;                     // see stft512_try (DSB200_STFT_V)
 
 struct Args {
@@ -61,6 +62,7 @@ struct Args {
   int in_floats;        // floats per input buffer (>= span, multiple of 4)
   int bulk_in;          // waveform layout allows bulk copies (alignment)
   int bulk_out;         // output layout allows bulk stores
+  int stagger_ns;       // start delay per scheduler slot (warp >> 2), see stft512_try (DSB200_STFT_STAGGER)
   float eps;
   // MFCC epilogue (FMT == kFmtMfcc): fbank.py:315-320, dct.py:135-137, mfcc.py:252-256
   const float* mf_H;       // [257, C] filter bank
@@ -234,6 +236,10 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   // buffer `it & 1` at iteration `it` is (it >> 1) & 1: no phase bits are carried through the loop.
   if (q < A.n_quads) stage(b, g, in0, &mbar[0]);
   bool store_pending = false;
+  // The four warps that share a scheduler run the same phase sequence (loads, FP32 butterflies, shared-memory
+  // transposes, output staging) at the same rate; started together they want the same pipe at the same time.
+  // A one-off start delay per scheduler slot spreads their phases.
+  if (A.stagger_ns > 0) __nanosleep(static_cast<unsigned>(A.stagger_ns * (warp >> 2)));
 
   for (int it = 0; q < A.n_quads; ++it) {
     const int buf = it & 1;
@@ -623,6 +629,11 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
   A.bulk_in = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (T_len % 4 == 0) && (left % 4 == 0) &&
               (f.frame_period % 4 == 0);
   A.eps = static_cast<float>(s.eps);
+  static const int stagger_knob = [] {   // DSB200_STFT_STAGGER=<ns per scheduler slot> (tuning knob, read once)
+    const char* e = getenv("DSB200_STFT_STAGGER");
+    return e != nullptr ? atoi(e) : kDefaultStaggerNs;
+  }();
+  A.stagger_ns = stagger_knob;
   return DSB200_OK;
 }
 

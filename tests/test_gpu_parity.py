@@ -44,6 +44,13 @@ def check_outputs(name, op, params, prec, got, outs):
         if op == "frame" and not params.get("zmean"):
             assert np.array_equal(g, w, equal_nan=True), f"{name}: frame must be bit-exact"
             continue
+        if prec == "f32" and op in ("lpc2par", "par2lpc"):
+            # step-down / step-up recursions: on ill-conditioned rows the float32 rounding of the INPUT alone moves
+            # the result more than any implementation difference, so the yardstick is exact (float64 oracle)
+            # arithmetic on the same float32 inputs, with the reference's own float32 error as the allowance
+            exact = H.run_oracle(op, params, [a.astype(np.float64) for a in H.load_case(name, "f32")[2]])
+            H.assert_close_conditioned(g, w, exact, what=f"{name}[f32]")
+            continue
         if prec == "f32" and op in ILL:
             w64 = H.load_case(name, "f64")[3][0]
             H.assert_close_conditioned(g, w, w64, what=f"{name}[f32]")
