@@ -25,13 +25,15 @@ constexpr int kThreads = 256;
 // DF > 0: the row length is the compile-time DF and the O(M^2) recursions run in registers.
 template <typename T, int DF>
 __global__ void __launch_bounds__(kThreads) rowconv_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows,
-                                                           int D, int pitch, int op, T g) {
+                                                           int D, int pitch, int op, T g, int RB) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  T* tile = reinterpret_cast<T*>(smem_raw);   // [kThreads][pitch]
-  const int64_t n_tiles = (rows + kThreads - 1) / kThreads;
+  T* tile = reinterpret_cast<T*>(smem_raw);   // [RB][pitch], RB <= kThreads rows per tile
+  T* scale = tile + static_cast<size_t>(RB) * pitch;   // [RB] multiplier of x_1..x_M (gnorm / ignorm / norm0)
+  const bool scalar_op = op == DSB200_CONV_GNORM || op == DSB200_CONV_IGNORM || op == DSB200_CONV_NORM0;
+  const int64_t n_tiles = (rows + RB - 1) / RB;
   for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-    const int64_t base = t * kThreads;
-    const int nr = static_cast<int>(rows - base < kThreads ? rows - base : kThreads);
+    const int64_t base = t * RB;
+    const int nr = static_cast<int>(rows - base < RB ? rows - base : RB);
     const T* src = x + base * D;
     T* dst = y + base * D;
     // coalesced load: element e of the tile -> (row e / D, column e % D), walked incrementally
@@ -47,15 +49,19 @@ __global__ void __launch_bounds__(kThreads) rowconv_kernel(const T* __restrict__
     }
     __syncthreads();
     if (threadIdx.x < nr) {
-      if (DF > 0) convert_row_fixed<T, (DF > 0 ? DF : 1)>(tile + threadIdx.x * pitch, op, g);
-      else convert_row<T>(tile + threadIdx.x * pitch, D, op, g);
+      T* row = tile + threadIdx.x * pitch;
+      if (scalar_op) row_scalar<T>(row[0], op, g, &row[0], &scale[threadIdx.x]);   // the row is scaled on the way out
+      else if (DF > 0) convert_row_fixed<T, (DF > 0 ? DF : 1)>(row, op, g);
+      else convert_row<T>(row, D, op, g);
     }
     __syncthreads();
     {
       int r = threadIdx.x / D, c = threadIdx.x - r * D;
       const int dr = kThreads / D, dc = kThreads - dr * D;
       for (int e = threadIdx.x; e < nr * D; e += kThreads) {
-        dst[e] = tile[r * pitch + c];
+        T v = tile[r * pitch + c];
+        if (scalar_op && c > 0) v *= scale[r];
+        dst[e] = v;
         r += dr;
         c += dc;
         if (c >= D) { c -= D; ++r; }
@@ -78,16 +84,19 @@ int rowconv_impl(const void* x, void* y, int64_t rows, int32_t dim, int32_t op, 
   DeviceScope ds(device);
   DSB_CUDA(ds.err);
   const int pitch = dim | 1;
-  const size_t smem = static_cast<size_t>(kThreads) * pitch * sizeof(T);
+  // rows per tile: one per thread while a tile stays below ~64 KB, fewer for long rows
+  const size_t row_bytes = static_cast<size_t>(pitch) * sizeof(T);
+  const int RB = static_cast<int>(std::max<size_t>(1, std::min<size_t>(kThreads, (64 * 1024) / row_bytes)));
+  const size_t smem = static_cast<size_t>(RB) * (row_bytes + sizeof(T));
   if (smem > static_cast<size_t>(max_dynamic_smem(device)))
     return fail(DSB200_E_UNSUPPORTED, "row length %d does not fit in shared memory", dim);
-  const int64_t n_tiles = (rows + kThreads - 1) / kThreads;
+  const int64_t n_tiles = (rows + RB - 1) / RB;
   const int per_sm = std::max<int>(1, std::min<int>(8, static_cast<int>((200 * 1024) / std::max<size_t>(smem, 1))));
   const int blocks = static_cast<int>(std::min<int64_t>(n_tiles, static_cast<int64_t>(sm_count(device)) * per_sm));
   auto launch = [&](auto kern) -> int {
     DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<blocks, kThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const T*>(x), static_cast<T*>(y), rows, dim, pitch, op, static_cast<T>(param));
+        static_cast<const T*>(x), static_cast<T*>(y), rows, dim, pitch, op, static_cast<T>(param), RB);
     return DSB200_OK;
   };
   // register-resident recursions for the usual LPC orders 12 / 16 / 20 / 24 (DSB200_ROWCONV_GENERIC=1: A/B knob)

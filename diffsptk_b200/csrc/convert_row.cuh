@@ -6,6 +6,34 @@
 
 namespace dsb200 {
 
+// gnorm.py:101-112, ignorm.py:98-109, norm0.py:88-94: y_0 and the factor that multiplies x_1..x_M.
+template <typename T>
+__host__ __device__ __forceinline__ void row_scalar(T x0, int op, T g, T* y0, T* mult) {
+  const T one = static_cast<T>(1);
+  if (op == DSB200_CONV_GNORM) {
+    if (g == static_cast<T>(0)) {
+      *y0 = dexp(x0);
+      *mult = one;
+    } else {
+      const T z = one + g * x0;
+      *y0 = dpow(z, one / g);
+      *mult = one / z;
+    }
+  } else if (op == DSB200_CONV_IGNORM) {
+    if (g == static_cast<T>(0)) {
+      *y0 = dlog(x0);
+      *mult = one;
+    } else {
+      const T z = dpow(x0, g);
+      *y0 = (z - one) / g;
+      *mult = z;
+    }
+  } else {  // DSB200_CONV_NORM0
+    *y0 = one / x0;
+    *mult = one / x0;
+  }
+}
+
 template <typename T>
 __host__ __device__ __forceinline__ void convert_row(T* a, int D, int op, T g) {
   const int M = D - 1;
@@ -41,31 +69,11 @@ __host__ __device__ __forceinline__ void convert_row(T* a, int D, int op, T g) {
       }
       break;
     }
-    case DSB200_CONV_GNORM: {
-      if (g == static_cast<T>(0)) {
-        a[0] = dexp(a[0]);
-      } else {
-        const T z = static_cast<T>(1) + g * a[0];
-        const T rz = static_cast<T>(1) / z;
-        a[0] = dpow(z, static_cast<T>(1) / g);
-        for (int i = 1; i <= M; ++i) a[i] = a[i] * rz;
-      }
-      break;
-    }
-    case DSB200_CONV_IGNORM: {
-      if (g == static_cast<T>(0)) {
-        a[0] = dlog(a[0]);
-      } else {
-        const T z = dpow(a[0], g);
-        a[0] = (z - static_cast<T>(1)) / g;
-        for (int i = 1; i <= M; ++i) a[i] = a[i] * z;
-      }
-      break;
-    }
-    default: {  // DSB200_CONV_NORM0
-      const T b0 = static_cast<T>(1) / a[0];
-      a[0] = b0;
-      for (int i = 1; i <= M; ++i) a[i] = a[i] * b0;
+    default: {  // gnorm / ignorm / norm0: a new zeroth element and one multiplier for the rest of the row
+      T mult;
+      row_scalar<T>(a[0], op, g, &a[0], &mult);
+      if (mult != static_cast<T>(1))
+        for (int i = 1; i <= M; ++i) a[i] = a[i] * mult;
       break;
     }
   }

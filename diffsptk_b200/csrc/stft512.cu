@@ -46,6 +46,7 @@ constexpr int kWarpsMfcc = 12;
 constexpr int kOutFloats = 4 * 257;                    // one quad of real-valued output rows
 constexpr int kDefaultBulkStore = 1;                   // see stft512_try (DSB200_STFT_STORE)
 constexpr int kDefaultStaggerNs = 0;                   // see setup_args (DSB200_STFT_STAGGER)
+constexpr int kDefaultWarpsV7 = 20;                    // see stft512_try (DSB200_STFT_W)
 constexpr int kDefaultVariant = 1;                     // see stft512_try (DSB200_STFT_V)
 
 struct Args {
@@ -128,12 +129,18 @@ __device__ __forceinline__ void put_bin(float* rowA, float* rowB, bool vB, int k
 // proxy fence in front of the span copies (no change), and moving (re A, re B, im A, im B) through the transposes
 // as one 128-bit access (32 fewer LDS/STS but 60 more MOVs to build aligned register quads).
 constexpr int kVPair2 = 1;
+// 2 = ONE staging buffer per warp: the next span's bulk copy is issued as soon as the current samples sit in
+// registers and lands while the butterflies run (saves the second 2.5 KB buffer per warp); 4 = the inter-pass
+// twiddles W256^(l k2) come from a shared-memory table instead of 30 registers per thread.  Both together make
+// room -- 96 registers, 11 KB of shared memory per warp -- for 20 warps per SM instead of 16.
+constexpr int kVSingleBuf = 2, kVTwSmem = 4;
 constexpr int kShift = 5;   // 2 * 80 / 32
 
 template <int NJ, bool MASK_ALL, int FMT, int W, int V = 0>
 __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   constexpr int kWarps = W, kThreads = W * 32;
-  constexpr bool PAIR2 = (V & kVPair2) != 0;
+  constexpr bool PAIR2 = (V & kVPair2) != 0, SB = (V & kVSingleBuf) != 0, TWS = (V & kVTwSmem) != 0;
+  constexpr int kBufs = SB ? 1 : 2;
   constexpr int kFB = PAIR2 ? 2 : 1;        // frame B = frame A + kFB
   constexpr int kRowB = kFB * 257;          // its staged row
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -149,13 +156,14 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   float* win = reinterpret_cast<float*>(smem_raw + 16 * kWarps);
   float2* htw = reinterpret_cast<float2*>(win + 512);  // [128]
   // MFCC tables (FMT == kFmtMfcc only), see mf_table_floats(): W^T | lifter | cb | ce | seg_k0 | chs | wT | info
-  float* mfW = reinterpret_cast<float*>(htw + 128);
+  float2* tw16 = htw + 128;                            // [16 k2][16 l] (TWS only)
+  float* mfW = reinterpret_cast<float*>(tw16 + (TWS ? 256 : 0));
   const int mf_floats = (FMT == kFmtMfcc) ? mf_table_floats(A.mf_C, A.mf_M) : 0;
-  unsigned char* wbase = smem_raw + 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) +
+  unsigned char* wbase = smem_raw + 16 * kWarps + 512 * sizeof(float) + (128 + (TWS ? 256 : 0)) * sizeof(float2) +
                          static_cast<size_t>(mf_floats) * 4 +
-                         static_cast<size_t>(warp) * (2 * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
+                         static_cast<size_t>(warp) * (kBufs * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
   float* in0 = reinterpret_cast<float*>(wbase);
-  float2* xch = reinterpret_cast<float2*>(wbase + 2 * static_cast<size_t>(A.in_floats) * 4);
+  float2* xch = reinterpret_cast<float2*>(wbase + kBufs * static_cast<size_t>(A.in_floats) * 4);
   float* ostage = reinterpret_cast<float*>(xch);            // aliases the exchange planes (see loop)
   float2* xr = xch + h * (2 * kPlane);
   float2* xi = xr + kPlane;
@@ -168,12 +176,16 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   }
   // per-lane twiddles: W256^(l k2) for the inter-pass rotation, W512^(16 k1 + l) / 2 for the split
   const float2* tw = reinterpret_cast<const float2*>(A.tw512);
-  float twr[16], twi[16];
+  float twr[TWS ? 1 : 16], twi[TWS ? 1 : 16];
+  if (TWS) {
+    for (int i = tid; i < 256; i += kThreads) tw16[i] = tw[2 * (i & 15) * (i >> 4)];
+  } else {
 #pragma unroll
-  for (int k2 = 1; k2 < 16; ++k2) {
-    const float2 v = tw[2 * l * k2];
-    twr[k2] = v.x;
-    twi[k2] = v.y;
+    for (int k2 = 1; k2 < 16; ++k2) {
+      const float2 v = tw[2 * l * k2];
+      twr[TWS ? 0 : k2] = v.x;
+      twi[TWS ? 0 : k2] = v.y;
+    }
   }
   for (int i = tid; i < 128; i += kThreads) {  // half split-twiddles W512^k / 2, k = 16 k1 + l < 128
     const float2 v = tw[i];
@@ -247,10 +259,10 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     const int qn = q + n_warps;
     int bn = b + db, gn = g + dg;
     if (gn >= A.quads_per_utt) { gn -= A.quads_per_utt; ++bn; }
-    if (qn < A.n_quads) stage(bn, gn, in0 + (buf ^ 1) * A.in_floats, &mbar[buf ^ 1]);
-    mbar_wait(&mbar[buf], static_cast<uint32_t>(it >> 1) & 1u);
+    if (!SB && qn < A.n_quads) stage(bn, gn, in0 + (buf ^ 1) * A.in_floats, &mbar[buf ^ 1]);
+    mbar_wait(&mbar[SB ? 0 : buf], static_cast<uint32_t>(SB ? it : (it >> 1)) & 1u);
     __syncwarp();  // zero-fill / guarded stores of the other lanes
-    const float* span = in0 + buf * A.in_floats;
+    const float* span = in0 + (SB ? 0 : buf) * A.in_floats;
 
     const int hf = PAIR2 ? h : 2 * h;         // first frame of this half-warp's pair within the quad
     const int fA = 4 * g + hf;
@@ -290,9 +302,22 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       }
     }
 
+    if (SB) {
+      // every sample of this quad is in registers (the multiplies above consumed the loads): refill the buffer
+      __syncwarp();
+      if (qn < A.n_quads) stage(bn, gn, in0, &mbar[0]);
+    }
+
     fft16<NJ>(a);  // over j -> k2, result in digit-swapped order
 #pragma unroll
-    for (int k2 = 1; k2 < 16; ++k2) a[dig(k2)] = cmul_s(a[dig(k2)], twr[k2], twi[k2]);
+    for (int k2 = 1; k2 < 16; ++k2) {
+      if (TWS) {
+        const float2 t = tw16[16 * k2 + l];
+        a[dig(k2)] = cmul_s(a[dig(k2)], t.x, t.y);
+      } else {
+        a[dig(k2)] = cmul_s(a[dig(k2)], twr[TWS ? 0 : k2], twi[TWS ? 0 : k2]);
+      }
+    }
 
     // the previous quad's bulk store reads the staging rows that alias the exchange planes
     if (store_pending) {
@@ -419,7 +444,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       __syncwarp();
       // Table pointers are re-derived here from an opaque offset: hoisted out of the quad loop they would pin
       // ~12 registers across the register-tight FFT (128 per thread at 16 warps) and spill its loop state.
-      uint32_t tbl_off = 16u * kWarps + 512u * sizeof(float) + 128u * sizeof(float2);
+      uint32_t tbl_off = 16u * kWarps + 512u * sizeof(float) + (128u + (TWS ? 256u : 0u)) * sizeof(float2);
       int C = A.mf_C, M = A.mf_M;
       asm volatile("" : "+r"(tbl_off), "+r"(C), "+r"(M));
       const int M1 = M + 1;
@@ -646,9 +671,10 @@ static int stft_variant_knob() {
   return v;
 }
 
-static size_t smem_bytes(const Args& A, int mf_floats, int kWarps) {
-  return 16 * kWarps + 512 * sizeof(float) + 128 * sizeof(float2) + static_cast<size_t>(mf_floats) * 4 +
-         static_cast<size_t>(kWarps) * (2 * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
+static size_t smem_bytes(const Args& A, int mf_floats, int kWarps, int variant = 0) {
+  const size_t bufs = (variant & kVSingleBuf) ? 1 : 2, tws = (variant & kVTwSmem) ? 256 : 0;
+  return 16 * kWarps + 512 * sizeof(float) + (128 + tws) * sizeof(float2) + static_cast<size_t>(mf_floats) * 4 +
+         static_cast<size_t>(kWarps) * (bufs * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
 }
 
 int stft512_try(const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
@@ -670,8 +696,23 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
   }();
   A.bulk_out = store_mode && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   if (NJ == 13) {
-    if ((stft_variant_knob() & kVPair2) && A.P == 80)
+    const int v = stft_variant_knob();
+    if ((v & kVPair2) && A.P == 80) {
+      if ((v & 6) == 6) {   // single buffer + shared-memory twiddles: 16 or 20 warps (DSB200_STFT_W)
+        static const int w_knob = [] {
+          const char* e = getenv("DSB200_STFT_W");
+          return e != nullptr ? atoi(e) : kDefaultWarpsV7;
+        }();
+        if (w_knob == 20) {
+          const size_t sm20 = smem_bytes(A, 0, 20, 7);
+          if (sm20 <= static_cast<size_t>(max_dynamic_smem(device)))
+            return launch_fmt<13, false, 20, 7>(A, p->spec.out_format, sm20, device, stream);
+        }
+        return launch_fmt<13, false, kWarpsSpectrum, 7>(A, p->spec.out_format, smem_bytes(A, 0, kWarpsSpectrum, 7),
+                                                        device, stream);
+      }
       return launch_fmt<13, false, kWarpsSpectrum, kVPair2>(A, p->spec.out_format, smem, device, stream);
+    }
     return launch_fmt<13, false, kWarpsSpectrum, 0>(A, p->spec.out_format, smem, device, stream);
   }
   return launch_fmt<16, true, kWarpsMfcc>(A, p->spec.out_format, smem, device, stream);

@@ -8,7 +8,6 @@ Parity: neither knob changes the arithmetic of a frame, so every variant must re
 output BIT FOR BIT on a batch with ragged edges (the default itself is pinned by tests/test_gpu_parity.py).
 Timing: CUDA events over `steps` launches of BASELINE config 2 (256 x 10 s), two rotating inputs.
 """
-import itertools
 import json
 import os
 import subprocess
@@ -26,7 +25,7 @@ def child():
 
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(7)
-    res = {"V": os.environ.get("DSB200_STFT_V", "1"), "STAGGER": os.environ.get("DSB200_STFT_STAGGER", "0")}
+    res = {k[12:]: v for k, v in os.environ.items() if k.startswith("DSB200_STFT_")}
     # parity batch: ragged length (last quad partial), several utterances, all real formats + complex
     outs = {}
     for T in (16000, 16084, 400, 81):
@@ -39,7 +38,7 @@ def child():
         with torch.no_grad():
             outs[f"{T}_mfcc"] = D.mfcc_from_waveform(x).cpu()
     ref_path = os.path.join(OUT, "sweep_ref.pt")
-    if res["V"] == "0" and res["STAGGER"] == "0":
+    if res == {"V": "0"}:
         torch.save(outs, ref_path)
         res["parity"] = "reference"
     else:
@@ -68,30 +67,32 @@ def child():
 
 
 def main():
+    """SWEEP_COMBOS="V=1;V=7,W=16;V=7,W=20": ';'-separated configurations, each a ','-list of DSB200_STFT_<K>=<v>.
+    The first configuration must be the parity reference (V=0)."""
     os.makedirs(OUT, exist_ok=True)
-    combos = [("0", "0")] + [("1", st) for st in os.environ.get("SWEEP_STAGGERS", "0,200,400,800,1200,1600").split(",")]
+    spec = os.environ.get("SWEEP_COMBOS", "V=0;V=1;V=7,W=16;V=7,W=20")
+    combos = [dict(kv.split("=") for kv in c.split(",")) for c in spec.split(";")]
     rows = []
-    for rep in range(2):   # second pass: the default and the three fastest again (clocks drift between processes)
+    for rep in range(2):   # second pass: the reference and the three fastest again (clocks drift between processes)
         if rep == 1:
             ok = sorted((r for r in rows if "ms_median" in r), key=lambda r: r["ms_median"])[:3]
-            combos = [("0", "0")] + [(r["V"], r["STAGGER"]) for r in ok if (r["V"], r["STAGGER"]) != ("0", "0")]
-        for v, a in combos:
-            env = dict(os.environ, DSB200_STFT_V=v, DSB200_STFT_STAGGER=a)
+            combos = [combos[0]] + [r["combo"] for r in ok if r["combo"] != combos[0]]
+        for c in combos:
+            env = dict(os.environ, **{f"DSB200_STFT_{k}": v for k, v in c.items()})
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, capture_output=True,
                                text=True, timeout=600)
             line = [ln for ln in r.stdout.splitlines() if ln.startswith("SWEEP ")]
-            if not line:
-                rows.append({"V": v, "STAGGER": a, "error": (r.stderr or r.stdout)[-400:]})
-            else:
-                rows.append(json.loads(line[0][6:]))
-            print(rows[-1], flush=True)
+            row = json.loads(line[0][6:]) if line else {"error": (r.stderr or r.stdout)[-400:]}
+            row["combo"] = c
+            rows.append(row)
+            print(row, flush=True)
     with open(os.path.join(OUT, "stft_variant_sweep.json"), "w") as f:
         json.dump(rows, f, indent=1)
     ok = [r for r in rows if r.get("parity") in ("bit-exact", "reference")]
     best = min(ok, key=lambda r: r["ms_median"])
     print("BEST", best)
     with open(os.path.join(OUT, "sweep_best.env"), "w") as f:
-        f.write(f"export DSB200_STFT_V={best['V']} DSB200_STFT_STAGGER={best['STAGGER']}\n")
+        f.write("export " + " ".join(f"DSB200_STFT_{k}={v}" for k, v in best["combo"].items()) + "\n")
 
 
 if __name__ == "__main__":
