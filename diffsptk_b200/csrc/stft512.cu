@@ -45,7 +45,6 @@ constexpr int kWarpsSpectrum = 16;
 constexpr int kWarpsMfcc = 12;
 constexpr int kOutFloats = 4 * 257;                    // one quad of real-valued output rows
 constexpr int kDefaultBulkStore = 1;                   // see stft512_try (DSB200_STFT_STORE)
-constexpr int kDefaultStaggerNs = 0;                   // see setup_args (DSB200_STFT_STAGGER)
 constexpr int kDefaultWarpsV7 = 20;                    // see stft512_try (DSB200_STFT_W)
 constexpr int kDefaultVariant = 1;                     // see stft512_try (DSB200_STFT_V)
 
@@ -63,7 +62,6 @@ struct Args {
   int in_floats;        // floats per input buffer (>= span, multiple of 4)
   int bulk_in;          // waveform layout allows bulk copies (alignment)
   int bulk_out;         // output layout allows bulk stores
-  int stagger_ns;       // start delay per scheduler slot (warp >> 2), see stft512_try (DSB200_STFT_STAGGER)
   float eps;
   // MFCC epilogue (FMT == kFmtMfcc): fbank.py:315-320, dct.py:135-137, mfcc.py:252-256
   const float* mf_H;       // [257, C] filter bank
@@ -132,7 +130,10 @@ constexpr int kVPair2 = 1;
 // 2 = ONE staging buffer per warp: the next span's bulk copy is issued as soon as the current samples sit in
 // registers and lands while the butterflies run (saves the second 2.5 KB buffer per warp); 4 = the inter-pass
 // twiddles W256^(l k2) come from a shared-memory table instead of 30 registers per thread.  Both together make
-// room -- 96 registers, 11 KB of shared memory per warp -- for 20 warps per SM instead of 16.
+// room -- 96 registers, 11 KB of shared memory per warp -- for 20 warps per SM instead of 16.  Measured
+// (profiles/r1_stft512_v5_sweep.json): 0.1884 ms with 20 warps against 0.1894 ms for variant 1 with 16 -- the
+// kernel does not respond to occupancy (nor to a start stagger of the warps that share a scheduler, tried and
+// removed), so variant 1 stays the default and this one is kept as an A/B knob (DSB200_STFT_V=7).
 constexpr int kVSingleBuf = 2, kVTwSmem = 4;
 constexpr int kShift = 5;   // 2 * 80 / 32
 
@@ -248,10 +249,6 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   // buffer `it & 1` at iteration `it` is (it >> 1) & 1: no phase bits are carried through the loop.
   if (q < A.n_quads) stage(b, g, in0, &mbar[0]);
   bool store_pending = false;
-  // The four warps that share a scheduler run the same phase sequence (loads, FP32 butterflies, shared-memory
-  // transposes, output staging) at the same rate; started together they want the same pipe at the same time.
-  // A one-off start delay per scheduler slot spreads their phases.
-  if (A.stagger_ns > 0) __nanosleep(static_cast<unsigned>(A.stagger_ns * (warp >> 2)));
 
   for (int it = 0; q < A.n_quads; ++it) {
     const int buf = it & 1;
@@ -654,11 +651,6 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
   A.bulk_in = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (T_len % 4 == 0) && (left % 4 == 0) &&
               (f.frame_period % 4 == 0);
   A.eps = static_cast<float>(s.eps);
-  static const int stagger_knob = [] {   // DSB200_STFT_STAGGER=<ns per scheduler slot> (tuning knob, read once)
-    const char* e = getenv("DSB200_STFT_STAGGER");
-    return e != nullptr ? atoi(e) : kDefaultStaggerNs;
-  }();
-  A.stagger_ns = stagger_knob;
   return DSB200_OK;
 }
 

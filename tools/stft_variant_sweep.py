@@ -63,6 +63,43 @@ def child():
     res["ms_median"] = ts[len(ts) // 2]
     res["ms_min"] = ts[0]
     res["ms_mean"] = sum(ts) / len(ts)
+    # sustained run with NVML sampling: is the kernel running into the board's power cap?
+    sustained = int(os.environ.get("SWEEP_SUSTAINED", "3000"))
+    if sustained:
+        import threading
+        import time
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(0)
+            mhz, watts, stop = [], [], threading.Event()
+
+            def poll():
+                while not stop.is_set():
+                    mhz.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    watts.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                    time.sleep(0.005)
+            th = threading.Thread(target=poll, daemon=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.no_grad():
+                for i in range(200):
+                    y = m(xs[i & 1])
+                torch.cuda.synchronize()
+                th.start()
+                e0.record()
+                for i in range(sustained):
+                    y = m(xs[i & 1])
+                e1.record()
+                torch.cuda.synchronize()
+            stop.set()
+            th.join(timeout=2)
+            k = len(mhz) // 4    # drop the ramp
+            res["sustained_ms"] = e0.elapsed_time(e1) / sustained
+            res["sm_mhz"] = sorted(mhz[k:])[len(mhz[k:]) // 2] if mhz[k:] else None
+            res["watts"] = sum(watts[k:]) / max(1, len(watts[k:]))
+            res["power_limit_w"] = nv.nvmlDeviceGetEnforcedPowerLimit(h) / 1000.0
+        except Exception as exc:   # NVML missing: timing only
+            res["nvml_error"] = repr(exc)[:100]
     print("SWEEP " + json.dumps(res), flush=True)
 
 
