@@ -26,6 +26,7 @@ from .mcep import MelCepstralAnalysis
 from .mfcc import MelFrequencyCepstralCoefficientsAnalysis
 from .mgc2mgc import MelGeneralizedCepstrumToMelGeneralizedCepstrum
 from .mgc2sp import MelGeneralizedCepstrumToSpectrum
+from .mgcep import MelGeneralizedCepstralAnalysis
 from .plp import PerceptualLinearPredictiveCoefficientsAnalysis
 from .plp import PerceptualLinearPredictiveCoefficientsAnalysis as PLP
 from .mfcc import MelFrequencyCepstralCoefficientsAnalysis as MFCC
@@ -48,4 +49,5 @@ __all__ = [
     "LinearPredictiveCoefficientsToParcorCoefficients", "ParcorCoefficientsToLinearPredictiveCoefficients",
     "AllPoleToAllZeroDigitalFilterCoefficients", "MelGeneralizedCepstrumToMelGeneralizedCepstrum",
     "MelGeneralizedCepstrumToSpectrum", "PerceptualLinearPredictiveCoefficientsAnalysis", "PLP",
+    "MelGeneralizedCepstralAnalysis",
 ]

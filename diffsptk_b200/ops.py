@@ -1138,3 +1138,48 @@ def _rowconv_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{_NS}::rowconv", _rowconv_bwd, setup_context=_rowconv_setup)
+
+
+# ------------------------------------------------------------------ Toeplitz-plus-Hankel solve (mgcep Newton step)
+@torch.library.custom_op(f"{_NS}::thsolve", mutates_args=(), device_types="cuda")
+def thsolve(t: Tensor, h: Tensor, r: Tensor) -> Tensor:
+    """``(Toeplitz(t) + Hankel(h)) x = r`` per row: ``t (..., M)``, ``h (..., 2M-1)``, ``r (..., M) -> x (..., M)``."""
+    dt = _native_dtype(t, h, r)
+    tc, hc, rc = _prep(t, dt), _prep(h, dt), _prep(r, dt)
+    M = tc.shape[-1]
+    if hc.shape[-1] != 2 * M - 1 or rc.shape[-1] != M:
+        raise ValueError("thsolve: h must have 2 M - 1 and r must have M elements per row.")
+    rows = tc.numel() // max(M, 1)
+    x = torch.empty_like(rc)
+    N.check(N.typed("dsb200_thsolve", dt == torch.float64)(_ptr(tc), _ptr(hc), _ptr(rc), _ptr(x), rows, M, _dev(t),
+                                                           _stream(t)))
+    return x
+
+
+@thsolve.register_fake
+def _(t, h, r):
+    return r.new_empty(r.shape, dtype=_native_dtype(t, h, r))
+
+
+def _thsolve_setup(ctx, inputs, output):
+    t, h, r = inputs
+    ctx.save_for_backward(t, h, output)
+
+
+def _thsolve_bwd(ctx, g):
+    # A x = r with A = T(t) + H(h) symmetric:  lam = A^-1 g (the same solver);  dr = lam;  dA = -lam x^T;
+    # dt_d = sum_{|i-j|=d} dA_ij,  dh_s = sum_{i+j=s} dA_ij
+    t, h, x = ctx.saved_tensors
+    lam = thsolve(t, h, g.to(x.dtype))
+    dA = -lam.unsqueeze(-1) * x.unsqueeze(-2)
+    M = x.shape[-1]
+    i = torch.arange(M, device=x.device)
+    dist = (i[:, None] - i[None, :]).abs().reshape(-1)
+    summ = (i[:, None] + i[None, :]).reshape(-1)
+    flat = dA.reshape(*dA.shape[:-2], M * M)
+    dt = torch.zeros_like(t, dtype=x.dtype).index_add_(-1, dist, flat)
+    dh = torch.zeros_like(h, dtype=x.dtype).index_add_(-1, summ, flat)
+    return _like_input(dt, t), _like_input(dh, h), _like_input(lam, x)
+
+
+torch.library.register_autograd(f"{_NS}::thsolve", _thsolve_bwd, setup_context=_thsolve_setup)

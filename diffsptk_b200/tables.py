@@ -359,3 +359,43 @@ def make_b2mc_matrix(cep_order, alpha, device=None, dtype=None):
     A = torch.eye(int(cep_order) + 1, dtype=torch.double)
     A[:, 1:].fill_diagonal_(alpha)
     return _cast(A.T.contiguous(), device, dtype)
+
+
+# ------------------------------------------------------------------------- mgcep tables (section 8f rank 3)
+@functools.lru_cache(maxsize=32)
+def _mgcep_freqt_np(in_order, out_order, alpha):
+    """``CoefficientsFrequencyTransform`` of mgcep.py:251-283 (NOT the one of mcep.py), stored transposed."""
+    beta = 1 - alpha * alpha
+    L1, L2 = in_order + 1, out_order + 1
+    A = np.zeros((L2, L1))
+    A[0, 0] = 1
+    if 1 < L2 and 1 < L1:
+        A[1, 1:] = (alpha ** torch.arange(L1 - 1, dtype=torch.double)).numpy() * beta
+    for i in range(2, L2):
+        prev, cur = A[i - 1], A[i]
+        for j in range(1, L1):
+            cur[j] = prev[j - 1] + alpha * (cur[j - 1] - prev[j])
+    return np.ascontiguousarray(A.T)
+
+
+def make_mgcep_freqt_matrix(in_order, out_order, alpha, device=None, dtype=None):
+    return _cast(_mgcep_freqt_np(int(in_order), int(out_order), float(alpha)).copy(), device, dtype)
+
+
+def make_mgcep_ptrans(order, alpha, device=None, dtype=None):
+    """``PTransform`` of mgcep.py:286-308, stored transposed."""
+    A = torch.eye(order + 1, dtype=torch.double)
+    A[:, 1:].fill_diagonal_(alpha)
+    A[0, 0] -= alpha * alpha
+    A[0, 1] += alpha
+    A[-1, -1] += alpha
+    return _cast(A.T.contiguous(), device, dtype)
+
+
+def make_mgcep_qtrans(order, alpha, device=None, dtype=None):
+    """``QTransform`` of mgcep.py:311-332, stored transposed."""
+    A = torch.eye(order + 1, dtype=torch.double)
+    A[1:].fill_diagonal_(alpha)
+    A[1, 0] = 0
+    A[1, 1] += alpha
+    return _cast(A.T.contiguous(), device, dtype)

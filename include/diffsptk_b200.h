@@ -264,6 +264,12 @@ DSB200_DECL2(dsb200_delta_backward, (const void* gy, const void* window, void* g
 DSB200_DECL2(dsb200_rowconv, (const void* x, void* y, int64_t rows, int32_t dim, int32_t op, double param,
                               int device, void* stream))
 
+/* Per-row solve of (Toeplitz(t) + Hankel(h)) x = r: t[rows, order], h[rows, 2 * order - 1], r[rows, order] ->
+ * x[rows, order].  The Newton step of MelGeneralizedCepstralAnalysis, diffsptk/modules/mgcep.py:219-222
+ * (symmetric_toeplitz / hankel, diffsptk/utils/private.py:291-302, then torch.linalg.solve). */
+DSB200_DECL2(dsb200_thsolve, (const void* t, const void* h, const void* r, void* x, int64_t rows, int32_t order,
+                              int device, void* stream))
+
 /* ---- host-buffer pipeline (the end-to-end path: pinned host -> device -> kernel -> host) -------------
  * One object owns two device staging slots and three streams (H2D, compute, D2H) and runs
  * dsb200_stft on utterance chunks so that copies overlap compute.  x_host[batch,T], y_host[batch,N,K]

@@ -969,3 +969,88 @@ def plp(x, plp_order, n_channel, sample_rate, compression_factor=0.33, lifter=1,
     if out_format in (3, "ycE"):
         return np.concatenate([y, c0, E], axis=-1)
     raise ValueError(f"out_format {out_format} is not supported.")
+
+
+# ----------------------------------------------------------------------------- mgcep (8f rank 3)
+def _mgcep_freqt_matrix(in_order, out_order, alpha):
+    """CoefficientsFrequencyTransform of diffsptk/modules/mgcep.py:251-283, shape (L1, L2)."""
+    beta = 1 - alpha * alpha
+    L1, L2 = in_order + 1, out_order + 1
+    A = np.zeros((L2, L1))
+    A[0, 0] = 1
+    if 1 < L2 and 1 < L1:
+        A[1, 1:] = alpha ** np.arange(L1 - 1, dtype=np.float64) * beta
+    for i in range(2, L2):
+        for j in range(1, L1):
+            A[i, j] = A[i - 1, j - 1] + alpha * (A[i, j - 1] - A[i - 1, j])
+    return np.ascontiguousarray(A.T)
+
+
+def mgcep(x, *, fft_length, cep_order, alpha=0, gamma=0, c=None, n_iter=0):
+    """Newton iteration on the mel-generalized cepstrum.  diffsptk/modules/mgcep.py:173-246 (module-only API)."""
+    x = _as_float(x)
+    gamma = _get_gamma(gamma, c)
+    if fft_length < 2 * cep_order:
+        raise ValueError("cep_order must be less than or equal to fft_length // 2.")
+    if gamma < -1 or 0 < gamma:
+        raise ValueError("gamma must be in [-1, 0].")
+    if gamma == 0:
+        return mcep(x, cep_order, alpha, n_iter)
+    M, L, dt = cep_order, fft_length, x.dtype
+    cf = _mgcep_freqt_matrix(M, L - 1, -alpha).astype(dt)
+    pf = _mgcep_freqt_matrix(L - 1, 2 * M, alpha).astype(dt)
+    rf = _mgcep_freqt_matrix(L - 1, M, alpha).astype(dt)
+    P = np.eye(2 * M + 1)
+    P[np.arange(2 * M), np.arange(1, 2 * M + 1)] = alpha
+    P[0, 0] -= alpha * alpha
+    P[0, 1] += alpha
+    P[-1, -1] += alpha
+    Q = np.eye(2 * M + 1)
+    Q[np.arange(1, 2 * M + 1), np.arange(2 * M)] = alpha
+    Q[1, 0] = 0
+    Q[1, 1] += alpha
+    P, Q = P.T.astype(dt), Q.T.astype(dt)
+
+    def irfft(z):
+        return np.fft.irfft(z, axis=-1).astype(dt)
+
+    def newton(g, b1):
+        b = np.concatenate([np.zeros_like(b1[..., :1]), b1], axis=-1)
+        C = np.fft.rfft((b @ cf).astype(np.float64), n=L, axis=-1)
+        Cr, Ci = C.real.astype(dt), C.imag.astype(dt)
+        if g == -1:
+            p_re = x
+        else:
+            X, Y = 1 + dt.type(g) * Cr, dt.type(g) * Ci
+            XX, YY = X * X, Y * Y
+            D = XX + YY
+            p_re = x * np.power(D, dt.type(-1 / g)) / D
+            q = p_re / D
+            q_c = q * (XX - YY) + 1j * (q * (2 * X * Y))
+            r_c = p_re * X + 1j * (p_re * Y)
+        p = irfft(p_re) @ pf
+        if g == -1:
+            q, r = p, p[..., : M + 1]
+        else:
+            q, r = irfft(q_c) @ pf, irfft(r_c) @ rf
+        p, q = p @ P, q @ Q
+        if g != -1:
+            eps = r[..., 0] + dt.type(g) * (r[..., 1:] * b1).sum(-1)
+        R = _toeplitz(p[..., :M]) + _hankel(q[..., 2:] * dt.type(1 + g))
+        b1 = b1 + np.linalg.solve(R, r[..., 1:, None])[..., 0].astype(dt)
+        if g == -1:
+            eps = r[..., 0] + dt.type(g) * (r[..., 1:] * b1).sum(-1)
+        return np.sqrt(eps)[..., None], b1
+
+    b0, b1 = newton(-1, np.zeros((*x.shape[:-1], M), dtype=dt))
+    if gamma != -1:
+        b = np.concatenate([b0, b1], axis=-1)
+        b = ignorm(b, -1)
+        b = b2mc(b, alpha)
+        b = mgc2mgc(b, M, in_gamma=-1, out_gamma=gamma)
+        b = mc2b(b, alpha)
+        b = gnorm(b, gamma)
+        b1 = b[..., 1:]
+        for _ in range(n_iter):
+            b0, b1 = newton(gamma, b1)
+    return b2mc(ignorm(np.concatenate([b0, b1], axis=-1), gamma), alpha)

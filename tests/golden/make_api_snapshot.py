@@ -1,7 +1,7 @@
 """Snapshot the reference's public signatures for the hot path (run in the build container).
 
 Writes ``tests/golden/api_signatures.json``: constructor / functional parameter names, kinds and
-defaults of the 35 exported classes (incl. aliases) and 28 functional delegates, plus the
+defaults of the 36 exported classes (incl. aliases) and 28 functional delegates, plus the
 ``_takes_input_size`` flags -- the drop-in contract of SURVEY.md section 8(b).
 """
 
@@ -23,7 +23,8 @@ CLASSES = ["Autocorrelation", "DiscreteCosineTransform", "DCT", "MelFilterBankAn
            "GeneralizedCepstrumGainNormalization", "GeneralizedCepstrumInverseGainNormalization",
            "LinearPredictiveCoefficientsToParcorCoefficients", "ParcorCoefficientsToLinearPredictiveCoefficients",
            "AllPoleToAllZeroDigitalFilterCoefficients", "MelGeneralizedCepstrumToMelGeneralizedCepstrum",
-           "MelGeneralizedCepstrumToSpectrum", "PerceptualLinearPredictiveCoefficientsAnalysis", "PLP"]
+           "MelGeneralizedCepstrumToSpectrum", "PerceptualLinearPredictiveCoefficientsAnalysis", "PLP",
+           "MelGeneralizedCepstralAnalysis"]
 FUNCTIONS = ["acorr", "dct", "fbank", "fftr", "frame", "freqt", "levdur", "lpc", "mcep", "mfcc", "spec", "stft",
              "window", "ifftr", "unframe", "istft", "fftcep", "delta", "b2mc", "mc2b", "gnorm", "ignorm", "lpc2par",
              "par2lpc", "norm0", "mgc2mgc", "mgc2sp", "plp"]
@@ -44,7 +45,7 @@ def snapshot(pkg):
     for c in CLASSES:
         cls = getattr(pkg, c)
         snap["classes"][c] = {"init": describe(cls.__init__), "name": cls.__name__,
-                              "takes_input_size": bool(cls._takes_input_size),
+                              "takes_input_size": bool(getattr(cls, "_takes_input_size", False)),
                               "forward": describe(cls.forward)}
     for f in FUNCTIONS:
         snap["functions"][f] = describe(getattr(pkg.functional, f))

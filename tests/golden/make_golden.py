@@ -317,6 +317,18 @@ def cases():
     yield ("plp_512_m12", "plp", dict(plp_order=12, n_channel=40, sample_rate=16000), [Pw])
     yield ("plp_512_bark", "plp", dict(plp_order=8, n_channel=20, sample_rate=16000, f_min=100, f_max=7000,
                                         scale="bark", lifter=22, out_format="ycE"), [Pw])
+    # ---- mgcep, section 8(f) rank 3 (tests/test_mgcep.py:23-48); MODULE-ONLY in the reference: no functional ----
+    P17g = np.abs(np.fft.rfft(rm.standard_normal((2, 3, 32)), axis=-1)) ** 2 + 1e-6
+    for it in (0, 3):
+        for gm in (0, -0.5, -1):
+            tag = f"g{gm}_i{it}".replace("-", "m").replace(".", "")
+            yield (f"mgcep_32_{tag}", "mgcep", dict(fft_length=32, cep_order=8, alpha=0.1, gamma=gm, n_iter=it),
+                   [P17g])
+    yield ("mgcep_512_m24", "mgcep", dict(fft_length=512, cep_order=24, alpha=0.42, gamma=-0.5, n_iter=5), [Pw[:, :8]])
+    yield ("mgcep_512_c3", "mgcep", dict(fft_length=512, cep_order=12, alpha=0.42, gamma=0, c=3, n_iter=2), [Pw[:, :8]])
+
+
+MODULE_ONLY = {"mgcep": "MelGeneralizedCepstralAnalysis"}   # ops the reference exposes as nn.Module only
 
 
 def main():
@@ -336,7 +348,10 @@ def main():
             cast = lambda v: v.astype(cdt if np.iscomplexobj(v) else ndt)  # noqa: E731
             tin = [None if v is None else torch.from_numpy(np.ascontiguousarray(cast(v))) for v in inputs]
             with torch.no_grad():
-                out = getattr(F, op)(*tin, **params)
+                if op in MODULE_ONLY:
+                    out = getattr(D, MODULE_ONLY[op])(**params, dtype=tdt)(*tin)
+                else:
+                    out = getattr(F, op)(*tin, **params)
             outs = out if isinstance(out, tuple) else (out,)
             for i, v in enumerate(inputs):
                 if v is not None:

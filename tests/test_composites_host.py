@@ -39,6 +39,13 @@ def _levdur(r, eps):
     return torch.cat((K, a), dim=-1)
 
 
+def _thsolve(t, h, r):
+    M = t.shape[-1]
+    i = torch.arange(M)
+    A = t[..., (i[:, None] - i[None, :]).abs()] + h[..., i[:, None] + i[None, :]]
+    return torch.linalg.solve(A, r.unsqueeze(-1)).squeeze(-1)
+
+
 @pytest.fixture()
 def host_ops(monkeypatch):
     from diffsptk_b200 import ops
@@ -48,6 +55,7 @@ def host_ops(monkeypatch):
     monkeypatch.setattr(ops, "rowconv", lambda x, op, g: ops.rowconv_composite(x, op, g))
     monkeypatch.setattr(ops, "fbank", _fbank)
     monkeypatch.setattr(ops, "levdur", _levdur)
+    monkeypatch.setattr(ops, "thsolve", _thsolve)
     return ops
 
 
@@ -77,3 +85,18 @@ def test_module_host_logic_matches_reference(host_ops, name):
         mod = B.PLP(fft_length=2 * n - 2, **p, dtype=torch.float64)
     got = mod(torch.from_numpy(np.ascontiguousarray(ins[0])))
     H.assert_close(got.numpy(), outs[0], "f64", what=name, scale_atol=True)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", [n for n in H.case_names(["mgcep"]) if H.load_case(n, "f64")[1].get("gamma") != 0
+                                  or H.load_case(n, "f64")[1].get("c")])
+def test_mgcep_host_logic_matches_reference(host_ops, name, prec):
+    """gamma != 0 only: gamma = 0 is the fused mcep kernel, which has no stand-in."""
+    import diffsptk_b200 as B
+    op, params, ins, outs = H.load_case(name, prec)
+    mod = B.MelGeneralizedCepstralAnalysis(**params, dtype=torch.float64 if prec == "f64" else torch.float32)
+    got = mod(torch.from_numpy(np.ascontiguousarray(ins[0])))
+    if prec == "f32":
+        H.assert_close_conditioned(got.numpy(), outs[0], H.load_case(name, "f64")[3][0], what=f"{name}[f32]")
+    else:
+        H.assert_close(got.numpy(), outs[0], prec, what=f"{name}[{prec}]", scale_atol=True)

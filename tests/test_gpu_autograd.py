@@ -536,3 +536,28 @@ def test_converter_gradients():
                 e[:, j] = h
                 num[:, j] = ((fn(x0 + e) - fn(x0 - e)) * w).sum(-1) / (2 * h)
         assert torch.allclose(gx, num, rtol=1e-5, atol=1e-6), name
+
+
+def test_thsolve_matches_a_dense_solve_and_its_gradients():
+    """dsb200_thsolve against torch.linalg.solve of the explicit Toeplitz + Hankel matrix (float64), forward and
+    the three gradients (the backward reuses the kernel: the matrix is symmetric)."""
+    from diffsptk_b200 import ops
+    d = dev()
+    g = torch.Generator().manual_seed(11)
+    for M in (1, 2, 8, 24, 40):
+        i = torch.arange(M)
+        t0 = torch.randn(5, M, generator=g, dtype=torch.float64) * 0.1
+        t0[:, 0] = 3.0 + torch.rand(5, generator=g, dtype=torch.float64)          # diagonally dominant: well posed
+        h0 = torch.randn(5, 2 * M - 1, generator=g, dtype=torch.float64) * 0.1
+        r0 = torch.randn(5, M, generator=g, dtype=torch.float64)
+        w = torch.randn(5, M, generator=g, dtype=torch.float64).to(d)
+        t, h, r = (v.to(d).requires_grad_(True) for v in (t0, h0, r0))
+        x = ops.thsolve(t, h, r)
+        gt, gh, gr = torch.autograd.grad((x * w).sum(), (t, h, r))
+        t2, h2, r2 = (v.to(d).requires_grad_(True) for v in (t0, h0, r0))
+        A = t2[..., (i[:, None] - i[None, :]).abs().to(d)] + h2[..., (i[:, None] + i[None, :]).to(d)]
+        x2 = torch.linalg.solve(A, r2.unsqueeze(-1)).squeeze(-1)
+        rt, rh, rr = torch.autograd.grad((x2 * w).sum(), (t2, h2, r2))
+        assert torch.allclose(x, x2, rtol=1e-9, atol=1e-11), M
+        for a, b, what in ((gt, rt, "t"), (gh, rh, "h"), (gr, rr, "r")):
+            assert torch.allclose(a, b, rtol=1e-8, atol=1e-10), (M, what)
