@@ -78,7 +78,6 @@ class MelCepstralAnalysis(BaseFunctionalModule):
     def _forward(x: torch.Tensor, *, fft_length: int, n_iter: int, alpha_vector: torch.Tensor,
                  P0: torch.Tensor, G: torch.Tensor, Hm: torch.Tensor, freqt=None, ifreqt=None,
                  rfreqt=None) -> torch.Tensor:
-        ops._no_grad_check(x)
         return ops.mcep(x, P0, G, Hm, alpha_vector, n_iter)
 
 

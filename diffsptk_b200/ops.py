@@ -59,10 +59,9 @@ def _dev(t: Tensor) -> int:
 def _no_grad_check(*ts):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
         raise NotImplementedError(
-            "this diffsptk_b200 op is forward-only for that input (differentiable: frame / window / fftr / spec / "
-            "stft / freqt / dct / acorr / levdur / lpc / fbank / mfcc, including learnable analysis windows and filter banks, and ifftr / unframe / istft; not "
-            "mcep, learnable synthesis windows, or a learnable DFT basis): wrap the call in torch.no_grad() or "
-            "detach() the inputs."
+            "this diffsptk_b200 op is forward-only for that input (differentiable: every op with respect to its signal "
+            "input, learnable analysis windows and filter banks included; not the Spectrum denominator, learnable "
+            "synthesis windows, or a learnable DFT basis): wrap the call in torch.no_grad() or detach() the inputs."
         )
 
 
@@ -1183,3 +1182,46 @@ def _thsolve_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{_NS}::thsolve", _thsolve_bwd, setup_context=_thsolve_setup)
+
+
+# ------------------------------------------------------------------ mcep gradients (recompute + autograd)
+def mcep_composite(x: Tensor, P0: Tensor, G: Tensor, Hm: Tensor, alpha_vector: Tensor, n_iter: int) -> Tensor:
+    """The Newton iteration of the fused mcep kernels, step by step on DIFFERENTIABLE kernels of this package
+    (``rowmat`` with the folded tables, ``thsolve``) and device-side elementwise ops -- used by the backward of
+    ``mcep`` only (the forward is one fused kernel that keeps nothing for autograd)."""
+    D = alpha_vector.shape[-1]
+    lx = torch.log(x)
+    mc = rowmat(lx, P0)
+    for _ in range(n_iter):
+        e = torch.exp(lx - 2 * rowmat(mc, G))
+        rt = rowmat(e, Hm)
+        mc = mc + thsolve(rt[..., :D], rt, rt[..., :D] - alpha_vector)
+    return mc
+
+
+def _mcep_setup(ctx, inputs, output):
+    x, P0, G, Hm, alpha_vector, n_iter = inputs
+    ctx.save_for_backward(x, P0, G, Hm, alpha_vector)
+    ctx.n_iter = n_iter
+
+
+def _mcep_bwd(ctx, g):
+    x, P0, G, Hm, av = ctx.saved_tensors
+    if any(ctx.needs_input_grad[1:5]):
+        raise NotImplementedError("gradients with respect to the mel-cepstral analysis tables are not implemented")
+    dt = _native_dtype(x, av)
+    K = x.shape[-1]
+    xf = x.detach().to(dt).reshape(-1, K)
+    gf = g.to(dt).reshape(-1, g.shape[-1])
+    tabs = [t.detach().to(dt) for t in (P0, G, Hm, av)]
+    out = torch.empty_like(xf)
+    chunk = 32768   # rows per recompute: bounds the autograd tape (~ n_iter * 350 floats per row)
+    for lo in range(0, xf.shape[0], chunk):
+        with torch.enable_grad():
+            xd = xf[lo:lo + chunk].clone().requires_grad_(True)
+            y = mcep_composite(xd, *tabs, ctx.n_iter)
+            (out[lo:lo + chunk],) = torch.autograd.grad(y, xd, gf[lo:lo + chunk])
+    return _like_input(out, x), None, None, None, None, None
+
+
+torch.library.register_autograd(f"{_NS}::mcep", _mcep_bwd, setup_context=_mcep_setup)

@@ -561,3 +561,33 @@ def test_thsolve_matches_a_dense_solve_and_its_gradients():
         assert torch.allclose(x, x2, rtol=1e-9, atol=1e-11), M
         for a, b, what in ((gt, rt, "t"), (gh, rh, "h"), (gr, rr, "r")):
             assert torch.allclose(a, b, rtol=1e-8, atol=1e-10), (M, what)
+
+
+def test_mcep_gradients():
+    """mcep backward = recompute of the Newton iteration on differentiable kernels (rowmat, thsolve) + autograd:
+    checked against central differences of the fused forward kernel itself (float64)."""
+    import diffsptk_b200.functional as F
+    d = dev()
+    g = torch.Generator().manual_seed(23)
+    for K, M, alpha, n_iter in ((17, 4, 0.1, 2), (17, 4, 0.3, 0), (257, 24, 0.42, 3)):
+        base = torch.randn(3, 2 * (K - 1), generator=g, dtype=torch.float64)
+        x0 = (torch.fft.rfft(base).abs().square() + 0.5).to(d)
+        w = torch.randn(3, M + 1, generator=g, dtype=torch.float64).to(d)
+        x = x0.clone().requires_grad_(True)
+        (gx,) = torch.autograd.grad((F.mcep(x, M, alpha, n_iter) * w).sum(), x)
+        cols = torch.randperm(K, generator=g)[:12].tolist()
+        with torch.no_grad():
+            for j in cols:
+                h = 1e-6 * float(x0[:, j].abs().max())
+                e = torch.zeros_like(x0)
+                e[:, j] = h
+                num = ((F.mcep(x0 + e, M, alpha, n_iter) - F.mcep(x0 - e, M, alpha, n_iter)) * w).sum(-1) / (2 * h)
+                assert torch.allclose(gx[:, j], num, rtol=2e-4, atol=1e-7), (K, M, n_iter, j)
+    # float32 and the module path run, and mgcep with gamma = 0 (which is this kernel) is differentiable too
+    import diffsptk_b200 as B
+    xs = (torch.rand(5, 257, generator=g) + 0.1).to(d).requires_grad_(True)
+    B.MelCepstralAnalysis(fft_length=512, cep_order=24, alpha=0.42, n_iter=2).to(d)(xs).sum().backward()
+    assert torch.isfinite(xs.grad).all() and float(xs.grad.abs().max()) > 0
+    xs.grad = None
+    B.MelGeneralizedCepstralAnalysis(fft_length=512, cep_order=12, alpha=0.42, gamma=-0.5, n_iter=2).to(d)(xs).sum().backward()
+    assert torch.isfinite(xs.grad).all() and float(xs.grad.abs().max()) > 0

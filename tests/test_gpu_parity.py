@@ -285,8 +285,8 @@ def test_edge_cases():
         F.stft(torch.randn(100, device=d), fft_length=511)
     with pytest.raises((ValueError, RuntimeError)):
         F.frame(torch.randn(2, 100, device=d), mode="reflect")  # pad 200 >= T (torch raises here too)
-    with pytest.raises(NotImplementedError):  # the Newton solver is forward-only and must say so
-        F.mcep(torch.rand(4, 257, device=d, requires_grad=True) + 0.1, 24, 0.42, 2)
+    with pytest.raises(NotImplementedError):  # what is forward-only must say so: the Spectrum denominator
+        F.spec(torch.randn(4, 8, device=d), torch.rand(4, 3, device=d, requires_grad=True) + 0.5, fft_length=16)
     # a side stream is honoured
     s = torch.cuda.Stream(device=d)
     xs = torch.randn(4, 8000, device=d)
