@@ -125,6 +125,12 @@ def ignorm(y: Tensor, gamma: float = 0, c: int | None = None) -> Tensor:
     return nn.GeneralizedCepstrumInverseGainNormalization._func(y, gamma=gamma, c=c)
 
 
+def lpc2lsp(a: Tensor, log_gain: bool = False, sample_rate: int | None = None, out_format: str = "radian") -> Tensor:
+    """LPC to line spectral pairs ``(..., M+1) -> (..., M+1)``."""
+    return nn.LinearPredictiveCoefficientsToLineSpectralPairs._func(a, log_gain=log_gain, sample_rate=sample_rate,
+                                                                    out_format=out_format)
+
+
 def lpc2par(a: Tensor, gamma: float = 1, c: int | None = None) -> Tensor:
     """LPC to PARCOR coefficients ``(..., M+1) -> (..., M+1)``."""
     return nn.LinearPredictiveCoefficientsToParcorCoefficients._func(a, gamma=gamma, c=c)

@@ -20,6 +20,7 @@ from .ignorm import GeneralizedCepstrumInverseGainNormalization
 from .levdur import LevinsonDurbin
 from .lpc import LinearPredictiveCodingAnalysis
 from .lpc import LinearPredictiveCodingAnalysis as LPC
+from .lpc2lsp import LinearPredictiveCoefficientsToLineSpectralPairs
 from .lpc2par import LinearPredictiveCoefficientsToParcorCoefficients
 from .mc2b import MelCepstrumToMLSADigitalFilterCoefficients
 from .mcep import MelCepstralAnalysis
@@ -49,5 +50,5 @@ __all__ = [
     "LinearPredictiveCoefficientsToParcorCoefficients", "ParcorCoefficientsToLinearPredictiveCoefficients",
     "AllPoleToAllZeroDigitalFilterCoefficients", "MelGeneralizedCepstrumToMelGeneralizedCepstrum",
     "MelGeneralizedCepstrumToSpectrum", "PerceptualLinearPredictiveCoefficientsAnalysis", "PLP",
-    "MelGeneralizedCepstralAnalysis",
+    "MelGeneralizedCepstralAnalysis", "LinearPredictiveCoefficientsToLineSpectralPairs",
 ]

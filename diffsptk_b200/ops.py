@@ -1225,3 +1225,56 @@ def _mcep_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{_NS}::mcep", _mcep_bwd, setup_context=_mcep_setup)
+
+
+# ------------------------------------------------------------------ lpc2lsp (section 8f rank 4)
+@torch.library.custom_op(f"{_NS}::lpc2lsp", mutates_args=(), device_types="cuda")
+def lpc2lsp(a: Tensor, log_gain: bool, scale: float) -> Tensor:
+    """``[K, a_1..a_M] -> [K or log K, scale * w_1..w_M]`` (ascending line spectral frequencies)."""
+    dt = _native_dtype(a)
+    ac = _prep(a, dt)
+    D = ac.shape[-1]
+    rows = ac.numel() // max(D, 1)
+    w = torch.empty_like(ac)
+    N.check(N.typed("dsb200_lpc2lsp", dt == torch.float64)(_ptr(ac), _ptr(w), rows, D - 1, int(log_gain), float(scale),
+                                                           _dev(a), _stream(a)))
+    return w
+
+
+@lpc2lsp.register_fake
+def _(a, log_gain, scale):
+    return a.new_empty(a.shape, dtype=_native_dtype(a))
+
+
+def _lpc2lsp_setup(ctx, inputs, output):
+    a, log_gain, scale = inputs
+    ctx.save_for_backward(a, output)
+    ctx.log_gain, ctx.scale = log_gain, scale
+
+
+def _lpc2lsp_bwd(ctx, g):
+    # Implicit differentiation.  With h = (M + 1) / 2 and a_0 = 1 the zeros of Q are the zeros of
+    # R(w) = sum_k a_k cos((h - k) w) and the zeros of P those of I(w) = sum_k a_k sin((h - k) w)
+    # (e^{j h w} A(e^{jw}) = R + j I):  dw/da_k = -cos((h - k) w) / R'(w)  resp.  -sin((h - k) w) / I'(w).
+    a, out = ctx.saved_tensors
+    dt = out.dtype
+    M = a.shape[-1] - 1
+    K = a[..., :1].to(dt)
+    gK = g[..., :1].to(dt) / K if ctx.log_gain else g[..., :1].to(dt)
+    if M == 0:
+        return _like_input(gK, a), None, None
+    w = (out[..., 1:] / ctx.scale).unsqueeze(-1)                       # (..., M, 1) radians
+    k = torch.arange(M + 1, device=a.device, dtype=dt)
+    hk = (M + 1) / 2 - k                                               # (M + 1,)
+    coef = torch.cat((torch.ones_like(K), a[..., 1:].to(dt)), dim=-1).unsqueeze(-2)   # (..., 1, M + 1)
+    c, s = torch.cos(hk * w), torch.sin(hk * w)                        # (..., M, M + 1)
+    R, I = (coef * c).sum(-1), (coef * s).sum(-1)                      # (..., M)
+    is_q = R.abs() < I.abs()
+    num = torch.where(is_q.unsqueeze(-1), c, s)
+    den = torch.where(is_q, -(coef * hk * s).sum(-1), (coef * hk * c).sum(-1))
+    dw_da = -num / den.unsqueeze(-1)                                   # (..., M zeros, M + 1 coefficients)
+    ga = (g[..., 1:].to(dt).unsqueeze(-1) * ctx.scale * dw_da).sum(-2)[..., 1:]
+    return _like_input(torch.cat((gK, ga), dim=-1), a), None, None
+
+
+torch.library.register_autograd(f"{_NS}::lpc2lsp", _lpc2lsp_bwd, setup_context=_lpc2lsp_setup)

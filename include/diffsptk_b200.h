@@ -264,6 +264,13 @@ DSB200_DECL2(dsb200_delta_backward, (const void* gy, const void* window, void* g
 DSB200_DECL2(dsb200_rowconv, (const void* x, void* y, int64_t rows, int32_t dim, int32_t op, double param,
                               int device, void* stream))
 
+/* LinearPredictiveCoefficientsToLineSpectralPairs._forward, diffsptk/modules/lpc2lsp.py:159-197:
+ * a[rows, lpc_order + 1] = [K, a_1..a_M] -> w[rows, lpc_order + 1] = [K or log K, scale * w_1..w_M], the line
+ * spectral frequencies in ascending order (radians times `scale`: 1, 1/2pi, sr/2000pi, sr/2pi for the reference's
+ * out_format radian / cycle / khz / hz).  Zeros that cannot be isolated (a double zero) are returned as NaN. */
+DSB200_DECL2(dsb200_lpc2lsp, (const void* a, void* w, int64_t rows, int32_t lpc_order, int32_t log_gain,
+                              double scale, int device, void* stream))
+
 /* Per-row solve of (Toeplitz(t) + Hankel(h)) x = r: t[rows, order], h[rows, 2 * order - 1], r[rows, order] ->
  * x[rows, order].  The Newton step of MelGeneralizedCepstralAnalysis, diffsptk/modules/mgcep.py:219-222
  * (symmetric_toeplitz / hankel, diffsptk/utils/private.py:291-302, then torch.linalg.solve). */

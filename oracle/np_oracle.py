@@ -1054,3 +1054,50 @@ def mgcep(x, *, fft_length, cep_order, alpha=0, gamma=0, c=None, n_iter=0):
         for _ in range(n_iter):
             b0, b1 = newton(gamma, b1)
     return b2mc(ignorm(np.concatenate([b0, b1], axis=-1), gamma), alpha)
+
+
+# ----------------------------------------------------------------------------- lpc2lsp (8f rank 4)
+def lpc2lsp(a, log_gain=False, sample_rate=None, out_format="radian"):
+    """LPC -> line spectral pairs: the roots of the deflated symmetric / antisymmetric polynomials, found as the
+    eigenvalues of the companion matrix like the reference (diffsptk/modules/lpc2lsp.py:159-197,
+    root_pol.py:130-146); the positive-angle member of every conjugate pair is kept (the reference takes every
+    other eigenvalue, which LAPACK returns pair by pair)."""
+    a = _as_float(a)
+    M = a.shape[-1] - 1
+    if out_format in (2, 3, "hz", "khz") and (sample_rate is None or sample_rate <= 0):
+        raise ValueError("sample_rate must be positive.")
+    tau = 2 * math.pi
+    if out_format in (0, "radian"):
+        scale = 1.0
+    elif out_format in (1, "cycle"):
+        scale = 1 / tau
+    elif out_format in (2, "khz"):
+        scale = 1 / (tau / sample_rate * 1000)
+    elif out_format in (3, "hz"):
+        scale = 1 / (tau / sample_rate)
+    else:
+        raise ValueError(f"out_format {out_format} is not supported.")
+    K = a[..., :1]
+    if log_gain:
+        K = np.log(K)
+    if M == 0:
+        return K
+    flat = a.reshape(-1, M + 1).astype(np.float64)
+    out = np.empty((flat.shape[0], M))
+    for n, row in enumerate(flat):
+        a1 = np.concatenate([[1.0], row[1:], [0.0]])
+        a2 = a1[::-1]
+        p, q = a1 - a2, a1 + a2
+        if M == 1:
+            r = np.roots(q)
+            out[n] = np.abs(np.angle(r[:1]))
+            continue
+        if M % 2 == 0:
+            p = np.polydiv(p, [1.0, -1.0])[0]
+            q = np.polydiv(q, [1.0, 1.0])[0]
+        else:
+            p = np.polydiv(p, [1.0, 0.0, -1.0])[0]
+        ang = np.concatenate([np.angle(np.roots(p)), np.angle(np.roots(q))])
+        out[n] = np.sort(ang[ang > 0])
+    w = (out * scale).astype(a.dtype).reshape(*a.shape[:-1], M)
+    return np.concatenate([K, w], axis=-1)

@@ -1,7 +1,7 @@
 """Snapshot the reference's public signatures for the hot path (run in the build container).
 
 Writes ``tests/golden/api_signatures.json``: constructor / functional parameter names, kinds and
-defaults of the 36 exported classes (incl. aliases) and 28 functional delegates, plus the
+defaults of the 37 exported classes (incl. aliases) and 29 functional delegates, plus the
 ``_takes_input_size`` flags -- the drop-in contract of SURVEY.md section 8(b).
 """
 
@@ -24,10 +24,10 @@ CLASSES = ["Autocorrelation", "DiscreteCosineTransform", "DCT", "MelFilterBankAn
            "LinearPredictiveCoefficientsToParcorCoefficients", "ParcorCoefficientsToLinearPredictiveCoefficients",
            "AllPoleToAllZeroDigitalFilterCoefficients", "MelGeneralizedCepstrumToMelGeneralizedCepstrum",
            "MelGeneralizedCepstrumToSpectrum", "PerceptualLinearPredictiveCoefficientsAnalysis", "PLP",
-           "MelGeneralizedCepstralAnalysis"]
+           "MelGeneralizedCepstralAnalysis", "LinearPredictiveCoefficientsToLineSpectralPairs"]
 FUNCTIONS = ["acorr", "dct", "fbank", "fftr", "frame", "freqt", "levdur", "lpc", "mcep", "mfcc", "spec", "stft",
              "window", "ifftr", "unframe", "istft", "fftcep", "delta", "b2mc", "mc2b", "gnorm", "ignorm", "lpc2par",
-             "par2lpc", "norm0", "mgc2mgc", "mgc2sp", "plp"]
+             "par2lpc", "norm0", "mgc2mgc", "mgc2sp", "plp", "lpc2lsp"]
 
 
 def describe(fn):

@@ -326,6 +326,27 @@ def cases():
                    [P17g])
     yield ("mgcep_512_m24", "mgcep", dict(fft_length=512, cep_order=24, alpha=0.42, gamma=-0.5, n_iter=5), [Pw[:, :8]])
     yield ("mgcep_512_c3", "mgcep", dict(fft_length=512, cep_order=12, alpha=0.42, gamma=0, c=3, n_iter=2), [Pw[:, :8]])
+    # ---- lpc2lsp, section 8(f) rank 4 (tests/test_lpc2lsp.py:23-55): LPC rows obtained from windowed noise and
+    #      from the speech-like signal by the oracle-independent normal equations below --------------------------------
+    def lpc_of(frames, M):
+        L = frames.shape[-1]
+        r = np.stack([(frames[..., : L - k] * frames[..., k:]).sum(-1) for k in range(M + 1)], axis=-1)
+        if M == 0:
+            return np.sqrt(r)
+        idx = np.abs(np.arange(M)[:, None] - np.arange(M)[None, :])
+        a = np.linalg.solve(r[..., :-1][..., idx] + 1e-9 * np.eye(M), -r[..., 1:, None])[..., 0]
+        return np.concatenate([np.sqrt(r[..., :1] + (r[..., 1:] * a).sum(-1, keepdims=True)), a], axis=-1)
+    noise = rm.standard_normal((2, 6, 32))
+    for M in (0, 1, 7, 8):
+        for fmt in (0, 1, 2, 3):
+            yield (f"lpc2lsp_m{M}_o{fmt}", "lpc2lsp", dict(log_gain=True, sample_rate=8000, out_format=fmt),
+                   [lpc_of(noise, M)])
+    sp = speechlike(16000)
+    spf = np.lib.stride_tricks.sliding_window_view(sp, 400)[4000:12000:80] * np.hanning(400)
+    spf = spf[np.abs(spf).max(-1) > 1e-4]
+    yield ("lpc2lsp_speech_m24", "lpc2lsp", dict(), [lpc_of(spf, 24)])
+    yield ("lpc2lsp_speech_m12", "lpc2lsp", dict(log_gain=True, sample_rate=16000, out_format="khz"), [lpc_of(spf, 12)])
+    yield ("lpc2lsp_noise_m24", "lpc2lsp", dict(), [lpc_of(rm.standard_normal((50, 400)) * np.hanning(400), 24)])
 
 
 MODULE_ONLY = {"mgcep": "MelGeneralizedCepstralAnalysis"}   # ops the reference exposes as nn.Module only

@@ -232,3 +232,56 @@ def stft512_staged_store_banks(d):
                     banks.append(addr % 32)
             rows.append(banks)
     return rows
+
+
+# lsp.cu: the numerical steps of lpc2lsp_kernel for one row (deflation, Chebyshev series, grid + bisection in x).
+def lsp_model(row, G=None):
+    row = np.asarray(row, dtype=np.float64)
+    M = row.size - 1
+    if M == 0:
+        return np.zeros(0)
+    if G is None:
+        G = min(2048, max(256, 32 * M))
+    a1 = np.concatenate([[1.0], row[1:], [0.0]])
+    p, q = a1 - a1[::-1], a1 + a1[::-1]
+    if M % 2 == 0:
+        nP = nQ = M // 2
+        for i in range(1, M + 1):
+            p[i] += p[i - 1]
+            q[i] -= q[i - 1]
+    else:
+        nP, nQ = (M - 1) // 2, (M + 1) // 2
+        for i in range(2, M):
+            p[i] += p[i - 2]
+
+    def cheb(g, n, x):
+        b1 = b2 = 0.0
+        for k in range(n, 0, -1):
+            b1, b2 = 2.0 * x * b1 + (g[k] - b2), b1
+        return x * b1 + (g[0] - b2)
+
+    out = []
+    for c, n in ((p, nP), (q, nQ)):
+        if n == 0:
+            continue
+        g = np.array([(1.0 if k == 0 else 2.0) * c[n - k] for k in range(n + 1)])
+        brackets = []
+        for fine in (1, 16):
+            Gn = G * fine
+            xs = np.cos(np.pi * np.arange(Gn + 1) / Gn)
+            fs = np.array([cheb(g, n, x) for x in xs])
+            idx = np.nonzero((fs[:-1] < 0) != (fs[1:] < 0))[0]
+            brackets = [(xs[i], xs[i + 1]) for i in idx]
+            if len(brackets) == n:
+                break
+        for xa, xb in brackets[:n]:
+            neg_a = cheb(g, n, xa) < 0
+            for _ in range(54):
+                xm = 0.5 * (xa + xb)
+                if (cheb(g, n, xm) < 0) == neg_a:
+                    xa = xm
+                else:
+                    xb = xm
+            out.append(np.arccos(0.5 * (xa + xb)))
+        out += [np.nan] * (n - min(n, len(brackets)))
+    return np.sort(np.array(out))

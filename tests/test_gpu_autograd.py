@@ -591,3 +591,26 @@ def test_mcep_gradients():
     xs.grad = None
     B.MelGeneralizedCepstralAnalysis(fft_length=512, cep_order=12, alpha=0.42, gamma=-0.5, n_iter=2).to(d)(xs).sum().backward()
     assert torch.isfinite(xs.grad).all() and float(xs.grad.abs().max()) > 0
+
+
+def test_lpc2lsp_gradients():
+    """Implicit-differentiation backward of lpc2lsp against central differences of the kernel (float64)."""
+    import diffsptk_b200.functional as F
+    d = dev()
+    g = torch.Generator().manual_seed(31)
+    for M, kw in ((1, {}), (7, dict(log_gain=True, sample_rate=8000, out_format="khz")), (8, {}), (16, dict(out_format="cycle"))):
+        k = torch.empty(4, M + 1, dtype=torch.float64).uniform_(-0.7, 0.7, generator=g)
+        k[:, 0] = torch.empty(4, dtype=torch.float64).uniform_(0.5, 2.0, generator=g)
+        with torch.no_grad():
+            a0 = F.par2lpc(k.to(d))        # a stable filter
+        w = torch.randn(4, M + 1, generator=g, dtype=torch.float64).to(d)
+        a = a0.clone().requires_grad_(True)
+        (ga,) = torch.autograd.grad((F.lpc2lsp(a, **kw) * w).sum(), a)
+        num = torch.zeros_like(a0)
+        h = 1e-6
+        with torch.no_grad():
+            for j in range(M + 1):
+                e = torch.zeros_like(a0)
+                e[:, j] = h
+                num[:, j] = ((F.lpc2lsp(a0 + e, **kw) - F.lpc2lsp(a0 - e, **kw)) * w).sum(-1) / (2 * h)
+        assert torch.allclose(ga, num, rtol=1e-5, atol=1e-6), (M, (ga - num).abs().max())

@@ -45,8 +45,8 @@ def check_outputs(name, op, params, prec, got, outs):
         if op == "frame" and not params.get("zmean"):
             assert np.array_equal(g, w, equal_nan=True), f"{name}: frame must be bit-exact"
             continue
-        if prec == "f32" and op in ("lpc2par", "par2lpc"):
-            # step-down / step-up recursions: on ill-conditioned rows the float32 rounding of the INPUT alone moves
+        if prec == "f32" and op in ("lpc2par", "par2lpc", "lpc2lsp"):
+            # step-down / step-up recursions and polynomial zeros: on ill-conditioned rows the float32 rounding of the INPUT alone moves
             # the result more than any implementation difference, so the yardstick is exact (float64 oracle)
             # arithmetic on the same float32 inputs, with the reference's own float32 error as the allowance
             exact = H.run_oracle(op, params, [a.astype(np.float64) for a in H.load_case(name, "f32")[2]])
@@ -132,6 +132,8 @@ def build_module(op, params, ins, prec):
         return B.PLP(fft_length=2 * n - 2, **p, device=d, dtype=dt)
     if op == "mgcep":
         return B.MelGeneralizedCepstralAnalysis(**p, device=d, dtype=dt)
+    if op == "lpc2lsp":
+        return B.LinearPredictiveCoefficientsToLineSpectralPairs(n - 1, **p, device=d, dtype=dt)
     if op == "b2mc":
         return B.MLSADigitalFilterCoefficientsToMelCepstrum(n - 1, **p, device=d, dtype=dt)
     if op == "ifftr":

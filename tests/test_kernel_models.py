@@ -72,3 +72,16 @@ def test_stft512_staged_stores_are_bank_conflict_free():
     for d in (1, 2):
         for banks in KM.stft512_staged_store_banks(d):
             assert len(set(banks)) == 32, (d, sorted(banks))
+
+
+def test_lsp_model_matches_reference():
+    """The numerical recipe of lsp.cu (unit-circle zeros by Chebyshev series + bisection) against the reference's
+    companion-matrix eigenvalues (golden vectors, float64)."""
+    import helpers as H
+    for name in ("lpc2lsp_m1_o0", "lpc2lsp_m7_o0", "lpc2lsp_m8_o0", "lpc2lsp_speech_m24", "lpc2lsp_noise_m24"):
+        op, params, ins, outs = H.load_case(name, "f64")
+        a = ins[0].reshape(-1, ins[0].shape[-1])
+        want = outs[0].reshape(-1, outs[0].shape[-1])
+        for r in range(0, a.shape[0], max(1, a.shape[0] // 12)):
+            got = KM.lsp_model(a[r])
+            assert np.allclose(got, want[r, 1:], rtol=1e-9, atol=1e-11), (name, r, np.abs(got - want[r, 1:]).max())
