@@ -40,6 +40,8 @@ WORKLOADS = {
               52, 156),
     "lpc2par": ("LPC -> PARCOR (step-down recursion, M=24) on the LPC rows of config 3: 1024 utt x 5 s", 1024, 80000,
                 100, 100),
+    "lpc2lsp": ("LPC -> line spectral pairs (M=24) on the LPC rows of config 3: 1024 utt x 5 s", 1024, 80000,
+                100, 100),
     "istft": ("Inverse STFT (ifftr -> window -> overlap-add, one kernel): 256 utt x 10 s of complex spectra", 256,
               160000, 2056, 320),
 }
@@ -139,6 +141,8 @@ def _cpu_task(args):
         y = O.delta(x, [2, 2], True)
     elif workload == "lpc2par":  # x holds LPC rows
         y = O.lpc2par(x)
+    elif workload == "lpc2lsp":
+        y = O.lpc2lsp(x)
     elif workload == "stft_grad":  # the oracle has no autograd: forward only (a lower bound on the CPU cost)
         y = O.stft(x)
     else:  # mcep: x holds power spectra
@@ -164,8 +168,10 @@ def cpu_oracle_throughput(workload, utterances, T, steps, warmup, budget_s=25.0)
         _CPU_X = O.stft(rng.standard_normal((utterances, T)).astype(np.float32), out_format="complex")
     elif workload == "delta":
         _CPU_X = rng.standard_normal((utterances, n_frames(T), 13)).astype(np.float32)
-    elif workload == "lpc2par":
+    elif workload in ("lpc2par", "lpc2lsp"):
         from oracle import np_oracle as O
+        if workload == "lpc2lsp":
+            utterances = min(utterances, max(1, cores // 8))   # an eigenvalue problem per row: keep a step to seconds
         k = rng.uniform(-0.9, 0.9, (utterances, n_frames(T), 25)).astype(np.float32)
         _CPU_X = O.par2lpc(k)
     else:
@@ -227,11 +233,14 @@ def make_step(workload, B, T, dev):
         dl = D.Delta([2, 2], True).to(dev)
         xs = [torch.randn(B, n_frames(T), 13, generator=g, device=dev) for _ in range(2)]
         return xs, lambda i: dl(xs[i & 1])
-    if workload == "lpc2par":
+    if workload in ("lpc2par", "lpc2lsp"):
         with torch.no_grad():   # stable LPC rows: step-up recursion from random PARCOR coefficients
             xs = [F.par2lpc(torch.empty(B, n_frames(T), 25, device=dev).uniform_(-0.9, 0.9, generator=g))
                   for _ in range(2)]
-        return xs, lambda i: F.lpc2par(xs[i & 1])
+            for x in xs:
+                x[..., 0].abs_().add_(0.1)   # positive gain
+        fn = F.lpc2par if workload == "lpc2par" else F.lpc2lsp
+        return xs, lambda i: fn(xs[i & 1])
     if workload == "istft":
         stft = D.STFT(FL, FP, NFFT, out_format="complex").to(dev)
         istft = D.ISTFT(FL, FP, NFFT).to(dev)

@@ -1060,8 +1060,8 @@ def mgcep(x, *, fft_length, cep_order, alpha=0, gamma=0, c=None, n_iter=0):
 def lpc2lsp(a, log_gain=False, sample_rate=None, out_format="radian"):
     """LPC -> line spectral pairs: the roots of the deflated symmetric / antisymmetric polynomials, found as the
     eigenvalues of the companion matrix like the reference (diffsptk/modules/lpc2lsp.py:159-197,
-    root_pol.py:130-146); the positive-angle member of every conjugate pair is kept (the reference takes every
-    other eigenvalue, which LAPACK returns pair by pair)."""
+    root_pol.py:130-146); one member of every conjugate pair is kept (the reference takes every other eigenvalue,
+    which LAPACK returns pair by pair)."""
     a = _as_float(a)
     M = a.shape[-1] - 1
     if out_format in (2, 3, "hz", "khz") and (sample_rate is None or sample_rate <= 0):
@@ -1097,7 +1097,8 @@ def lpc2lsp(a, log_gain=False, sample_rate=None, out_format="radian"):
             q = np.polydiv(q, [1.0, 1.0])[0]
         else:
             p = np.polydiv(p, [1.0, 0.0, -1.0])[0]
-        ang = np.concatenate([np.angle(np.roots(p)), np.angle(np.roots(q))])
-        out[n] = np.sort(ang[ang > 0])
+        # conjugate pairs: one angle of each pair (sorted |angle| come in equal twos)
+        ang = [np.sort(np.abs(np.angle(np.roots(c))))[0::2] for c in (p, q)]
+        out[n] = np.sort(np.concatenate(ang))
     w = (out * scale).astype(a.dtype).reshape(*a.shape[:-1], M)
     return np.concatenate([K, w], axis=-1)
