@@ -7,7 +7,8 @@
 // a real function of one variable with n simple zeros in (0, pi).
 //
 // Mapping: ONE WARP per row, float64 throughout (the zeros of an order-24 polynomial are too ill-conditioned for
-// float32 evaluation).  The lanes evaluate the series on a grid of w (Clenshaw recurrence), mark the sign changes,
+// float32 evaluation).  The lanes evaluate the series on a grid of w (Clenshaw recurrence; the abscissae cos(w_i)
+// are a per-CTA table, one evaluation per grid point, signs exchanged by warp ballots), mark the sign changes,
 // then one lane per bracket bisects in x down to machine precision -- no data-dependent trip counts -- and
 // the M angles are rank-sorted into the output row.  A row whose brackets do not add up to n on the first grid is
 // searched again on a 16x finer one; zeros still missing after that (a double zero: an unstable or degenerate
@@ -36,7 +37,10 @@ __global__ void __launch_bounds__(256) lpc2lsp_kernel(const T* __restrict__ a, T
                                                       int log_gain, double scale, int G, int NC, int per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-  double* base = reinterpret_cast<double*>(smem_raw) + static_cast<size_t>(warp) * per_warp;
+  double* xg = reinterpret_cast<double*>(smem_raw);     // [G + 1] cos(pi i / G): the same grid for every row
+  for (int i = threadIdx.x; i <= G; i += blockDim.x) xg[i] = cospi(static_cast<double>(i) / G);
+  __syncthreads();
+  double* base = xg + (G + 2) + static_cast<size_t>(warp) * per_warp;
   double* pq = base;                 // [2][M + 2] p then q (raw, then deflated in place)
   double* gc = pq + 2 * (M + 2);     // [2][NC]    Chebyshev coefficients of the two deflated polynomials
   double* lo = gc + 2 * NC;          // [M]        bracket ends (x = cos w, descending in w) / refined angles
@@ -85,13 +89,29 @@ __global__ void __launch_bounds__(256) lpc2lsp_kernel(const T* __restrict__ a, T
         const int Gn = G * fine;
         if (lane == 0) cnt[0] = 0;
         __syncwarp();
-        for (int i = lane; i < Gn; i += 32) {
-          const double x0 = cospi(static_cast<double>(i) / Gn), x1 = cospi(static_cast<double>(i + 1) / Gn);
-          const double f0 = cheb_eval(g, n, x0), f1 = cheb_eval(g, n, x1);
-          if ((f0 < 0.0) != (f1 < 0.0)) {
-            const int slot = atomicAdd(&cnt[0], 1);
-            if (slot < n) { lo[off + slot] = x0; hi[off + slot] = x1; }
+        auto grid_x = [&](int i) { return fine == 1 ? xg[i] : cospi(static_cast<double>(i) / Gn); };
+        unsigned carry = 0;
+        // 32 grid points per round, one evaluation each; the signs are exchanged by a ballot.  Lane l < 31 owns the
+        // interval (base + l, base + l + 1); the interval that straddles two rounds belongs to lane 31 of the later.
+        for (int base = 0; base <= Gn; base += 32) {
+          const int i = base + lane;
+          const bool valid = i <= Gn;
+          const bool neg = valid && cheb_eval(g, n, grid_x(valid ? i : Gn)) < 0.0;
+          const unsigned vbits = __ballot_sync(0xffffffffu, valid), bits = __ballot_sync(0xffffffffu, neg);
+          bool change;
+          int idx;
+          if (lane < 31) {
+            idx = i;
+            change = ((vbits >> (lane + 1)) & 1u) && (((bits >> lane) ^ (bits >> (lane + 1))) & 1u);
+          } else {
+            idx = base - 1;
+            change = base > 0 && ((carry ^ bits) & 1u);
           }
+          if (change) {
+            const int slot = atomicAdd(&cnt[0], 1);
+            if (slot < n) { lo[off + slot] = grid_x(idx); hi[off + slot] = grid_x(idx + 1); }
+          }
+          carry = bits >> 31;
         }
         __syncwarp();
         found = cnt[0];
@@ -146,11 +166,11 @@ int lpc2lsp_impl(const void* a, void* w, int64_t rows, int32_t M, int32_t log_ga
   const int NC = M / 2 + 2;
   const int per_warp = 2 * (M + 2) + 2 * NC + 2 * std::max(M, 1) + 2;   // doubles
   const int wpb = 8;
-  const size_t smem = static_cast<size_t>(wpb) * per_warp * sizeof(double);
+  const int G = std::min(2048, std::max(256, 32 * M));   // grid intervals on (0, pi): ~ 64 per expected zero
+  const size_t smem = (static_cast<size_t>(G) + 2 + static_cast<size_t>(wpb) * per_warp) * sizeof(double);
   if (smem > static_cast<size_t>(max_dynamic_smem(device)))
     return fail(DSB200_E_UNSUPPORTED, "lpc_order %d does not fit in shared memory", M);
   DSB_CUDA(cudaFuncSetAttribute(lpc2lsp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int G = std::min(2048, std::max(256, 32 * M));   // grid intervals on (0, pi): ~ 64 per expected zero
   const int64_t need = (rows + wpb - 1) / wpb;
   const int blocks = static_cast<int>(std::min<int64_t>(need, static_cast<int64_t>(sm_count(device)) * 8));
   lpc2lsp_kernel<T><<<blocks, wpb * 32, smem, static_cast<cudaStream_t>(stream)>>>(
