@@ -234,7 +234,7 @@ def stft512_staged_store_banks(d):
     return rows
 
 
-# lsp.cu: the numerical steps of lpc2lsp_kernel for one row (deflation, Chebyshev series, grid + bisection in x).
+# lsp.cu: the numerical steps of lpc2lsp_kernel for one row (deflation, Chebyshev series, grid + refinement in x).
 def lsp_model(row, G=None):
     row = np.asarray(row, dtype=np.float64)
     M = row.size - 1
@@ -275,13 +275,25 @@ def lsp_model(row, G=None):
             if len(brackets) == n:
                 break
         for xa, xb in brackets[:n]:
-            neg_a = cheb(g, n, xa) < 0
-            for _ in range(54):
+            fa, fb = cheb(g, n, xa), cheb(g, n, xb)
+            for _ in range(4):                       # bisection
                 xm = 0.5 * (xa + xb)
-                if (cheb(g, n, xm) < 0) == neg_a:
-                    xa = xm
+                fm = cheb(g, n, xm)
+                if (fm < 0) == (fa < 0):
+                    xa, fa = xm, fm
                 else:
-                    xb = xm
-            out.append(np.arccos(0.5 * (xa + xb)))
+                    xb, fb = xm, fm
+            for _ in range(12):                      # regula falsi with the Illinois damping
+                d = fb - fa
+                if d == 0:
+                    break
+                xc = (xa * fb - xb * fa) / d
+                fc = cheb(g, n, xc)
+                if (fc < 0) != (fb < 0):
+                    xa, fa = xb, fb
+                else:
+                    fa *= 0.5
+                xb, fb = xc, fc
+            out.append(np.arccos(xb))
         out += [np.nan] * (n - min(n, len(brackets)))
     return np.sort(np.array(out))
