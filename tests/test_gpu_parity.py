@@ -508,3 +508,58 @@ def test_extreme_shapes_long_utterance_and_many_short_ones():
     Ys = F.stft(xs, out_format="complex")
     back = F.istft(Ys, out_length=333)
     assert float((back - xs).abs().max()) < 5e-4
+
+
+def test_converter_and_consumer_edge_cases():
+    """Section 8f ranks 3-4: empty batches, 1-D rows, non-contiguous and integer inputs, round trips, error paths,
+    and a config-3-sized batch checked by size-independent properties."""
+    import diffsptk_b200 as B
+    import diffsptk_b200.functional as F
+    from oracle import np_oracle as O
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(5)
+    # empty batch and 1-D input
+    for fn in (F.lpc2par, F.par2lpc, F.gnorm, F.ignorm, F.norm0, F.lpc2lsp, lambda t: F.mc2b(t, 0.42),
+               lambda t: F.b2mc(t, 0.42), lambda t: F.mgc2mgc(t, 7, in_alpha=0.1), lambda t: F.mgc2sp(t, 32)):
+        assert fn(torch.empty(0, 9, device=d)).shape[0] == 0
+        assert fn(torch.rand(9, device=d) * 0.3 + 0.5).dim() == 1
+    # round trips at full size (1 024 000 rows of order 24, the LPC output of BASELINE config 3)
+    k = torch.empty(1024, 1000, 25, device=d).uniform_(-0.6, 0.6, generator=g)
+    k[..., 0] = k[..., 0].abs() + 0.5
+    a = F.par2lpc(k)
+    assert torch.allclose(F.lpc2par(a), k, rtol=1e-3, atol=1e-4)          # PARCOR -> LPC -> PARCOR
+    assert torch.allclose(F.norm0(F.norm0(a)[..., :1]), a[..., :1], rtol=1e-5)
+    w = F.lpc2lsp(a)
+    lsp = w[..., 1:]
+    assert bool(torch.isfinite(lsp).all()) and bool((lsp[..., 1:] > lsp[..., :-1]).all())       # sorted, all found
+    assert float(lsp.min()) > 0 and float(lsp.max()) < np.pi                                    # inside (0, pi)
+    rows = np.random.default_rng(0).integers(0, 1024 * 1000, 40)                                # sampled vs oracle
+    got = to_np(w.reshape(-1, 25)[rows].double())
+    want = O.lpc2lsp(to_np(a.reshape(-1, 25)[rows]).astype(np.float64))
+    assert np.allclose(got, want, rtol=1e-4, atol=1e-5)
+    c = torch.randn(4096, 25, device=d, generator=g) * 0.2
+    c[..., 0] = c[..., 0].abs() + 0.1
+    for gm in (0.0, -0.5, 1.0):
+        assert torch.allclose(F.ignorm(F.gnorm(c, gm), gm), c, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(F.b2mc(F.mc2b(c, 0.42), 0.42), c, rtol=1e-4, atol=1e-5)
+    # mgc2sp(mcep(P)) is a smooth version of P: same level (log-spectral mean within 1 dB)
+    x = torch.randn(8, 16000, device=d, generator=g)
+    P = F.stft(x)
+    mc = F.mcep(P, 24, 0.42, 5)
+    S = F.mgc2sp(mc, 512, alpha=0.42)
+    assert S.shape == P.shape and float((10 * torch.log10(S) - 10 * torch.log10(P)).mean().abs()) < 3.0
+    # non-contiguous and integer input
+    at = a[0, :25].t().contiguous().t()                                    # (25, 25) view with stride (1, 25)
+    assert torch.equal(F.norm0(at), F.norm0(at.contiguous()))
+    assert F.norm0(torch.arange(1, 6, device=d)).dtype == torch.float32
+    # error paths keep the reference's messages
+    with pytest.raises(ValueError, match="gamma must be in"):
+        F.gnorm(c, 2.0)
+    with pytest.raises(ValueError, match="sample_rate must be positive"):
+        F.lpc2lsp(a, out_format="hz")
+    with pytest.raises(ValueError, match="plp_order must be less than n_channel"):
+        F.plp(P, 40, 40, 16000)
+    with pytest.raises(ValueError, match="gamma must be in"):
+        B.MelGeneralizedCepstralAnalysis(fft_length=512, cep_order=24, gamma=0.5)
+    with pytest.raises(ValueError, match="Unexpected dimension"):
+        B.LinearPredictiveCoefficientsToLineSpectralPairs(24).to(d)(torch.zeros(3, 24, device=d))
