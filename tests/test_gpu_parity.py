@@ -523,35 +523,47 @@ def test_converter_and_consumer_edge_cases():
                lambda t: F.b2mc(t, 0.42), lambda t: F.mgc2mgc(t, 7, in_alpha=0.1), lambda t: F.mgc2sp(t, 32)):
         assert fn(torch.empty(0, 9, device=d)).shape[0] == 0
         assert fn(torch.rand(9, device=d) * 0.3 + 0.5).dim() == 1
-    # round trips at full size (1 024 000 rows of order 24, the LPC output of BASELINE config 3)
-    k = torch.empty(1024, 1000, 25, device=d).uniform_(-0.6, 0.6, generator=g)
+    # round trips on 128 000 rows of order 24 (results reduced to Python scalars before asserting: pytest would
+    # otherwise format the operands of a failing comparison)
+    k = torch.empty(128, 1000, 25, device=d, dtype=torch.float64).uniform_(-0.6, 0.6, generator=g)
     k[..., 0] = k[..., 0].abs() + 0.5
     a = F.par2lpc(k)
-    assert torch.allclose(F.lpc2par(a), k, rtol=1e-3, atol=1e-4)          # PARCOR -> LPC -> PARCOR
-    assert torch.allclose(F.norm0(F.norm0(a)[..., :1]), a[..., :1], rtol=1e-5)
+    err = float((F.lpc2par(a) - k).abs().max())
+    assert err < 1e-8, err                                                 # PARCOR -> LPC -> PARCOR (float64)
+    k32 = (k * 0.5).float()                                                # |k| < 0.3: well conditioned in float32
+    k32[..., 0] = k[..., 0].float()
+    err = float((F.lpc2par(F.par2lpc(k32)) - k32).abs().max())
+    assert err < 1e-4, err
+    err = float((F.norm0(F.norm0(a)[..., :1]) - a[..., :1]).abs().max())
+    assert err < 1e-12, err
+    a = a.float()
     w = F.lpc2lsp(a)
     lsp = w[..., 1:]
-    assert bool(torch.isfinite(lsp).all()) and bool((lsp[..., 1:] > lsp[..., :-1]).all())       # sorted, all found
-    assert float(lsp.min()) > 0 and float(lsp.max()) < np.pi                                    # inside (0, pi)
-    rows = np.random.default_rng(0).integers(0, 1024 * 1000, 40)                                # sampled vs oracle
+    assert bool(torch.isfinite(lsp).all()), int((~torch.isfinite(lsp)).sum())
+    assert bool((lsp[..., 1:] > lsp[..., :-1]).all())                     # sorted, all found
+    assert float(lsp.min()) > 0 and float(lsp.max()) < np.pi              # inside (0, pi)
+    rows = np.random.default_rng(0).integers(0, 128 * 1000, 40)          # sampled vs oracle
     got = to_np(w.reshape(-1, 25)[rows].double())
     want = O.lpc2lsp(to_np(a.reshape(-1, 25)[rows]).astype(np.float64))
-    assert np.allclose(got, want, rtol=1e-4, atol=1e-5)
+    assert np.allclose(got, want, rtol=1e-4, atol=1e-5), float(np.abs(got - want).max())
     c = torch.randn(4096, 25, device=d, generator=g) * 0.2
     c[..., 0] = c[..., 0].abs() + 0.1
     for gm in (0.0, -0.5, 1.0):
-        assert torch.allclose(F.ignorm(F.gnorm(c, gm), gm), c, rtol=1e-4, atol=1e-5)
-    assert torch.allclose(F.b2mc(F.mc2b(c, 0.42), 0.42), c, rtol=1e-4, atol=1e-5)
+        err = float((F.ignorm(F.gnorm(c, gm), gm) - c).abs().max())
+        assert err < 1e-4, (gm, err)
+    err = float((F.b2mc(F.mc2b(c, 0.42), 0.42) - c).abs().max())
+    assert err < 1e-4, err
     # mgc2sp(mcep(P)) is a smooth version of P at the same level (mcep is unbiased in the log domain, the periodogram
     # is not: the mean log difference of white noise is Euler's constant = 2.5 dB)
     x = torch.randn(8, 16000, device=d, generator=g)
     P = F.stft(x)
     mc = F.mcep(P, 24, 0.42, 5)
     S = F.mgc2sp(mc, 512, alpha=0.42)
-    assert S.shape == P.shape and float((10 * torch.log10(S) - 10 * torch.log10(P)).mean().abs()) < 5.0
+    level = float((10 * torch.log10(S) - 10 * torch.log10(P)).mean().abs())
+    assert S.shape == P.shape and level < 5.0, level
     # non-contiguous and integer input
     at = a[0, :25].t().contiguous().t()                                    # (25, 25) view with stride (1, 25)
-    assert torch.equal(F.norm0(at), F.norm0(at.contiguous()))
+    assert bool((F.norm0(at) == F.norm0(at.contiguous())).all())
     assert F.norm0(torch.arange(1, 6, device=d)).dtype == torch.float32
     # error paths keep the reference's messages
     with pytest.raises(ValueError, match="gamma must be in"):
