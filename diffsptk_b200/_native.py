@@ -75,6 +75,7 @@ _TYPED = {
     "dsb200_rowconv": [_P, _P, _I64, _I32, _I32, _D, _INT, _P],
     "dsb200_thsolve": [_P, _P, _P, _P, _I64, _I32, _INT, _P],
     "dsb200_lpc2lsp": [_P, _P, _I64, _I32, _I32, _D, _INT, _P],
+    "dsb200_gc2gc": [_P, _P, _I64, _I32, _I32, _D, _D, _I32, _INT, _P],
     "dsb200_delta_backward": [_P, _P, _P, _I64, _I64, _I32, _I32, _I32, _INT, _P],
     "dsb200_fbank_backward": [_P, _P, _P, _P, _P, _P, _P, _I64, C.POINTER(FbankParams), _INT, _P],
     "dsb200_acorr_backward": [_P, _P, _P, _I64, _I32, _I32, _I32, _INT, _P],

@@ -3,10 +3,10 @@
 SURVEY.md section 8(f) rank 3/4.  The conversion is the reference's sequence of steps (mgc2mgc.py:209-297), each
 step running on this package's kernels: frequency transform = ``dsb200_rowmat`` with the reference's table,
 gain (de)normalisation = ``dsb200_rowconv``, and the gamma conversion (``GeneralizedCepstrumToGeneralizedCepstrum``,
-mgc2mgc.py:327-364) = ``dsb200_rfft`` -> pointwise complex power / log on the device -> ``dsb200_ifftr`` (no
-torch.fft).  The one-coefficient scalings (gamma multiplication / division) and the pointwise spectrum map are
-torch elementwise ops on the device, so autograd flows through the whole chain.  First version: a fused
-per-row kernel for the gamma conversion is the natural next step.
+mgc2mgc.py:327-364) = ``dsb200_gc2gc``: forward transform, pointwise complex power / log and inverse transform in
+one kernel (no torch.fft, any ``n_fft``).  The one-coefficient scalings (gamma multiplication / division) are torch
+elementwise ops on the device; autograd flows through the whole chain (the backward of ``gc2gc`` recomputes the
+step on the differentiable FFT kernels).
 """
 
 from __future__ import annotations
@@ -22,22 +22,8 @@ from .base import BaseFunctionalModule, Precomputed
 
 def gc2gc(c1: torch.Tensor, out_order: int, in_gamma: float, out_gamma: float, n_fft: int) -> torch.Tensor:
     """Generalized cepstrum (normalised) with ``in_gamma`` -> ``out_gamma`` in the spectral domain
-    (mgc2mgc.py:327-364)."""
-    if n_fft % 2:
-        raise NotImplementedError("n_fft must be even (the kernels transform real sequences by the half-length trick).")
-    c01 = torch.cat((torch.zeros_like(c1[..., :1]), c1[..., 1:]), dim=-1)
-    C1 = torch.view_as_complex(ops.rfft(c01, n_fft, 0))     # the other half of fft(c01) is its mirror image
-    if in_gamma == 0:
-        sC1 = torch.polar(torch.exp(C1.real), C1.imag)
-    else:
-        C1 = torch.complex(C1.real * in_gamma + 1, C1.imag * in_gamma)
-        sC1 = torch.polar(C1.abs() ** (1 / in_gamma), C1.angle() / in_gamma)
-    if out_gamma == 0:
-        C2 = torch.log(sC1.abs())
-    else:
-        C2 = ((sC1.abs() ** out_gamma) * torch.cos(sC1.angle() * out_gamma) - 1) / out_gamma
-    c02 = ops.ifftr(torch.complex(C2, torch.zeros_like(C2)), n_fft)[..., : out_order + 1]   # C2 is real and even
-    return torch.cat((c1[..., :1], 2 * c02[..., 1:]), dim=-1)
+    (mgc2mgc.py:327-364): one kernel, ``dsb200_gc2gc`` (csrc/gc2gc.cu)."""
+    return ops.gc2gc(c1, out_order, in_gamma, out_gamma, n_fft)
 
 
 def _scale_tail(g: float) -> Callable:          # GammaDivision / GammaMultiplication (mgc2mgc.py:367-411)

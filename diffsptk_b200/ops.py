@@ -1278,3 +1278,59 @@ def _lpc2lsp_bwd(ctx, g):
 
 
 torch.library.register_autograd(f"{_NS}::lpc2lsp", _lpc2lsp_bwd, setup_context=_lpc2lsp_setup)
+
+
+# ------------------------------------------------------------------ gc2gc (the gamma conversion inside mgc2mgc)
+def gc2gc_composite(c1: Tensor, out_order: int, in_gamma: float, out_gamma: float, n_fft: int) -> Tensor:
+    """mgc2mgc.py:327-364 step by step on the differentiable FFT kernels (``rfft`` / ``ifftr``) and device-side
+    elementwise ops: the backward of ``gc2gc`` (and its cross-check in the tests); even ``n_fft`` only."""
+    c01 = torch.cat((torch.zeros_like(c1[..., :1]), c1[..., 1:]), dim=-1)
+    C1 = torch.view_as_complex(rfft(c01, n_fft, 0))     # the other half of fft(c01) is its mirror image
+    if in_gamma == 0:
+        sC1 = torch.polar(torch.exp(C1.real), C1.imag)
+    else:
+        C1 = torch.complex(C1.real * in_gamma + 1, C1.imag * in_gamma)
+        sC1 = torch.polar(C1.abs() ** (1 / in_gamma), C1.angle() / in_gamma)
+    if out_gamma == 0:
+        C2 = torch.log(sC1.abs())
+    else:
+        C2 = ((sC1.abs() ** out_gamma) * torch.cos(sC1.angle() * out_gamma) - 1) / out_gamma
+    c02 = ifftr(torch.complex(C2, torch.zeros_like(C2)), n_fft)[..., : out_order + 1]   # C2 is real and even
+    return torch.cat((c1[..., :1], 2 * c02[..., 1:]), dim=-1)
+
+
+@torch.library.custom_op(f"{_NS}::gc2gc", mutates_args=(), device_types="cuda")
+def gc2gc(c1: Tensor, out_order: int, in_gamma: float, out_gamma: float, n_fft: int) -> Tensor:
+    dt = _native_dtype(c1)
+    cc = _prep(c1, dt)
+    D1 = cc.shape[-1]
+    rows = cc.numel() // max(D1, 1)
+    c2 = torch.empty((*cc.shape[:-1], out_order + 1), device=c1.device, dtype=dt)
+    N.check(N.typed("dsb200_gc2gc", dt == torch.float64)(_ptr(cc), _ptr(c2), rows, D1 - 1, out_order, float(in_gamma),
+                                                         float(out_gamma), n_fft, _dev(c1), _stream(c1)))
+    return c2
+
+
+@gc2gc.register_fake
+def _(c1, out_order, in_gamma, out_gamma, n_fft):
+    return c1.new_empty((*c1.shape[:-1], out_order + 1), dtype=_native_dtype(c1))
+
+
+def _gc2gc_setup(ctx, inputs, output):
+    c1, out_order, in_gamma, out_gamma, n_fft = inputs
+    ctx.save_for_backward(c1)
+    ctx.args = (out_order, in_gamma, out_gamma, n_fft)
+
+
+def _gc2gc_bwd(ctx, g):
+    (c1,) = ctx.saved_tensors
+    if ctx.args[3] % 2:
+        raise NotImplementedError("gradients of gc2gc need an even n_fft (they run on the real-FFT kernels)")
+    with torch.enable_grad():
+        cd = c1.detach().to(_native_dtype(c1)).requires_grad_(True)
+        y = gc2gc_composite(cd, *ctx.args)
+        (gc,) = torch.autograd.grad(y, cd, g.to(y.dtype))
+    return _like_input(gc, c1), None, None, None, None
+
+
+torch.library.register_autograd(f"{_NS}::gc2gc", _gc2gc_bwd, setup_context=_gc2gc_setup)

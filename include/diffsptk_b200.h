@@ -271,6 +271,12 @@ DSB200_DECL2(dsb200_rowconv, (const void* x, void* y, int64_t rows, int32_t dim,
 DSB200_DECL2(dsb200_lpc2lsp, (const void* a, void* w, int64_t rows, int32_t lpc_order, int32_t log_gain,
                               double scale, int device, void* stream))
 
+/* GeneralizedCepstrumToGeneralizedCepstrum._forward, diffsptk/modules/mgc2mgc.py:327-364: gamma conversion of
+ * gain-normalised generalized cepstra, c1[rows, in_order + 1] -> c2[rows, out_order + 1], both transforms and
+ * the pointwise spectrum map in one kernel (any n_fft > max(in_order, out_order) + 1, even or odd). */
+DSB200_DECL2(dsb200_gc2gc, (const void* c1, void* c2, int64_t rows, int32_t in_order, int32_t out_order,
+                            double in_gamma, double out_gamma, int32_t n_fft, int device, void* stream))
+
 /* Per-row solve of (Toeplitz(t) + Hankel(h)) x = r: t[rows, order], h[rows, 2 * order - 1], r[rows, order] ->
  * x[rows, order].  The Newton step of MelGeneralizedCepstralAnalysis, diffsptk/modules/mgcep.py:219-222
  * (symmetric_toeplitz / hankel, diffsptk/utils/private.py:291-302, then torch.linalg.solve). */

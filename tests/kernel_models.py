@@ -297,3 +297,39 @@ def lsp_model(row, G=None):
             out.append(np.arccos(xb))
         out += [np.nan] * (n - min(n, len(brackets)))
     return np.sort(np.array(out))
+
+
+# gc2gc.cu: direct evaluation of both transforms from a twiddle table (index arithmetic mod n, half-spectrum weights).
+def gc2gc_model(c1, out_order, g1, g2, n):
+    c1 = np.asarray(c1, dtype=np.float64)
+    D1, D2, K = c1.size, out_order + 1, n // 2 + 1
+    tw = np.exp(-2j * np.pi * np.arange(n) / n)
+    C2 = np.zeros(K)
+    for k in range(K):
+        acc, idx = 0j, 0
+        for m in range(1, D1):
+            idx += k
+            if idx >= n:
+                idx -= n
+            acc += c1[m] * tw[idx]
+        re, im = acc.real, acc.imag
+        if g1 == 0:
+            mag, ang = np.exp(re), np.arctan2(np.sin(im), np.cos(im))
+        else:
+            zr, zi = 1 + g1 * re, g1 * im
+            mag = np.hypot(zr, zi) ** (1 / g1)
+            th = np.arctan2(zi, zr) / g1
+            ang = np.arctan2(np.sin(th), np.cos(th))
+        C2[k] = np.log(mag) if g2 == 0 else (mag ** g2 * np.cos(ang * g2) - 1) / g2
+    out = np.zeros(D2)
+    out[0] = c1[0]
+    for m in range(1, D2):
+        acc, idx = 0.0, 0
+        for k in range(K):
+            wk = 1.0 if (k == 0 or 2 * k == n) else 2.0
+            acc += wk * C2[k] * tw[idx].real
+            idx += m
+            if idx >= n:
+                idx -= n
+        out[m] = 2 * acc / n
+    return out

@@ -576,3 +576,38 @@ def test_converter_and_consumer_edge_cases():
         B.MelGeneralizedCepstralAnalysis(fft_length=512, cep_order=24, gamma=0.5)
     with pytest.raises(ValueError, match="Unexpected dimension"):
         B.LinearPredictiveCoefficientsToLineSpectralPairs(24).to(d)(torch.zeros(3, 24, device=d))
+
+
+def test_gc2gc_kernel_against_oracle_and_composite():
+    """dsb200_gc2gc (direct transforms, one kernel) against the oracle's FFT route -- even AND odd n_fft -- and
+    against the composite on the real-FFT kernels that serves as its backward; gradient by central differences."""
+    from diffsptk_b200 import ops
+    from oracle import np_oracle as O
+    d = dev()
+    rng = np.random.default_rng(9)
+    for n, M1, M2, g1, g2 in ((512, 24, 24, 0.0, -0.5), (512, 24, 256, -0.5, 0.0), (255, 12, 30, -1.0, -0.3),
+                              (64, 8, 8, 0.2, 0.1), (1024, 40, 40, -0.25, -1.0), (32, 4, 0, 0.0, -0.5)):
+        c1 = 0.15 * rng.standard_normal((3, 7, M1 + 1))
+        c1[..., 0] = rng.uniform(0.3, 1.2, (3, 7))
+        want = O._gc2gc(c1, M2, g1, g2, n)
+        for prec in ("f64", "f32"):
+            got = to_np(ops.gc2gc(to_dev(c1, prec), M2, g1, g2, n))
+            H.assert_close(got, want, prec, what=f"gc2gc n={n} {prec}", scale_atol=True)
+        if n % 2 == 0:
+            comp = to_np(ops.gc2gc_composite(to_dev(c1, "f64"), M2, g1, g2, n))
+            H.assert_close(comp, want, "f64", what=f"gc2gc composite n={n}", scale_atol=True)
+    x0 = to_dev(c1, "f64")                                   # last case: (32, 4 -> 0): a single output, the gain
+    c1 = 0.15 * rng.standard_normal((4, 9))
+    c1[:, 0] = 0.8
+    x0 = to_dev(c1, "f64")
+    w = to_dev(rng.standard_normal((4, 13)), "f64")
+    x = x0.clone().requires_grad_(True)
+    (gx,) = torch.autograd.grad((ops.gc2gc(x, 12, -0.5, 0.25, 64) * w).sum(), x)
+    num = torch.zeros_like(x0)
+    with torch.no_grad():
+        for j in range(9):
+            e = torch.zeros_like(x0)
+            e[:, j] = 1e-6
+            num[:, j] = ((ops.gc2gc(x0 + e, 12, -0.5, 0.25, 64) - ops.gc2gc(x0 - e, 12, -0.5, 0.25, 64)) * w).sum(-1) / 2e-6
+    err = float((gx - num).abs().max())
+    assert err < 1e-6, err

@@ -85,3 +85,15 @@ def test_lsp_model_matches_reference():
         for r in range(0, a.shape[0], max(1, a.shape[0] // 12)):
             got = KM.lsp_model(a[r])
             assert np.allclose(got, want[r, 1:], rtol=1e-9, atol=1e-11), (name, r, np.abs(got - want[r, 1:]).max())
+
+
+def test_gc2gc_model_matches_oracle():
+    """Direct-transform recipe of gc2gc.cu against the oracle's FFT route, even and odd n_fft."""
+    rng = np.random.default_rng(3)
+    for n, M1, M2, g1, g2 in ((64, 6, 9, 0.0, -0.5), (64, 6, 4, -0.5, 0.0), (63, 5, 7, -1.0, -0.3), (32, 8, 8, 0.2, 0.1),
+                              (128, 12, 64, 0.0, 0.0)):
+        c1 = 0.2 * rng.standard_normal(M1 + 1)
+        c1[0] = 0.7
+        want = O._gc2gc(c1[None], M2, g1, g2, n)[0]
+        got = KM.gc2gc_model(c1, M2, g1, g2, n)
+        assert np.allclose(got, want, rtol=1e-10, atol=1e-12), (n, M1, M2, g1, g2, np.abs(got - want).max())
