@@ -435,6 +435,33 @@ def main():
             except Exception as e:  # an extra must never take the headline down
                 extras[wl] = {"error": repr(e)[:200]}
         line["extra_workloads"] = extras
+        if args.workload == "stft":
+            # COMPARATOR ONLY (never on the product path): the route the reference's modules take on a GPU --
+            # pad + unfold + window multiply + torch.fft.rfft (cuFFT) + abs/square/add as separate torch kernels
+            # (stft.py:237-241) -- on the same device and the same batch.
+            try:
+                import torch.nn.functional as TF
+                del xs, step
+                torch.cuda.empty_cache()
+                xc = torch.randn(B, T, device=dev)
+                wc = tables.make_window(FL, device=dev, dtype=torch.float32)
+
+                def composite(i):
+                    fr = TF.pad(xc, (FL // 2, (FL - 1) // 2)).unfold(-1, FL, FP) * wc
+                    return torch.fft.rfft(TF.pad(fr, (0, NFFT - FL))).abs().square() + 1e-9
+                _, perc = timed_steps(composite, 5, 3, False)
+                cms = statistics.mean(perc)
+                line["comparators"] = {"torch_composite_same_gpu": {
+                    "frames_per_s": frames_per_step / (cms / 1e3), "ms_per_step": cms,
+                    "what": "F.pad + unfold + window + torch.fft.rfft + abs().square() + eps, fp32, same batch"}}
+            except Exception as e:
+                line["comparators"] = {"torch_composite_same_gpu": {"error": repr(e)[:200]}}
+    if args.workload == "stft" and clocks and clocks.get("sm_mhz"):
+        # the kernel sits at the HBM / FP32 ridge: report the FP32 side as well
+        slots = 8320.0   # FMA-pipe lane-slots per frame: 1 040 pipe cycles x 32 lanes per quad of 4 frames
+        peak_slots = 148 * 128 * float(clocks["sm_mhz"]) * 1e6
+        line["roofline"]["fp32_pipe"] = {"lane_slots_per_frame": slots, "frac": frames_per_step / (kernel_ms / 1e3) * slots / peak_slots,
+                                         "peak": "148 SMs x 128 lanes x measured SM clock"}
     print(json.dumps(line), flush=True)
     if dist_on:
         dist.destroy_process_group()

@@ -614,3 +614,38 @@ def test_lpc2lsp_gradients():
                 e[:, j] = h
                 num[:, j] = ((F.lpc2lsp(a0 + e, **kw) - F.lpc2lsp(a0 - e, **kw)) * w).sum(-1) / (2 * h)
         assert torch.allclose(ga, num, rtol=1e-5, atol=1e-6), (M, (ga - num).abs().max())
+
+
+def test_composite_consumer_gradients():
+    """mgc2mgc / mgc2sp / plp / mgcep chain kernels that each carry their own backward: the chain rule through the
+    whole composite against central differences of the forward (float64)."""
+    import diffsptk_b200 as B
+    import diffsptk_b200.functional as F
+    d = dev()
+    g = torch.Generator().manual_seed(77)
+    c = (0.2 * torch.randn(3, 9, generator=g, dtype=torch.float64))
+    c[:, 0] = 0.6
+    P = (torch.fft.rfft(torch.randn(3, 64, generator=g, dtype=torch.float64)).abs().square() + 0.1)
+    mg = B.MelGeneralizedCepstralAnalysis(fft_length=64, cep_order=6, alpha=0.2, gamma=-0.5, n_iter=2,
+                                          dtype=torch.float64).to(d)
+    cases = [("mgc2mgc", lambda t: F.mgc2mgc(t, 10, in_alpha=0.1, out_alpha=0.3, in_gamma=-0.5, out_gamma=-0.25, n_fft=128), c),
+             ("mgc2mgc_norm", lambda t: F.mgc2mgc(t, 8, in_gamma=0.0, out_gamma=-1.0, out_norm=True, out_mul=True, n_fft=64), c),
+             ("mgc2sp", lambda t: F.mgc2sp(t, 32, alpha=0.3, gamma=-0.5, n_fft=128, out_format="log-magnitude"), c),
+             ("plp", lambda t: F.plp(t, 5, 10, 8000, lifter=20, floor=1e-3, out_format="ycE"), P),
+             ("mgcep", mg, P)]
+    for name, fn, x0 in cases:
+        x0 = x0.to(d)
+        x = x0.clone().requires_grad_(True)
+        y = fn(x)
+        w = torch.randn(y.shape, generator=g, dtype=torch.float64).to(d)
+        (gx,) = torch.autograd.grad((y * w).sum(), x)
+        num = torch.zeros_like(x0)
+        with torch.no_grad():
+            for j in range(x0.shape[-1]):
+                h = 1e-6 * max(1.0, float(x0[:, j].abs().max()))
+                e = torch.zeros_like(x0)
+                e[:, j] = h
+                num[:, j] = ((fn(x0 + e) - fn(x0 - e)) * w).sum(-1) / (2 * h)
+        scale = float(num.abs().max())
+        err = float((gx - num).abs().max())
+        assert err <= 2e-5 * scale + 1e-7, (name, err, scale)
