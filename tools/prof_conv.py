@@ -1,0 +1,15 @@
+"""Tiny driver for ncu: a few launches of the section-8f converter kernels at config-3 size (1 024 000 rows, M = 24)."""
+import sys, torch
+sys.path.insert(0, ".")
+import diffsptk_b200.functional as F
+dev = torch.device("cuda", 0)
+k = torch.empty(1024, 1000, 25, device=dev).uniform_(-0.6, 0.6)
+k[..., 0] = k[..., 0].abs() + 0.5
+with torch.no_grad():
+    a = F.par2lpc(k)
+    for _ in range(3):
+        p = F.lpc2par(a)
+        w = F.lpc2lsp(a)
+        c = F.mgc2mgc(k * 0.3, 24, in_gamma=0.0, out_gamma=-0.5)
+torch.cuda.synchronize()
+print(float(p.sum()), float(w.sum()), float(c.sum()))
