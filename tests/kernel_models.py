@@ -299,20 +299,18 @@ def lsp_model(row, G=None):
     return np.sort(np.array(out))
 
 
-# gc2gc.cu: direct evaluation of both transforms from a twiddle table (index arithmetic mod n, half-spectrum weights).
+# gc2gc.cu: both transforms as trigonometric series evaluated by Clenshaw recurrences in float64 (one recurrence
+# yields the cosine AND the sine sum of the forward transform), half-spectrum weights in the inverse.
 def gc2gc_model(c1, out_order, g1, g2, n):
     c1 = np.asarray(c1, dtype=np.float64)
     D1, D2, K = c1.size, out_order + 1, n // 2 + 1
-    tw = np.exp(-2j * np.pi * np.arange(n) / n)
     C2 = np.zeros(K)
     for k in range(K):
-        acc, idx = 0j, 0
-        for m in range(1, D1):
-            idx += k
-            if idx >= n:
-                idx -= n
-            acc += c1[m] * tw[idx]
-        re, im = acc.real, acc.imag
+        x, sn = np.cos(2 * np.pi * k / n), np.sin(2 * np.pi * k / n)
+        b1 = b2 = 0.0
+        for m in range(D1 - 1, 0, -1):              # b_m = c_m + 2 x b_{m+1} - b_{m+2}
+            b1, b2 = c1[m] + 2 * x * b1 - b2, b1
+        re, im = x * b1 - b2, -sn * b1              # sum c_m cos(m t), -sum c_m sin(m t)
         if g1 == 0:
             mag, ang = np.exp(re), np.arctan2(np.sin(im), np.cos(im))
         else:
@@ -321,15 +319,16 @@ def gc2gc_model(c1, out_order, g1, g2, n):
             th = np.arctan2(zi, zr) / g1
             ang = np.arctan2(np.sin(th), np.cos(th))
         C2[k] = np.log(mag) if g2 == 0 else (mag ** g2 * np.cos(ang * g2) - 1) / g2
+    a = C2.copy()
+    a[1:] *= 2
+    if n % 2 == 0:
+        a[K - 1] *= 0.5
     out = np.zeros(D2)
     out[0] = c1[0]
     for m in range(1, D2):
-        acc, idx = 0.0, 0
-        for k in range(K):
-            wk = 1.0 if (k == 0 or 2 * k == n) else 2.0
-            acc += wk * C2[k] * tw[idx].real
-            idx += m
-            if idx >= n:
-                idx -= n
-        out[m] = 2 * acc / n
+        x = np.cos(2 * np.pi * m / n)
+        b1 = b2 = 0.0
+        for k in range(K - 1, 0, -1):
+            b1, b2 = a[k] + 2 * x * b1 - b2, b1
+        out[m] = 2 * (a[0] + x * b1 - b2) / n
     return out
