@@ -303,6 +303,17 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # Libraries (NCCL prints its version line at init) write to file descriptor 1 behind Python's back: keep the
+    # contract "rank 0 prints ONE JSON line" by pointing fd 1 at stderr for the run and printing the line through
+    # a saved copy of the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(obj) + "\n").encode())
+
     import torch
     import torch.distributed as dist
 
@@ -462,7 +473,7 @@ def main():
         peak_slots = 148 * 128 * float(clocks["sm_mhz"]) * 1e6
         line["roofline"]["fp32_pipe"] = {"lane_slots_per_frame": slots, "frac": frames_per_step / (kernel_ms / 1e3) * slots / peak_slots,
                                          "peak": "148 SMs x 128 lanes x measured SM clock"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if dist_on:
         dist.destroy_process_group()
 
