@@ -13,6 +13,25 @@ from .base import BaseFunctionalModule, Precomputed
 from .mgc2mgc import MelGeneralizedCepstrumToMelGeneralizedCepstrum
 
 
+_FORMAT_IDS = {"db": 0, "log-magnitude": 1, "magnitude": 2, "power": 3, "cycle": 4, "radian": 5, "degree": 6}
+
+
+def _log_spectrum_formatter(out_format) -> Callable:
+    """What to return from the complex log spectrum ``log|H| + j arg H`` (mgc2sp.py:152-169)."""
+    if out_format == "complex":
+        return lambda sp: torch.polar(torch.exp(sp.real), sp.imag)
+    fid = _FORMAT_IDS.get(out_format, out_format) if isinstance(out_format, str) else out_format
+    if isinstance(fid, bool) or fid not in range(7):
+        raise ValueError(f"out_format {out_format} is not supported.")
+    amplitude = {0: 20 / math.log(10), 1: 1.0}                        # scaled log magnitude
+    phase = {4: 1 / math.pi, 5: 1.0, 6: 180 / math.pi}                # scaled phase
+    if fid in amplitude:
+        return lambda sp: sp.real * amplitude[fid] if fid == 0 else sp.real
+    if fid in phase:
+        return lambda sp: sp.imag / torch.pi if fid == 4 else (sp.imag if fid == 5 else sp.imag * (180 / torch.pi))
+    return lambda sp: torch.exp(sp.real if fid == 2 else 2 * sp.real)
+
+
 class MelGeneralizedCepstrumToSpectrum(BaseFunctionalModule):
     """``(..., M+1) -> (..., L/2+1)``: un-warp / un-gamma the cepstrum to a plain cepstrum of order ``L/2``
     (``mgc2mgc``), transform it with ``dsb200_rfft`` and format the log spectrum (mgc2sp.py:131-202)."""
@@ -45,24 +64,7 @@ class MelGeneralizedCepstrumToSpectrum(BaseFunctionalModule):
                     out_format: str | int, device: torch.device | None, dtype: torch.dtype | None,
                     module: bool = True) -> Precomputed:
         MelGeneralizedCepstrumToSpectrum._check()
-        if out_format in (0, "db"):
-            formatter = lambda x: x.real * (20 / math.log(10))  # noqa: E731
-        elif out_format in (1, "log-magnitude"):
-            formatter = lambda x: x.real  # noqa: E731
-        elif out_format in (2, "magnitude"):
-            formatter = lambda x: torch.exp(x.real)  # noqa: E731
-        elif out_format in (3, "power"):
-            formatter = lambda x: torch.exp(2 * x.real)  # noqa: E731
-        elif out_format in (4, "cycle"):
-            formatter = lambda x: x.imag / torch.pi  # noqa: E731
-        elif out_format in (5, "radian"):
-            formatter = lambda x: x.imag  # noqa: E731
-        elif out_format in (6, "degree"):
-            formatter = lambda x: x.imag * (180 / torch.pi)  # noqa: E731
-        elif out_format == "complex":
-            formatter = lambda x: torch.polar(torch.exp(x.real), x.imag)  # noqa: E731
-        else:
-            raise ValueError(f"out_format {out_format} is not supported.")
+        formatter = _log_spectrum_formatter(out_format)
         mgc2c = get_layer(module, MelGeneralizedCepstrumToMelGeneralizedCepstrum,
                           dict(in_order=cep_order, in_alpha=alpha, in_gamma=gamma, in_norm=norm, in_mul=mul,
                                out_order=fft_length // 2, out_alpha=0, out_gamma=0, out_norm=False, out_mul=False,

@@ -23,6 +23,38 @@ from .levdur import LevinsonDurbin
 from .mgc2mgc import MelGeneralizedCepstrumToMelGeneralizedCepstrum
 
 
+def _equal_loudness(n_channel, sample_rate, f_min, f_max, scale) -> np.ndarray:
+    """Equal-loudness weight at the centre frequency of every filter-bank channel (plp.py:279-285), float64."""
+    lo = tables._to_auditory(np.asarray(f_min), scale)
+    hi = tables._to_auditory(np.asarray(sample_rate / 2 if f_max is None else f_max), scale)
+    centres = (hi - lo) / (n_channel + 1) * np.arange(1, n_channel + 2) + lo
+    f = tables._from_auditory(centres, scale)[:-1] ** 2
+    return (f / (f + 1.6e5)) ** 2 * (f + 1.44e6) / (f + 9.61e6)
+
+
+def _plp_lifter(plp_order, lifter, device) -> torch.Tensor:
+    """1 + (L/2) sin(pi m / L) with the zeroth term fixed at 2 (plp.py:287-289), float64."""
+    m = torch.arange(plp_order + 1, device=device, dtype=torch.double)
+    v = 1 + (lifter / 2) * torch.sin((torch.pi / lifter) * m)
+    v[0] = 2
+    return v
+
+
+_LAYOUTS = {0: "y", 1: "yE", 2: "yc", 3: "ycE"}
+
+
+def _packer(out_format) -> Callable:
+    """``y`` = coefficients without c0, ``c`` = c0, ``E`` = energy, concatenated in the order the name spells."""
+    name = _LAYOUTS.get(out_format, out_format)
+    if isinstance(out_format, bool) or name not in _LAYOUTS.values():
+        raise ValueError(f"out_format {out_format} is not supported.")
+
+    def pack(y, c, E):
+        parts = {"y": y, "c": c, "E": E}
+        return y if name == "y" else torch.cat([parts[ch] for ch in name], dim=-1)
+    return pack
+
+
 class PerceptualLinearPredictiveCoefficientsAnalysis(BaseFunctionalModule):
     """``(..., L/2+1)`` power spectrum ``-> (..., M [+1] [+1])`` (plp.py:303-320)."""
 
@@ -62,16 +94,7 @@ class PerceptualLinearPredictiveCoefficientsAnalysis(BaseFunctionalModule):
                     erb_factor: float | None, n_fft: int, out_format: str | int, learnable: bool,
                     device: torch.device | None, dtype: torch.dtype | None, module: bool = True) -> Precomputed:
         PerceptualLinearPredictiveCoefficientsAnalysis._check(plp_order, n_channel, compression_factor, lifter)
-        if out_format in (0, "y"):
-            formatter = lambda y, c, E: y  # noqa: E731
-        elif out_format in (1, "yE"):
-            formatter = lambda y, c, E: torch.cat((y, E), dim=-1)  # noqa: E731
-        elif out_format in (2, "yc"):
-            formatter = lambda y, c, E: torch.cat((y, c), dim=-1)  # noqa: E731
-        elif out_format in (3, "ycE"):
-            formatter = lambda y, c, E: torch.cat((y, c, E), dim=-1)  # noqa: E731
-        else:
-            raise ValueError(f"out_format {out_format} is not supported.")
+        formatter = _packer(out_format)
         if dtype is not None and not dtype.is_floating_point:
             dtype = None
         fbank = get_layer(module, MelFilterBankAnalysis,
@@ -83,22 +106,11 @@ class PerceptualLinearPredictiveCoefficientsAnalysis(BaseFunctionalModule):
                           dict(in_order=plp_order, in_alpha=0, in_gamma=-1, in_norm=True, in_mul=True,
                                out_order=plp_order, out_alpha=0, out_gamma=0, out_norm=False, out_mul=False,
                                n_fft=n_fft, device=device, dtype=dtype))
-        if f_max is None:
-            f_max = sample_rate / 2
-        mel_min = tables._to_auditory(np.asarray(f_min), scale)
-        mel_max = tables._to_auditory(np.asarray(f_max), scale)
-        seed = np.arange(1, n_channel + 2)
-        center_frequencies = (mel_max - mel_min) / (n_channel + 1) * seed + mel_min
-        f = tables._from_auditory(center_frequencies, scale)[:-1] ** 2
-        equal_loudness_curve = (f / (f + 1.6e5)) ** 2 * (f + 1.44e6) / (f + 9.61e6)
-        ramp = torch.arange(plp_order + 1, device=device, dtype=torch.double)
-        liftering_vector = 1 + (lifter / 2) * torch.sin((torch.pi / lifter) * ramp)
-        liftering_vector[0] = 2
-        return Precomputed(
-            values={"compression_factor": compression_factor, "formatter": formatter},
-            layers={"fbank": fbank, "levdur": levdur, "lpc2c": lpc2c},
-            tensors={"equal_loudness_curve": tables._cast(equal_loudness_curve, device, dtype),
-                     "liftering_vector": tables._cast(liftering_vector, None, dtype)})
+        tensors = {"equal_loudness_curve": tables._cast(_equal_loudness(n_channel, sample_rate, f_min, f_max, scale),
+                                                        device, dtype),
+                   "liftering_vector": tables._cast(_plp_lifter(plp_order, lifter, device), None, dtype)}
+        return Precomputed(values={"compression_factor": compression_factor, "formatter": formatter},
+                           layers={"fbank": fbank, "levdur": levdur, "lpc2c": lpc2c}, tensors=tensors)
 
     @staticmethod
     def _forward(x: torch.Tensor, *, compression_factor: float, formatter: Callable, fbank: Callable,
