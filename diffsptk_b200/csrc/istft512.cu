@@ -44,7 +44,8 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
   float2* tws = reinterpret_cast<float2*>(smem_raw);           // [256] W512^k
   float* wsm = reinterpret_cast<float*>(tws + 256);            // [512] window / 512 (zero beyond L)
   float* w2 = wsm + 512;                                       // [512] window^2
-  float2* planes1 = reinterpret_cast<float2*>(w2 + 512);       // [kIW][2 kPlane] exchange planes of half-warp 1
+  float* dtab = w2 + 512;                                      // [512] sum of window^2 over a full set of frames
+  float2* planes1 = reinterpret_cast<float2*>(dtab + 512);     // [kIW][2 kPlane] exchange planes of half-warp 1
   float2* planes0 = planes1 + kIW * 2 * kPlane;                // [kIW][2 kPlane] (only when they cannot alias)
   float* fbuf = reinterpret_cast<float*>(planes0 + A.fbuf_off);                              // [32][L]
 
@@ -61,6 +62,14 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
     const float2 v = A.tw512[2 * l * k2];
     twr[k2] = v.x;
     twi[k2] = v.y;
+  }
+  __syncthreads();
+  // Away from the utterance ends every output sample with the same phase r = q mod P is covered by the same set
+  // of frames, so its normaliser sum_u w^2[r + u P] is a table (summed in the order of the general loop below).
+  for (int r = tid; r < A.P; r += kIT) {
+    float d = 0.0f;
+    for (int j = r; j < L; j += A.P) d += w2[j];
+    dtab[r] = d;
   }
   // this half-warp's exchange planes: half-warp 0 borrows the first rows of the warp's own frames in fbuf
   // (dead until the samples are written, after the last plane read); half-warp 1 has private planes
@@ -158,16 +167,25 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
       for (int i = tid; i < cnt; i += kIT) {
         // frames n with 0 <= q - n P <= L - 1:  n in [ne - c + (r > m), ne], c = (L-1) / P, m = (L-1) % P.
         // The loop runs c + 1 times for every lane (no divergence); out-of-range frames are predicated off.
-        int na = ne - A.c + (r > A.m ? 1 : 0);
-        if (na < 0) na = 0;
-        const int nb = ne < Nm1 ? ne : Nm1;
-        int n = ne, j = r;
+        const int first = ne - A.c + (r > A.m ? 1 : 0);
         const float* fp = fbuf + (ne - nlo) * L + r;
-        float num = 0.0f, den = 0.0f;
-        for (int u = 0; u <= A.c; ++u, --n, fp -= L - P, j += P) {
-          if (n >= na && n <= nb) {
-            num += *fp;
-            den += w2[j];
+        float num = 0.0f, den;
+        if (first >= 0 && ne <= Nm1) {
+          // interior sample: all of its frames exist; only the numerator is summed
+          const int terms = ne - first + 1;
+#pragma unroll 5
+          for (int u = 0; u < terms; ++u, fp -= L - P) num += *fp;
+          den = dtab[r];
+        } else {
+          const int na = first < 0 ? 0 : first;
+          const int nb = ne < Nm1 ? ne : Nm1;
+          int n = ne, j = r;
+          den = 0.0f;
+          for (int u = 0; u <= A.c; ++u, --n, fp -= L - P, j += P) {
+            if (n >= na && n <= nb) {
+              num += *fp;
+              den += w2[j];
+            }
           }
         }
         outp[i] = num / (den + 1e-16f);
@@ -208,7 +226,7 @@ int istft512_try(const float* Y, const float* w, float* out, int64_t batch, int6
   A.tiles_per_utt = (T_out + tile - 1) / tile;
   A.alias = (static_cast<size_t>(4) * L * sizeof(float) >= 2 * kPlane * sizeof(float2)) ? 1 : 0;
   A.fbuf_off = A.alias ? 0 : kIW * 2 * kPlane;
-  const size_t smem = 256 * sizeof(float2) + 2 * 512 * sizeof(float) +
+  const size_t smem = 256 * sizeof(float2) + 3 * 512 * sizeof(float) +
                       static_cast<size_t>(kIW) * 2 * kPlane * sizeof(float2) * (A.alias ? 1 : 2) +
                       static_cast<size_t>(kTileFrames) * L * sizeof(float);
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
