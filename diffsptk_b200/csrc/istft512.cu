@@ -98,17 +98,19 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
     }
 
     const int fA = 4 * warp + 2 * h;                           // this half-warp's frames within the tile
-    const bool vA = fA < nf, vB = fA + 1 < nf;
     if (4 * warp < nf) {                                       // warp-uniform: some frame of the quad exists
-      const float2* ya = A.Y + (b * A.N + n_lo + fA) * 257;
-      const float2* yb = ya + 257;
+      // Frames past the end of a partial tile are computed from the tile's last valid row and parked in their own
+      // (never read) rows of fbuf: no predicate or branch per load / store, the lanes of a packed operation are
+      // independent and the overlap-add only visits frames < nf.
+      const int rA = fA < nf ? fA : nf - 1, rB = fA + 1 < nf ? fA + 1 : nf - 1;
+      const float2* ya = A.Y + (b * A.N + n_lo + rA) * 257;
+      const float2* yb = A.Y + (b * A.N + n_lo + rB) * 257;
       C2 a[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         const int k = 16 * j + l;
-        float2 pa = make_float2(0.0f, 0.0f), qa = pa, pb = pa, qb = pa;   // X[k], X[256 - k] of frames A, B
-        if (vA) { pa = __ldg(ya + k); qa = __ldg(ya + 256 - k); }
-        if (vB) { pb = __ldg(yb + k); qb = __ldg(yb + 256 - k); }
+        float2 pa = __ldg(ya + k), qa = __ldg(ya + 256 - k);   // X[k], X[256 - k] of frames A, B
+        float2 pb = __ldg(yb + k), qb = __ldg(yb + 256 - k);
         if (k == 0) { pa.y = 0.0f; qa.y = 0.0f; pb.y = 0.0f; qb.y = 0.0f; }   // irfft ignores these
         // E = X[k] + conj X[256-k], D = X[k] - conj X[256-k], O = D conj(W512^k); input conj(E + i O)
         // scalar adds write the (frame A, frame B) halves in place: cheaper than packing the loaded values first
@@ -145,11 +147,11 @@ __global__ void __launch_bounds__(kIT, 2) istft512_kernel(const IArgs A) {
           const C2 v = a[dig(k1)];
           const float w0 = wsm[s], w1 = wsm[s + 1];
           if (s + 1 < L) {
-            if (vA) *reinterpret_cast<float2*>(rowA + s) = make_float2(v.re.x * w0, -v.im.x * w1);
-            if (vB) *reinterpret_cast<float2*>(rowB + s) = make_float2(v.re.y * w0, -v.im.y * w1);
+            *reinterpret_cast<float2*>(rowA + s) = make_float2(v.re.x * w0, -v.im.x * w1);
+            *reinterpret_cast<float2*>(rowB + s) = make_float2(v.re.y * w0, -v.im.y * w1);
           } else {
-            if (vA) rowA[s] = v.re.x * w0;
-            if (vB) rowB[s] = v.re.y * w0;
+            rowA[s] = v.re.x * w0;
+            rowB[s] = v.re.y * w0;
           }
         }
       }
