@@ -115,7 +115,6 @@ __global__ void __launch_bounds__(kBT, 2) stft512_bwd_kernel(const BArgs A) {
     __syncthreads();
 
     const int fA = 4 * warp + 2 * h;                           // this half-warp's frames within the tile
-    const bool vA = fA < nf, vB = fA + 1 < nf;
     if (4 * warp < nf) {                                       // warp-uniform
       // ---- analysis: X = rfft(window * frame), exactly as stft512.cu ---------------------------------------
       const float* pa = xs + fA * A.P + 2 * l;
@@ -166,17 +165,17 @@ __global__ void __launch_bounds__(kBT, 2) stft512_bwd_kernel(const BArgs A) {
         r[j].im.y = __shfl_sync(0xffffffffu, s.im.y, partner);
       }
       // ---- G = g format'(s) X, then back to the half-length spectrum conj(E' + i O') ----------------------
-      const float* ga = A.gy + (b * A.N + n_lo + fA) * 257;
-      const float* gb = ga + 257;
+      // Frames past the end of a partial tile take the gradient row of the tile's last valid frame and park their
+      // result in their own (never read) rows of fbuf: no predicate per load / store (packed lanes are independent,
+      // the overlap-add only visits frames < nf).
+      const float* ga = A.gy + (b * A.N + n_lo + (fA < nf ? fA : nf - 1)) * 257;
+      const float* gb = A.gy + (b * A.N + n_lo + (fA + 1 < nf ? fA + 1 : nf - 1)) * 257;
       const float2 eps2 = make_float2(A.eps, A.eps);
       C2 c128;        // lane 0: the self-mirrored bin 128
       {
         const float2 Xr = a[dig(8)].re, Xi = neg2(a[dig(8)].im);                 // X[128] = conj(Z[128])
         float2 g = make_float2(0.0f, 0.0f);
-        if (l == 0) {
-          if (vA) g.x = __ldg(ga + 128);
-          if (vB) g.y = __ldg(gb + 128);
-        }
+        if (l == 0) g = make_float2(__ldg(ga + 128), __ldg(gb + 128));
         const float2 d = fmt_grad(g, fma2(Xr, Xr, fma2(Xi, Xi, eps2)), A.fmt);
         c128.re = mul2s(__fmul2_rn(d, Xr), 2.0f);
         c128.im = mul2s(__fmul2_rn(d, Xi), 2.0f);
@@ -193,9 +192,8 @@ __global__ void __launch_bounds__(kBT, 2) stft512_bwd_kernel(const BArgs A) {
         const float2 ti = mul2s(fma2s(dr, -wv.x, mul2s(si, wv.y)), 0.5f);
         const float2 Xr = fma2s(sr, 0.5f, tr), Xi = fma2s(di, 0.5f, ti);
         const float2 Mr = fma2s(sr, 0.5f, neg2(tr)), Mi = fma2s(di, -0.5f, ti);
-        float2 gk = make_float2(0.0f, 0.0f), gm = gk;
-        if (vA) { gk.x = __ldg(ga + k); gm.x = __ldg(ga + 256 - k); }
-        if (vB) { gk.y = __ldg(gb + k); gm.y = __ldg(gb + 256 - k); }
+        const float2 gk = make_float2(__ldg(ga + k), __ldg(gb + k));
+        const float2 gm = make_float2(__ldg(ga + 256 - k), __ldg(gb + 256 - k));
         const float2 dk = fmt_grad(gk, fma2(Xr, Xr, fma2(Xi, Xi, eps2)), A.fmt);
         const float2 dm = fmt_grad(gm, fma2(Mr, Mr, fma2(Mi, Mi, eps2)), A.fmt);
         float2 Gr = __fmul2_rn(dk, Xr), Gi = __fmul2_rn(dk, Xi);     // Y'[k]
@@ -251,8 +249,8 @@ __global__ void __launch_bounds__(kBT, 2) stft512_bwd_kernel(const BArgs A) {
         if (s < L) {   // L is even: s + 1 < L too
           const C2 v = cc[dig(k1)];
           const float2 wv = *reinterpret_cast<const float2*>(win + s);
-          if (vA) *reinterpret_cast<float2*>(rowA + s) = make_float2(v.re.x * wv.x, -v.im.x * wv.y);
-          if (vB) *reinterpret_cast<float2*>(rowB + s) = make_float2(v.re.y * wv.x, -v.im.y * wv.y);
+          *reinterpret_cast<float2*>(rowA + s) = make_float2(v.re.x * wv.x, -v.im.x * wv.y);
+          *reinterpret_cast<float2*>(rowB + s) = make_float2(v.re.y * wv.x, -v.im.y * wv.y);
         }
       }
     }
