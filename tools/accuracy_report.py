@@ -40,7 +40,11 @@ def main():
         op, params, ins32, out32 = H.load_case(name, "f32")
         _, _, _, out64 = H.load_case(name, "f64")
         with torch.no_grad():
-            got = getattr(F, op)(*[to_dev(a) for a in ins32], **params)
+            if op == "mgcep":   # an nn.Module without functional form, in the reference too
+                import diffsptk_b200 as B
+                got = B.MelGeneralizedCepstralAnalysis(**params).cuda()(*[to_dev(a) for a in ins32])
+            else:
+                got = getattr(F, op)(*[to_dev(a) for a in ins32], **params)
         got = got if isinstance(got, tuple) else (got,)
         for g, r32, r64 in zip(got, out32, out64):
             g = g.cpu().numpy()
