@@ -3,7 +3,7 @@
     python tools/stft_variant_sweep.py            # parent: runs every combination in a child process
     python tools/stft_variant_sweep.py --child    # child: parity vs the default build + timing, prints one JSON line
 
-The knobs (DSB200_STFT_V, DSB200_STFT_STAGGER, DSB200_STFT_STORE) are read once per process, hence the children.
+The knobs (DSB200_STFT_V, DSB200_STFT_W, DSB200_STFT_STORE) are read once per process, hence the children.
 Parity: neither knob changes the arithmetic of a frame, so every variant must reproduce the default variant's
 output BIT FOR BIT on a batch with ragged edges (the default itself is pinned by tests/test_gpu_parity.py).
 Timing: CUDA events over `steps` launches of BASELINE config 2 (256 x 10 s), two rotating inputs.
