@@ -82,6 +82,8 @@ _TYPED = {
     "dsb200_levdur_backward": [_P, _P, _P, _I64, _I32, _D, _INT, _P],
     "dsb200_mfcc_wave": [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, C.POINTER(StftParams),
                          C.POINTER(MfccParams), _INT, _P],
+    "dsb200_mfcc_wave_ex": [_P, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_void_p), _I32, _I64, _I64, _I64,
+                            C.POINTER(StftParams), C.POINTER(MfccParams), _INT, _P],
 }
 
 _PLAIN = {
@@ -92,6 +94,9 @@ _PLAIN = {
     "dsb200_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p), _INT, _I64, _I64, C.POINTER(StftParams), _INT]),
     "dsb200_pipeline_stft_host": (C.c_int, [_P, _P, _P, _P, _I64]),
     "dsb200_pipeline_destroy": (C.c_int, [_P]),
+    "dsb200_mfcc_plan_ints": (C.c_int32, [_I32]),
+    "dsb200_mfcc_plan_build": (C.c_int, [C.POINTER(C.c_int32), C.POINTER(C.c_int32), _I32, _I32,
+                                         C.POINTER(C.c_int32)]),
 }
 
 

@@ -75,6 +75,9 @@ __device__ __forceinline__ void radix4(C2& x0, C2& x1, C2& x2, C2& x3) {
 // register order a[4 r + t] = A[r + 4 t]; callers index through dig().
 __host__ __device__ constexpr int dig(int k) { return 4 * (k & 3) + (k >> 2); }
 
+
+#ifdef DSB200_FFT16_LEGACY
+// Round-1 version: the W16^(c r) twiddles as separate multiplies (96 packed operations in the second layer).
 template <int NJ>
 __device__ __forceinline__ void fft16(C2 (&a)[16]) {
   radix4<(12 >= NJ)>(a[0], a[4], a[8], a[12]);
@@ -116,6 +119,73 @@ __device__ __forceinline__ void fft16(C2 (&a)[16]) {
   radix4<false>(a[8], a[9], a[10], a[11]);    // r = 2 -> k = 2, 6, 10, 14
   radix4<false>(a[12], a[13], a[14], a[15]);  // r = 3 -> k = 3, 7, 11, 15
 }
+#else
+constexpr float kT8 = 0.41421356237309504880f;  // tan(pi/8)
+
+// out = (x + s y, x - s y) with a real scalar s: two packed multiply-adds per complex value
+__device__ __forceinline__ void pm_s(C2 x, C2 y, float s, C2& plus, C2& minus) {
+  plus = {fma2s(y.re, s, x.re), fma2s(y.im, s, x.im)};
+  minus = {fma2s(y.re, -s, x.re), fma2s(y.im, -s, x.im)};
+}
+// out = (x - i s y, x + i s y)
+__device__ __forceinline__ void pm_is(C2 x, C2 y, float s, C2& minus_i, C2& plus_i) {
+  minus_i = {fma2s(y.im, s, x.re), fma2s(y.re, -s, x.im)};
+  plus_i = {fma2s(y.im, -s, x.re), fma2s(y.re, s, x.im)};
+}
+
+// Second layer for one residue r: X_t = sum_c W4^(c t) W16^(c r) b_c, with the W16 twiddles folded into the
+// butterflies' multiply-adds (round 2): a twiddle cos(1 - i tan) costs two multiply-adds for the rotation-by-tan
+// and its cosine rides on the following +/- as a multiply-add; R (1 -+ i) costs two additions and its R rides
+// likewise.  80 packed operations for the four residues instead of 96, none of them a bare multiply.
+template <int R>
+__device__ __forceinline__ void layer2(C2& x0, C2& x1, C2& x2, C2& x3) {
+  if constexpr (R == 0) {
+    radix4<false>(x0, x1, x2, x3);
+  } else if constexpr (R == 2) {
+    // W16^2 = R (1 - i), W16^4 = -i, W16^6 = -R (1 + i)
+    const C2 t0 = csub_i(x0, x2), t1 = cadd_i(x0, x2);          // x0 -+ i b2
+    const C2 s = cadd(x1, x3), d = csub(x1, x3);
+    const C2 p = csub_i(d, s);                                   // (1 - i) b1 - (1 + i) b3 = d - i s
+    const C2 m = csub_i(s, d);                                   // (1 - i) b1 + (1 + i) b3 = s - i d
+    pm_s(t0, p, kR, x0, x2);
+    pm_is(t1, m, kR, x1, x3);
+  } else {
+    // R == 1: W16^1 = c (1 - i t), W16^2 = R (1 - i), W16^3 = c (t - i)
+    // R == 3: W16^3 = c (t - i),  W16^6 = -R (1 + i), W16^9 = -c (1 - i t)       (c = cos pi/8, t = tan pi/8)
+    C2 t0, t1, u, v;
+    if constexpr (R == 1) {
+      const C2 q = {add2(x2.re, x2.im), sub2(x2.im, x2.re)};     // (1 - i) b2
+      pm_s(x0, q, kR, t0, t1);
+      u = {fma2s(x1.im, kT8, x1.re), fma2s(x1.re, -kT8, x1.im)};             // (1 - i t) b1
+      v = {fma2s(x3.re, kT8, x3.im), fma2s(x3.im, kT8, make_float2(-x3.re.x, -x3.re.y))};   // (t - i) b3
+      const C2 p = cadd(u, v), m = csub(u, v);
+      pm_s(t0, p, kC8, x0, x2);
+      pm_is(t1, m, kC8, x1, x3);
+    } else {
+      const C2 q = {sub2(x2.re, x2.im), add2(x2.im, x2.re)};     // (1 + i) b2
+      pm_s(x0, q, kR, t1, t0);                                   // t0 = x0 - R q, t1 = x0 + R q
+      u = {fma2s(x1.re, kT8, x1.im), fma2s(x1.im, kT8, make_float2(-x1.re.x, -x1.re.y))};   // (t - i) b1
+      v = {fma2s(x3.im, kT8, x3.re), fma2s(x3.re, -kT8, x3.im)};             // (1 - i t) b3
+      const C2 p = csub(u, v), m = cadd(u, v);
+      pm_s(t0, p, kC8, x0, x2);
+      pm_is(t1, m, kC8, x1, x3);
+    }
+  }
+}
+
+template <int NJ>
+__device__ __forceinline__ void fft16(C2 (&a)[16]) {
+  radix4<(12 >= NJ)>(a[0], a[4], a[8], a[12]);
+  radix4<(13 >= NJ)>(a[1], a[5], a[9], a[13]);
+  radix4<(14 >= NJ)>(a[2], a[6], a[10], a[14]);
+  radix4<(15 >= NJ)>(a[3], a[7], a[11], a[15]);
+  // a[c + 4 r] now holds b_c[r]
+  layer2<0>(a[0], a[1], a[2], a[3]);      // r = 0 -> k = 0, 4, 8, 12
+  layer2<1>(a[4], a[5], a[6], a[7]);      // r = 1 -> k = 1, 5, 9, 13
+  layer2<2>(a[8], a[9], a[10], a[11]);    // r = 2 -> k = 2, 6, 10, 14
+  layer2<3>(a[12], a[13], a[14], a[15]);  // r = 3 -> k = 3, 7, 11, 15
+}
+#endif
 
 }  // namespace fft16_detail
 }  // namespace dsb200

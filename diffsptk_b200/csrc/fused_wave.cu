@@ -20,14 +20,16 @@
 //
 // Envelope: float32, frame_length <= 400, lpc_order <= 24, even frame_period, no zmean.
 #include <algorithm>
+#include <cstdlib>
 
 #include "bulk.cuh"
 
 namespace dsb200 {
 namespace {
 
-constexpr int kLWarps = 8;      // 2 warps per scheduler -> 255 registers/thread (25 lags x 2 frames + a 25-deep window)
-constexpr int kLThreads = kLWarps * 32;
+// Warps per CTA (template parameter): 8 = 2 per scheduler, 255 registers/thread (round 1: FMA pipe 47 %, every
+// load / reduction / Levinson phase of one warp exposed); 12 = 3 per scheduler at 168 registers -- the 25 packed lag
+// accumulators + the 25-deep window need ~100, the rest covers the loads in flight.
 constexpr int kUnit = 32;     // frames per warp unit (one Levinson frame per lane)
 constexpr int kHalfUnit = 16; // frames staged at a time
 constexpr int kCh = 25;       // samples per lane (16 lanes x 25 = 400 >= frame_length)
@@ -47,8 +49,9 @@ struct LArgs {
 
 // FULL: frame_length == 400 exactly -- every chunk sample is inside the frame, and only lane 15's halo
 // (samples 400..423) must be forced to zero; otherwise every load is compared with the per-lane limit.
-template <bool FULL>
-__global__ void __launch_bounds__(kLThreads, 1) lpc_wave_kernel(const LArgs A) {
+template <bool FULL, int kLWarps>
+__global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A) {
+  constexpr int kLThreads = kLWarps * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int l = lane & 15, h = lane >> 4;
@@ -224,6 +227,13 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
   const int left = fp->center ? fp->frame_length / 2 : 0;
   const int span = ((kHalfUnit - 1) * fp->frame_period + 16 * kCh + kHalo + 3) & ~3;
   const size_t per_warp = static_cast<size_t>(span) * 4 + 2 * 16 * kLag * 8 + kUnit * kLag * 4;
+  // DSB200_LPC_W=8|12 (tuning knob, read once): warps per CTA
+  static const int w_knob = [] {
+    const char* e = getenv("DSB200_LPC_W");
+    return e != nullptr ? atoi(e) : 12;
+  }();
+  int kLWarps = (w_knob == 8) ? 8 : 12;
+  if (8 * kLWarps + 448 * sizeof(float) + kLWarps * per_warp > static_cast<size_t>(max_dynamic_smem(device))) kLWarps = 8;
   const size_t smem = 8 * kLWarps + 448 * sizeof(float) + kLWarps * per_warp;
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
 
@@ -246,11 +256,16 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
   A.bulk_out = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   A.eps = eps;
   const bool full = fp->frame_length == 16 * kCh;
-  DSB_CUDA(cudaFuncSetAttribute(lpc_wave_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  DSB_CUDA(cudaFuncSetAttribute(lpc_wave_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_units + kLWarps - 1) / kLWarps, sm_count(device)));
-  if (full) lpc_wave_kernel<true><<<blocks, kLThreads, smem, stream>>>(A);
-  else lpc_wave_kernel<false><<<blocks, kLThreads, smem, stream>>>(A);
+  auto launch = [&](auto kern) -> int {
+    DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<blocks, kLWarps * 32, smem, stream>>>(A);
+    return DSB200_OK;
+  };
+  int rc;
+  if (kLWarps == 8) rc = full ? launch(lpc_wave_kernel<true, 8>) : launch(lpc_wave_kernel<false, 8>);
+  else rc = full ? launch(lpc_wave_kernel<true, 12>) : launch(lpc_wave_kernel<false, 12>);
+  if (rc != DSB200_OK) return rc;
   return after_launch("lpc_wave_kernel");
 }
 
@@ -258,15 +273,14 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
 
 namespace dsb200 {
 int mfcc_wave_try(const float* x, const float* window, const float* H, const int32_t* cb, const int32_t* ce,
-                  const float* W, const float* lifter, float* y, int64_t batch, int64_t T_len,
-                  const dsb200_stft_params* sp, const dsb200_mfcc_params* mp, int device, cudaStream_t stream);
-}
+                  const float* W, const float* lifter, const int32_t* plan, float* const* y_dst, int n_dst,
+                  int64_t row_off, int64_t batch, int64_t T_len, const dsb200_stft_params* sp,
+                  const dsb200_mfcc_params* mp, int device, cudaStream_t stream);
 
-extern "C" {
-int dsb200_mfcc_wave_f32(const void* x, const void* window, const void* H, const int32_t* cb, const int32_t* ce,
-                         const void* W, const void* lifter, void* y, int64_t batch, int64_t T,
-                         const dsb200_stft_params* sp, const dsb200_mfcc_params* mp, int device, void* stream) {
-  using namespace dsb200;
+static int mfcc_wave_checked(const void* x, const void* window, const void* H, const int32_t* cb, const int32_t* ce,
+                             const void* W, const void* lifter, const int32_t* plan, void* const* y_dst, int n_dst,
+                             int64_t row_off, int64_t batch, int64_t T, const dsb200_stft_params* sp,
+                             const dsb200_mfcc_params* mp, int device, void* stream) {
   DSB_REQUIRE(sp != nullptr && mp != nullptr, "params are NULL");
   DSB_REQUIRE(sp->frame.frame_length > 0, "frame_length must be positive.");
   DSB_REQUIRE(sp->frame.frame_period > 0, "frame_period must be positive.");
@@ -276,21 +290,45 @@ int dsb200_mfcc_wave_f32(const void* x, const void* window, const void* H, const
   DSB_REQUIRE(mp->fbank.floor > 0, "floor must be positive.");
   DSB_REQUIRE(mp->mfcc_order >= 0 && mp->mfcc_order < mp->fbank.n_channel, "mfcc_order must be less than n_channel.");
   DSB_REQUIRE(mp->out_format >= DSB200_MFCC_Y && mp->out_format <= DSB200_MFCC_YCE, "out_format %d is not supported.", mp->out_format);
-  DSB_REQUIRE(T >= 1 && batch >= 0, "bad batch / waveform length");
+  DSB_REQUIRE(mp->fbank.fft_length == sp->spec.fft_length, "the filter bank and the STFT must share fft_length.");
+  DSB_REQUIRE(T >= 1 && batch >= 0 && row_off >= 0, "bad batch / waveform length / row offset");
+  DSB_REQUIRE(y_dst != nullptr && n_dst >= 1 && n_dst <= 8, "between 1 and 8 destinations");
   if (batch == 0) return DSB200_OK;
-  DSB_REQUIRE(x && window && H && W && lifter && y, "NULL data pointer");
+  DSB_REQUIRE(x && window && H && W && lifter, "NULL data pointer");
+  for (int d = 0; d < n_dst; ++d) DSB_REQUIRE(y_dst[d] != nullptr, "NULL destination pointer");
   DeviceScope ds(device);
   DSB_CUDA(ds.err);
   const int rc = mfcc_wave_try(static_cast<const float*>(x), static_cast<const float*>(window),
                                static_cast<const float*>(H), cb, ce, static_cast<const float*>(W),
-                               static_cast<const float*>(lifter), static_cast<float*>(y), batch, T, sp, mp, device,
-                               static_cast<cudaStream_t>(stream));
+                               static_cast<const float*>(lifter), plan, reinterpret_cast<float* const*>(y_dst), n_dst,
+                               row_off, batch, T, sp, mp, device, static_cast<cudaStream_t>(stream));
   if (rc == DSB200_E_UNSUPPORTED)
     return fail(DSB200_E_UNSUPPORTED, "fused waveform->MFCC kernel not available for this configuration");
   return rc;
 }
+}  // namespace dsb200
+
+extern "C" {
+int dsb200_mfcc_wave_f32(const void* x, const void* window, const void* H, const int32_t* cb, const int32_t* ce,
+                         const void* W, const void* lifter, void* y, int64_t batch, int64_t T,
+                         const dsb200_stft_params* sp, const dsb200_mfcc_params* mp, int device, void* stream) {
+  void* dst[1] = {y};
+  return dsb200::mfcc_wave_checked(x, window, H, cb, ce, W, lifter, nullptr, dst, 1, 0, batch, T, sp, mp, device, stream);
+}
 int dsb200_mfcc_wave_f64(const void*, const void*, const void*, const int32_t*, const int32_t*, const void*, const void*,
                          void*, int64_t, int64_t, const dsb200_stft_params*, const dsb200_mfcc_params*, int, void*) {
+  return dsb200::fail(DSB200_E_UNSUPPORTED, "fused waveform->MFCC kernel is float32 only");
+}
+int dsb200_mfcc_wave_ex_f32(const void* x, const void* window, const void* H, const int32_t* cb, const int32_t* ce,
+                            const void* W, const void* lifter, const int32_t* plan, void* const* y_dst, int32_t n_dst,
+                            int64_t row_offset, int64_t batch, int64_t T, const dsb200_stft_params* sp,
+                            const dsb200_mfcc_params* mp, int device, void* stream) {
+  return dsb200::mfcc_wave_checked(x, window, H, cb, ce, W, lifter, plan, y_dst, n_dst, row_offset, batch, T, sp, mp,
+                                   device, stream);
+}
+int dsb200_mfcc_wave_ex_f64(const void*, const void*, const void*, const int32_t*, const int32_t*, const void*,
+                            const void*, const int32_t*, void* const*, int32_t, int64_t, int64_t, int64_t,
+                            const dsb200_stft_params*, const dsb200_mfcc_params*, int, void*) {
   return dsb200::fail(DSB200_E_UNSUPPORTED, "fused waveform->MFCC kernel is float32 only");
 }
 }

@@ -15,7 +15,18 @@
 //     the pivot row equals the pivot COLUMN, one entry per lane, published through shared memory in one
 //     parallel store; two frames' systems are eliminated per pass (packed), back substitution likewise.
 // The three tables (G, Hm, P0: 114 KB) stay resident in shared memory for the whole persistent CTA.
+//
+// v2 (round 2).  v1 ran 8 warps of 255 registers (two per scheduler) and kept the log spectrum of the octet in
+// shared memory (9 KB per warp): FMA pipe 39 %, every dependency stall exposed.  Now
+//   * e = exp(log x - 2 d) is evaluated as x * exp(-2 d) with x re-read from global memory in every Newton step
+//     (the octet's 8 KB stay in L2 for its ten steps; HBM traffic is unchanged) -- no per-warp spectrum copy, so
+//     the CTA has room for 12 (default) or 16 warps;
+//   * the Newton systems are eliminated two frame pairs per pass (100 instead of 200 matrix registers), which
+//     fits the 168-register budget of 12 warps without spills;
+//   * rows past the end of a partial octet are clamped to the last valid row and simply not stored: no load
+//     predicates anywhere in the step.
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -23,20 +34,13 @@
 namespace dsb200 {
 namespace {
 
-#ifndef MCEP_Q
-#define MCEP_Q 4
-#endif
-constexpr int kQ = MCEP_Q;           // packed frame pairs eliminated per pass (4: all 8 frames at once; or 2)
-constexpr int kH = kQ / 2;           // float4 groups (two pairs each) exchanged through shared memory
-constexpr int kMW = 8;               // warps per CTA (2 per scheduler -> 255 registers per thread)
-constexpr int kMT = kMW * 32;
 constexpr int kKT = 9;               // bins per lane: k = lane + 32 t
 constexpr int kKS = 32 * kKT;        // 288: padded number of bins
 constexpr int kK = 257;
 constexpr int kDM = 25;              // max cepstral dimension (M + 1)
 constexpr int kJS = 49;              // row stride of Hm in shared memory (odd: conflict-free), = 2 * 24 + 1
 constexpr int kPS = 25;              // row stride of P0 in shared memory (odd)
-constexpr int kWarpFloats = kDM * 8 + 4 * kJS * 2 + 256 + 256 + 8 + kKT * 4 * 32 * 2;   // per-warp scratch
+constexpr int kWarpFloats = kDM * 8 + 4 * kJS * 2 + 256 + 256 + 8;   // per-warp scratch: mc, rt, pivot column, solution, rhs
 
 struct MArgs {
   const float* x;    // [rows, 257] power spectrum
@@ -90,7 +94,11 @@ __device__ __forceinline__ float fast_rcp(float x) {  // MUFU.RCP + one Newton s
   return fmaf(r, fmaf(-x, r, 1.0f), r);
 }
 
-__global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
+// kMW warps per CTA (12: 168 registers per thread, 16: 128); kQ packed frame pairs eliminated per pass.
+template <int kMW, int kQ>
+__global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
+  constexpr int kMT = kMW * 32;
+  constexpr int kH = kQ / 2;           // float4 groups (two pairs each) exchanged through shared memory
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int D = A.D, J = A.J;
@@ -105,7 +113,6 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
   float4* col = reinterpret_cast<float4*>(rts + 4 * kJS);   // [2][32] pivot column (= pivot row, by symmetry), 8 systems
   float4* xs = col + 64;                                 // [2][32] solution broadcast
   float4* pb = xs + 64;                                  // [2]     pivot right-hand sides
-  float2* lxs = reinterpret_cast<float2*>(pb + 2);       // [kKT][4][32] log spectrum (frame pair p, bin lane + 32 t)
 
   // tables -> shared memory (zero padded to 288 bins so that the tail lanes contribute nothing)
   for (int i = tid; i < kDM * kKS; i += kMT) {
@@ -126,31 +133,35 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
   const int64_t n_oct = (A.rows + 7) / 8;
   for (int64_t oct = static_cast<int64_t>(blockIdx.x) * kMW + warp; oct < n_oct;
        oct += static_cast<int64_t>(gridDim.x) * kMW) {
-    const int64_t r0 = oct * 8;
-    const int nf = static_cast<int>(A.rows - r0 < 8 ? A.rows - r0 : 8);
+    // The last octet of a batch that is not a multiple of 8 is moved back to end at the last row: its first rows
+    // are then computed twice (bit-identical results, stored twice) and no load or store needs a predicate.
+    const int64_t r0 = (oct * 8 + 8 <= A.rows) ? oct * 8 : A.rows - 8;
+    constexpr int nf = 8;
+    const float* xb = A.x + r0 * kK;                       // row f, bin k: xb[f * kK + k] (immediate offsets)
+    // Lane column t = 8 holds bins 256 + lane: only lane 0 has one.  The others re-read bin 256; their table
+    // entries are zero, so the (finite) value contributes nothing.
+    const int klast = (lane + 32 * (kKT - 1) < kK) ? lane + 32 * (kKT - 1) : kK - 1;
 
-    // ---- log spectrum of the 8 frames: lx[t][p] = (log x[2p][k_t], log x[2p+1][k_t]) ------------
-#pragma unroll
-    for (int t = 0; t < kKT; ++t) {
-      const int k = lane + 32 * t;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float a = (k < kK && 2 * p < nf) ? A.x[(r0 + 2 * p) * kK + k] : 1.0f;
-        const float b = (k < kK && 2 * p + 1 < nf) ? A.x[(r0 + 2 * p + 1) * kK + k] : 1.0f;
-        lxs[(t * 4 + p) * 32 + lane] = f2(logf(a), logf(b));
-      }
-    }
     // ---- initial estimate mc = log x @ P0 (mcep.py:203-207 folded) ------------------------------
-    for (int m = 0; m < D; ++m) {
-      float2 p4[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
+    {
+      float2 lx[kKT][4];                                   // (log x[2p][k_t], log x[2p+1][k_t])
 #pragma unroll
       for (int t = 0; t < kKT; ++t) {
-        const float c = Ps[(lane + 32 * t) * kPS + m];
+        const int k = (t < kKT - 1) ? lane + 32 * t : klast;
 #pragma unroll
-        for (int p = 0; p < 4; ++p) p4[p] = __ffma2_rn(lxs[(t * 4 + p) * 32 + lane], f2(c, c), p4[p]);
+        for (int p = 0; p < 4; ++p) lx[t][p] = f2(logf(__ldg(xb + 2 * p * kK + k)), logf(__ldg(xb + (2 * p + 1) * kK + k)));
       }
-      const float v = reduce8(p4, lane);
-      if ((lane & 3) == 0) mcs[m * 8 + (lane >> 2)] = v;
+      for (int m = 0; m < D; ++m) {
+        float2 p4[4] = {f2(0, 0), f2(0, 0), f2(0, 0), f2(0, 0)};
+#pragma unroll
+        for (int t = 0; t < kKT; ++t) {
+          const float c = Ps[(lane + 32 * t) * kPS + m];
+#pragma unroll
+          for (int p = 0; p < 4; ++p) p4[p] = __ffma2_rn(lx[t][p], f2(c, c), p4[p]);
+        }
+        const float v = reduce8(p4, lane);
+        if ((lane & 3) == 0) mcs[m * 8 + (lane >> 2)] = v;
+      }
     }
     __syncwarp();
 
@@ -172,13 +183,18 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
           for (int p = 0; p < 4; ++p) e[t][p] = __ffma2_rn(mc2[p], f2(gk, gk), e[t][p]);
         }
       }
+      // e = exp(log x - 2 d) = x * 2^(-2 log2(e) d): the spectrum comes back from L2, one MUFU.EX2 per value
+      constexpr float kM2L2E = -2.885390081777927f;        // -2 / ln 2
 #pragma unroll
-      for (int t = 0; t < kKT; ++t)
+      for (int t = 0; t < kKT; ++t) {
+        const int k = (t < kKT - 1) ? lane + 32 * t : klast;
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-          const float2 a = __ffma2_rn(e[t][p], f2(-2.0f, -2.0f), lxs[(t * 4 + p) * 32 + lane]);
-          e[t][p] = f2(__expf(a.x), __expf(a.y));
+          const float2 xv = f2(__ldg(xb + 2 * p * kK + k), __ldg(xb + (2 * p + 1) * kK + k));
+          const float2 a = __fmul2_rn(e[t][p], f2(kM2L2E, kM2L2E));
+          e[t][p] = __fmul2_rn(xv, f2(exp2f(a.x), exp2f(a.y)));
         }
+      }
       // ---- rt = e @ Hm, reduced over the lanes; four columns per round so that the shuffle chains of one
       //      column overlap the multiply-adds of the next ---------------------------------------------------
       auto rt_columns = [&](auto nc_c, int j0) {
@@ -331,12 +347,23 @@ __global__ void __launch_bounds__(kMT, 1) mcep_fast_kernel(const MArgs A) {
 
 }  // namespace
 
-int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_params* p, const float* P0,
-                  const float* G, const float* Hm, const float* av, int device, cudaStream_t stream) {
-  if (p->fft_length != 512 || p->cep_order > kDM - 1) return DSB200_E_UNSUPPORTED;
+template <int kMW, int kQ>
+static int launch_mcep_fast(const MArgs& A, int device, cudaStream_t stream) {
   const size_t smem = (static_cast<size_t>(kDM) * kKS + kKS * kJS + kKS * kPS + 32 +
                        static_cast<size_t>(kMW) * kWarpFloats) * sizeof(float);
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
+  DSB_CUDA(cudaFuncSetAttribute(mcep_fast_kernel<kMW, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  const int64_t n_oct = (A.rows + 7) / 8;
+  const int blocks = static_cast<int>(std::min<int64_t>((n_oct + kMW - 1) / kMW, sm_count(device)));
+  mcep_fast_kernel<kMW, kQ><<<blocks, kMW * 32, smem, stream>>>(A);
+  return after_launch("mcep_fast_kernel");
+}
+
+int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_params* p, const float* P0,
+                  const float* G, const float* Hm, const float* av, int device, cudaStream_t stream) {
+  if (p->fft_length != 512 || p->cep_order > kDM - 1) return DSB200_E_UNSUPPORTED;
+  if (rows < 8) return DSB200_E_UNSUPPORTED;   // fewer rows than one octet: the generic kernel
   MArgs A{};
   A.x = x;
   A.y = y;
@@ -348,11 +375,14 @@ int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_para
   A.D = p->cep_order + 1;
   A.J = 2 * p->cep_order + 1;
   A.n_iter = p->n_iter;
-  DSB_CUDA(cudaFuncSetAttribute(mcep_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const int64_t n_oct = (rows + 7) / 8;
-  const int blocks = static_cast<int>(std::min<int64_t>((n_oct + kMW - 1) / kMW, sm_count(device)));
-  mcep_fast_kernel<<<blocks, kMT, smem, stream>>>(A);
-  return after_launch("mcep_fast_kernel");
+  // DSB200_MCEP_V=8x4 | 12x2 | 16x2 (tuning knob, read once): warps per CTA x frame pairs per elimination pass
+  static const int variant = [] {
+    const char* e = getenv("DSB200_MCEP_V");
+    return e != nullptr ? atoi(e) : 12;
+  }();
+  if (variant == 8) return launch_mcep_fast<8, 4>(A, device, stream);
+  if (variant == 16) return launch_mcep_fast<16, 2>(A, device, stream);
+  return launch_mcep_fast<12, 2>(A, device, stream);
 }
 
 }  // namespace dsb200

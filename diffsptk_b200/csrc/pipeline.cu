@@ -93,23 +93,37 @@ int dsb200_pipeline_stft_host(dsb200_pipeline* pl, const void* x_host, const voi
   const size_t y_row = static_cast<size_t>(pl->N) * pl->K * pl->out_mult * es;
   const char* xh = static_cast<const char*>(x_host);
   char* yh = static_cast<char*>(y_host);
+  // Every exit, error exits included, first drains the three streams: the copies read and write caller-owned
+  // host buffers, which must not be touched after this call returns.
+  auto drain = [&](int rc) {
+    cudaStreamSynchronize(pl->s_out);
+    cudaStreamSynchronize(pl->s_run);
+    cudaStreamSynchronize(pl->s_in);
+    return rc;
+  };
+#define DSB_PIPE(call)                                                    \
+  do {                                                                    \
+    cudaError_t e__ = (call);                                             \
+    if (e__ != cudaSuccess) return drain(::dsb200::cuda_fail(e__, #call)); \
+  } while (0)
   int64_t c = 0;
   for (int64_t b0 = 0; b0 < batch; b0 += pl->chunk, ++c) {
     const int s = static_cast<int>(c & 1);
     const int64_t nb = batch - b0 < pl->chunk ? batch - b0 : pl->chunk;
-    if (c >= 2) DSB_CUDA(cudaStreamWaitEvent(pl->s_in, pl->e_run[s], 0));   // dx[s] no longer read
-    DSB_CUDA(cudaMemcpyAsync(pl->dx[s], xh + b0 * x_row, nb * x_row, cudaMemcpyHostToDevice, pl->s_in));
-    DSB_CUDA(cudaEventRecord(pl->e_in[s], pl->s_in));
-    DSB_CUDA(cudaStreamWaitEvent(pl->s_run, pl->e_in[s], 0));
-    if (c >= 2) DSB_CUDA(cudaStreamWaitEvent(pl->s_run, pl->e_out[s], 0));  // dy[s] drained
+    if (c >= 2) DSB_PIPE(cudaStreamWaitEvent(pl->s_in, pl->e_run[s], 0));   // dx[s] no longer read
+    DSB_PIPE(cudaMemcpyAsync(pl->dx[s], xh + b0 * x_row, nb * x_row, cudaMemcpyHostToDevice, pl->s_in));
+    DSB_PIPE(cudaEventRecord(pl->e_in[s], pl->s_in));
+    DSB_PIPE(cudaStreamWaitEvent(pl->s_run, pl->e_in[s], 0));
+    if (c >= 2) DSB_PIPE(cudaStreamWaitEvent(pl->s_run, pl->e_out[s], 0));  // dy[s] drained
     const int rc = pl->is_f64 ? dsb200_stft_f64(pl->dx[s], window_dev, pl->dy[s], nb, pl->T, &pl->p, pl->device, pl->s_run)
                               : dsb200_stft_f32(pl->dx[s], window_dev, pl->dy[s], nb, pl->T, &pl->p, pl->device, pl->s_run);
-    if (rc != DSB200_OK) return rc;
-    DSB_CUDA(cudaEventRecord(pl->e_run[s], pl->s_run));
-    DSB_CUDA(cudaStreamWaitEvent(pl->s_out, pl->e_run[s], 0));
-    DSB_CUDA(cudaMemcpyAsync(yh + b0 * y_row, pl->dy[s], nb * y_row, cudaMemcpyDeviceToHost, pl->s_out));
-    DSB_CUDA(cudaEventRecord(pl->e_out[s], pl->s_out));
+    if (rc != DSB200_OK) return drain(rc);
+    DSB_PIPE(cudaEventRecord(pl->e_run[s], pl->s_run));
+    DSB_PIPE(cudaStreamWaitEvent(pl->s_out, pl->e_run[s], 0));
+    DSB_PIPE(cudaMemcpyAsync(yh + b0 * y_row, pl->dy[s], nb * y_row, cudaMemcpyDeviceToHost, pl->s_out));
+    DSB_PIPE(cudaEventRecord(pl->e_out[s], pl->s_out));
   }
+#undef DSB_PIPE
   DSB_CUDA(cudaStreamSynchronize(pl->s_out));
   DSB_CUDA(cudaStreamSynchronize(pl->s_run));
   DSB_CUDA(cudaStreamSynchronize(pl->s_in));

@@ -31,6 +31,7 @@
 
 #include "bulk.cuh"
 #include "fft16.cuh"
+#include "mfcc_plan.h"
 
 namespace dsb200 {
 namespace {
@@ -47,6 +48,8 @@ constexpr int kOutFloats = 4 * 257;                    // one quad of real-value
 constexpr int kDefaultBulkStore = 1;                   // see stft512_try (DSB200_STFT_STORE)
 constexpr int kDefaultWarpsV7 = 20;                    // see stft512_try (DSB200_STFT_W)
 constexpr int kDefaultVariant = 1;                     // see stft512_try (DSB200_STFT_V)
+
+constexpr int kMaxDst = 8;     // destinations of one feature row (ranks of the fused all-gather)
 
 struct Args {
   const float* x;
@@ -71,15 +74,30 @@ struct Args {
   const float* mf_lifter;  // [M + 1]
   int mf_C, mf_M, mf_format, mf_D;
   float mf_floor, mf_gamma;
+  const int32_t* mf_plan;  // device copy of the host-built segment plan (mfcc_plan.cu), or nullptr
+  // Destinations of the feature rows: y_dst[0 .. n_dst) all receive every row of this launch at row offset
+  // mf_row_off.  One entry (the caller's tensor) normally; with the all-gather fused into the epilogue, the same
+  // tensor in every rank's memory (NVLink peer mappings) or its NVSwitch multicast address.
+  float* y_dst[kMaxDst];
+  int n_dst, mf_vec;       // mf_vec: every destination is 16-byte aligned (128-bit stores of whole quads)
+  int64_t mf_row_off;
 };
 
 constexpr int kFmtMfcc = 5;  // internal: stage amplitudes, then filter bank + DCT + lifter on chip
-constexpr int kSegLen = 8;     // bins per filter-bank segment
-constexpr int kMaxSeg = 128;   // segments the fast filter-bank path can hold (40 mel filters at 512 bins: ~85)
-constexpr int kAmpPitch = 264; // float2 units per staged amplitude row: 257 bins + zero padding for segment tails
+constexpr int kSegLen = kPlanSegLen;     // bins per filter-bank segment
+constexpr int kMaxSeg = kPlanMaxSeg;     // segment slots of the fast filter-bank path (40 mel filters at 512 bins: ~85)
+constexpr int kAmpPitch = kPlanAmpPitch; // float2 units per staged amplitude row: 257 bins + zero padding for segment tails
+constexpr int kSlotsPerCh = kPlanSlotsPerCh;
 
+// shared-memory tables of the MFCC epilogue: W^T [C][M+1] | lifter [M+1] | seg_start [kMaxSeg] | channel_slots
+// [C][kSlotsPerCh] | segment weights [kSegLen][kMaxSeg] | info [4]
 __host__ __device__ constexpr int mf_table_floats(int C, int M) {
-  return (C * (M + 1) + (M + 1) + 2 * C + kMaxSeg + (C + 1) + kSegLen * kMaxSeg + 4 + 3) & ~3;
+  return (C * (M + 1) + (M + 1) + kMaxSeg + C * kSlotsPerCh + kSegLen * kMaxSeg + 4 + 3) & ~3;
+}
+// per-warp scratch of the epilogue, in floats: two amplitude rows, segment sums (+ one zero entry), mel rows, and
+// the quad's finished feature rows
+__host__ __device__ constexpr int mf_warp_floats(int C, int D) {
+  return 4 * kAmpPitch + 4 * (kMaxSeg + 1) + 4 * C + ((4 * D + 3) & ~3);
 }
 
 template <int FMT>
@@ -156,7 +174,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw) + 2 * warp;
   float* win = reinterpret_cast<float*>(smem_raw + 16 * kWarps);
   float2* htw = reinterpret_cast<float2*>(win + 512);  // [128]
-  // MFCC tables (FMT == kFmtMfcc only), see mf_table_floats(): W^T | lifter | cb | ce | seg_k0 | chs | wT | info
+  // MFCC tables (FMT == kFmtMfcc only), see mf_table_floats()
   float2* tw16 = htw + 128;                            // [16 k2][16 l] (TWS only)
   float* mfW = reinterpret_cast<float*>(tw16 + (TWS ? 256 : 0));
   const int mf_floats = (FMT == kFmtMfcc) ? mf_table_floats(A.mf_C, A.mf_M) : 0;
@@ -193,44 +211,61 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     htw[i] = make_float2(0.5f * v.x, 0.5f * v.y);
   }
   float* mfL = mfW + A.mf_C * (A.mf_M + 1);
-  int* mfcb = reinterpret_cast<int*>(mfL + (A.mf_M + 1));
-  int* mfce = mfcb + A.mf_C;
-  int* seg_k0 = mfce + A.mf_C;            // [kMaxSeg] first bin of each segment (segments of a channel are adjacent)
-  int* chs = seg_k0 + kMaxSeg;            // [C + 1]   first segment of each channel
-  float* wT = reinterpret_cast<float*>(chs + A.mf_C + 1);   // [kSegLen][kMaxSeg] segment weights, zero padded
-  int* mf_info = reinterpret_cast<int*>(wT + kSegLen * kMaxSeg);   // [0] number of segments, 0 = dense fallback
+  int* seg_k0 = reinterpret_cast<int*>(mfL + (A.mf_M + 1));   // [kMaxSeg] first bin a segment reads
+  int* ch_slots = seg_k0 + kMaxSeg;                            // [C][kSlotsPerCh] segments of each filter (kMaxSeg = none)
+  float* wT = reinterpret_cast<float*>(ch_slots + A.mf_C * kSlotsPerCh);   // [kSegLen][kMaxSeg] segment weights
+  int* mf_info = reinterpret_cast<int*>(wT + kSegLen * kMaxSeg);   // [0] number of slots, 0 = dense fallback
   if (FMT == kFmtMfcc) {
     const int C = A.mf_C, M1 = A.mf_M + 1;
+    // scratch for the plan while the tables are built: the staging buffers of warp 0 (idle until the main loop)
+    int* seg_a = reinterpret_cast<int*>(smem_raw + 16 * kWarps + 512 * sizeof(float) +
+                                        (128 + (TWS ? 256 : 0)) * sizeof(float2) + static_cast<size_t>(mf_floats) * 4);
+    int* seg_b = seg_a + kMaxSeg;
+    int* seg_c = seg_b + kMaxSeg;
     for (int i = tid; i < C * M1; i += kThreads) mfW[i] = A.mf_W[(i / M1) * C + (i % M1)];
     for (int i = tid; i < M1; i += kThreads) mfL[i] = A.mf_lifter[i];
-    for (int i = tid; i < C; i += kThreads) { mfcb[i] = A.mf_cb[i]; mfce[i] = A.mf_ce[i]; }
-    for (int i = tid; i < kSegLen * kMaxSeg; i += kThreads) wT[i] = 0.0f;
-    __syncthreads();
-    // Cut every filter's support [cb, ce) into segments of <= kSegLen bins: 32 lanes then work on 32 segments
-    // of all four frames at once instead of walking one whole filter per lane (the mel filters differ 10x in
-    // length).  Filter banks whose segments do not fit (dense / learnable) use the slow general loop.
-    if (tid == 0) {
+    if (A.mf_plan != nullptr) {
+      // host-built plan (mfcc_plan.cu): starts and slots chosen so that a half-warp's 64-bit loads of the
+      // amplitude rows fall into distinct banks
+      const int32_t* P = A.mf_plan;
+      for (int i = tid; i < kMaxSeg; i += kThreads) {
+        seg_k0[i] = P[4 + i];
+        seg_a[i] = P[4 + kMaxSeg + i];
+        seg_b[i] = P[4 + 2 * kMaxSeg + i];
+        seg_c[i] = P[4 + 3 * kMaxSeg + i];
+      }
+      for (int i = tid; i < C * kSlotsPerCh; i += kThreads) ch_slots[i] = P[4 + 4 * kMaxSeg + i];
+      if (tid == 0) mf_info[0] = (P[1] == C) ? P[0] : 0;
+    } else if (tid == 0) {
+      // no plan: cut every filter's support [cb, ce) in order into segments of <= kSegLen bins
       int n = 0;
       bool fits = true;
       for (int c = 0; c < C; ++c) {
-        chs[c] = n;
-        for (int k = mfcb[c]; k < mfce[c]; k += kSegLen) {
-          if (n < kMaxSeg) seg_k0[n] = k;
-          else fits = false;
-          ++n;
+        int t = 0;
+        const int cb = A.mf_cb[c], ce = A.mf_ce[c];
+        for (int k = cb; k < ce; k += kSegLen, ++t, ++n) {
+          if (n < kMaxSeg && t < kSlotsPerCh) {
+            seg_k0[n] = k;
+            seg_a[n] = k;
+            seg_b[n] = (k + kSegLen < ce) ? k + kSegLen : ce;
+            seg_c[n] = c;
+            ch_slots[c * kSlotsPerCh + t] = n;
+          } else {
+            fits = false;
+          }
         }
+        for (; t < kSlotsPerCh; ++t) ch_slots[c * kSlotsPerCh + t] = kMaxSeg;
       }
-      chs[C] = n;
-      mf_info[0] = fits ? n : 0;
+      const int ns = (n + 31) & ~31;
+      for (int i = n; i < ns && i < kMaxSeg; ++i) { seg_k0[i] = 0; seg_c[i] = -1; }
+      mf_info[0] = (fits && n > 0) ? ns : 0;
     }
     __syncthreads();
-    const int ns = mf_info[0];
-    for (int c = warp; c < C && ns > 0; c += kWarps)
-      for (int sg = chs[c]; sg < chs[c + 1]; ++sg) {
-        const int k = seg_k0[sg] + lane;
-        if (lane < kSegLen && k < mfce[c]) wT[lane * kMaxSeg + sg] = A.mf_H[k * C + c];
-      }
-    for (int sg = ns + tid; sg < kMaxSeg; sg += kThreads) seg_k0[sg] = 0;   // padding segments: zero weights
+    // segment weights: H[k, c] for the bins the segment owns, zero for the bins it merely reads past
+    for (int i = tid; i < kSegLen * kMaxSeg; i += kThreads) {
+      const int sg = i % kMaxSeg, k = seg_k0[sg] + i / kMaxSeg, c = seg_c[sg];
+      wT[i] = (sg < mf_info[0] && c >= 0 && k >= seg_a[sg] && k < seg_b[sg]) ? A.mf_H[k * C + c] : 0.0f;
+    }
   }
   __syncthreads();  // last CTA-wide barrier (tables + mbarrier init); the main loop has none
 
@@ -442,21 +477,20 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       // Table pointers are re-derived here from an opaque offset: hoisted out of the quad loop they would pin
       // ~12 registers across the register-tight FFT (128 per thread at 16 warps) and spill its loop state.
       uint32_t tbl_off = 16u * kWarps + 512u * sizeof(float) + (128u + (TWS ? 256u : 0u)) * sizeof(float2);
-      int C = A.mf_C, M = A.mf_M;
-      asm volatile("" : "+r"(tbl_off), "+r"(C), "+r"(M));
+      int C = A.mf_C, M = A.mf_M, D = A.mf_D;
+      asm volatile("" : "+r"(tbl_off), "+r"(C), "+r"(M), "+r"(D));
       const int M1 = M + 1;
       const float* mfW = reinterpret_cast<const float*>(smem_raw + tbl_off);
       const float* mfL = mfW + C * M1;
-      const int* mfcb = reinterpret_cast<const int*>(mfL + M1);
-      const int* mfce = mfcb + C;
-      const int* seg_k0 = mfce + C;
-      const int* chs = seg_k0 + kMaxSeg;
-      const float* wT = reinterpret_cast<const float*>(chs + C + 1);
+      const int* seg_k0 = reinterpret_cast<const int*>(mfL + M1);
+      const int* ch_slots = seg_k0 + kMaxSeg;
+      const float* wT = reinterpret_cast<const float*>(ch_slots + C * kSlotsPerCh);
       const int* mf_info = reinterpret_cast<const int*>(wT + kSegLen * kMaxSeg);
       const float2* amp0 = reinterpret_cast<const float2*>(ostage);
       const float2* amp1 = amp0 + kAmpPitch;
-      float4* segsum = reinterpret_cast<float4*>(ostage + 4 * kAmpPitch);   // [kMaxSeg] partial sums, 4 frames
-      float4* mel4 = segsum + kMaxSeg;                                       // [C] log filter-bank outputs
+      float4* segsum = reinterpret_cast<float4*>(ostage + 4 * kAmpPitch);   // [kMaxSeg + 1] partial sums, 4 frames
+      float4* mel4 = segsum + kMaxSeg + 1;                                   // [C] log filter-bank outputs
+      float* orow = reinterpret_cast<float*>(mel4 + C);                      // [4][D] the quad's feature rows
       auto fb_out = [&](int c, float2 u, float2 v) {                         // fbank.py:195-202
         u.x = fmaxf(u.x, A.mf_floor); u.y = fmaxf(u.y, A.mf_floor);
         v.x = fmaxf(v.x, A.mf_floor); v.y = fmaxf(v.y, A.mf_floor);
@@ -471,6 +505,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       const int ns = mf_info[0];
       if (ns > 0) {
         // lane = segment of <= 8 bins of one filter; 32 segments x 4 frames per round
+        if (lane == 0) segsum[kMaxSeg] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);   // "no segment"
         for (int s0 = 0; s0 < ns; s0 += 32) {
           const int sg = s0 + lane;
           const float2* p0 = amp0 + seg_k0[sg];
@@ -487,10 +522,12 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         __syncwarp();
         for (int c = lane; c < C; c += 32) {
           float2 u = make_float2(0.0f, 0.0f), v = u;
-          for (int sg = chs[c]; sg < chs[c + 1]; ++sg) {
-            const float4 t = segsum[sg];
-            u = add2(u, make_float2(t.x, t.y));
-            v = add2(v, make_float2(t.z, t.w));
+          const int* sl = ch_slots + c * kSlotsPerCh;
+#pragma unroll 2
+          for (int t = 0; t < kSlotsPerCh && sl[t] < kMaxSeg; ++t) {
+            const float4 q4 = segsum[sl[t]];
+            u = add2(u, make_float2(q4.x, q4.y));
+            v = add2(v, make_float2(q4.z, q4.w));
           }
           fb_out(c, u, v);
         }
@@ -498,7 +535,8 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         // general filter bank (dense / learnable supports): lane = channel, weights from global memory
         for (int c = lane; c < C; c += 32) {
           float2 u = make_float2(0.0f, 0.0f), v = u;
-          for (int k = mfcb[c]; k < mfce[c]; ++k) {
+          const int k0 = A.mf_cb != nullptr ? A.mf_cb[c] : 0, k1 = A.mf_ce != nullptr ? A.mf_ce[c] : 257;
+          for (int k = k0; k < k1; ++k) {
             const float w = A.mf_H[k * C + c];
             u = fma2s(amp0[k], w, u);
             v = fma2s(amp1[k], w, v);
@@ -525,9 +563,9 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       }
       __syncwarp();
       // DCT-II columns 0..M (lane l), the channel range split between the half-warps, then lifter and
-      // y | yE | yc | ycE packing; half-warp h writes frames 2h, 2h + 1.
-      float* outA = A.y + (row0 + hf) * A.mf_D;
-      float* outB = outA + kFB * A.mf_D;
+      // y | yE | yc | ycE packing into the quad's staged rows; half-warp h owns frames hf, hf + kFB.
+      float* outA = orow + hf * D;
+      float* outB = outA + kFB * D;
       const int ch = (C + 1) >> 1, c0 = h * ch, c1 = (c0 + ch < C) ? c0 + ch : C;
       for (int m0 = 0; m0 < M1; m0 += 16) {
         const int m = m0 + l;
@@ -562,15 +600,31 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
           int pos = m - 1;
           if (m == 0) pos = (A.mf_format == DSB200_MFCC_YC || A.mf_format == DSB200_MFCC_YCE) ? M : -1;
           if (pos >= 0) {
-            if (vA) outA[pos] = acc.x;
-            if (vB) outB[pos] = acc.y;
+            outA[pos] = acc.x;
+            outB[pos] = acc.y;
           }
         }
       }
       if (l == 0 && want_e) {
         const int pos = (A.mf_format == DSB200_MFCC_YE) ? M : M + 1;
-        if (vA) outA[pos] = En.x;
-        if (vB) outB[pos] = En.y;
+        outA[pos] = En.x;
+        outB[pos] = En.y;
+      }
+      __syncwarp();
+      // The quad's rows are contiguous in the output (4 D floats at row row0): whole quads leave as 128-bit
+      // stores, D lanes x 16 bytes, to every destination (the local tensor; with the all-gather fused in, every
+      // rank's copy over NVLink, or the multicast address that the switch replicates).
+      const int64_t off = (A.mf_row_off + row0) * D;
+      if (A.mf_vec && rows == 4 && ((off & 3) == 0)) {
+        for (int i = lane; i < D; i += 32) {
+          const float4 v4 = reinterpret_cast<const float4*>(orow)[i];
+          for (int d = 0; d < A.n_dst; ++d) reinterpret_cast<float4*>(A.y_dst[d] + off)[i] = v4;
+        }
+      } else {
+        for (int i = lane; i < rows * D; i += 32) {
+          const float v1 = orow[i];
+          for (int d = 0; d < A.n_dst; ++d) A.y_dst[d][off + i] = v1;
+        }
       }
       __syncwarp();
     } else if (staged) {
@@ -710,20 +764,22 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
   return launch_fmt<16, true, kWarpsMfcc>(A, p->spec.out_format, smem, device, stream);
 }
 
-// Fused waveform -> STFT power -> MFCC (stft.py:237-241 + mfcc.py:243-256) in the same kernel.
+// Fused waveform -> STFT power -> MFCC (stft.py:237-241 + mfcc.py:243-256) in the same kernel.  `plan` (device,
+// optional) is the host-built segment plan of mfcc_plan.cu; the rows go to y_dst[0 .. n_dst) at row `row_off`.
 int mfcc_wave_try(const float* x, const float* window, const float* H, const int32_t* cb, const int32_t* ce,
-                  const float* W, const float* lifter, float* y, int64_t batch, int64_t T_len,
-                  const dsb200_stft_params* sp, const dsb200_mfcc_params* mp, int device, cudaStream_t stream) {
-  if (sp->spec.out_format != DSB200_SPEC_POWER || cb == nullptr || ce == nullptr) return DSB200_E_UNSUPPORTED;
+                  const float* W, const float* lifter, const int32_t* plan, float* const* y_dst, int n_dst,
+                  int64_t row_off, int64_t batch, int64_t T_len, const dsb200_stft_params* sp,
+                  const dsb200_mfcc_params* mp, int device, cudaStream_t stream) {
+  if (sp->spec.out_format != DSB200_SPEC_POWER || n_dst < 1 || n_dst > kMaxDst) return DSB200_E_UNSUPPORTED;
   const int C = mp->fbank.n_channel, M = mp->mfcc_order;
   if (C > 128 || M >= C || mp->fbank.fft_length != 512) return DSB200_E_UNSUPPORTED;
   Args A{};
   int NJ = 16;
-  if (int rc = setup_args(A, x, window, y, batch, T_len, sp, device, stream, &NJ)) return rc;
+  if (int rc = setup_args(A, x, window, y_dst[0], batch, T_len, sp, device, stream, &NJ)) return rc;
   const int mf_floats = mf_table_floats(C, M);
-  // segment sums [kMaxSeg] and mel rows [C] (float4 each) live behind the staged amplitude rows inside the
-  // per-warp exchange region
-  if ((4 * kAmpPitch + 4 * kMaxSeg + 4 * C) * 4 > kXchBytesPerWarp) return DSB200_E_UNSUPPORTED;
+  const int D = M + (mp->out_format == DSB200_MFCC_Y ? 0 : (mp->out_format == DSB200_MFCC_YCE ? 2 : 1));
+  // amplitude rows, segment sums, mel rows and the quad's feature rows live inside the per-warp exchange region
+  if (mf_warp_floats(C, D) * 4 > kXchBytesPerWarp) return DSB200_E_UNSUPPORTED;
   const size_t smem_max = static_cast<size_t>(max_dynamic_smem(device));
   // 16 warps (128 registers) when the tables fit next to 16 warp pipelines, else 12
   static const int warps_knob = [] {   // DSB200_MFCC_WARPS=12|16 (tuning knob, read once)
@@ -742,7 +798,15 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   A.mf_C = C;
   A.mf_M = M;
   A.mf_format = mp->out_format;
-  A.mf_D = M + (mp->out_format == DSB200_MFCC_Y ? 0 : (mp->out_format == DSB200_MFCC_YCE ? 2 : 1));
+  A.mf_D = D;
+  A.mf_plan = (cb != nullptr && ce != nullptr) ? plan : nullptr;
+  A.n_dst = n_dst;
+  A.mf_row_off = row_off;
+  A.mf_vec = 1;
+  for (int d = 0; d < n_dst; ++d) {
+    A.y_dst[d] = y_dst[d];
+    if (reinterpret_cast<uintptr_t>(y_dst[d]) & 15) A.mf_vec = 0;
+  }
   A.mf_floor = static_cast<float>(mp->fbank.floor);
   A.mf_gamma = static_cast<float>(mp->fbank.gamma);
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));

@@ -331,6 +331,14 @@ def _mfcc_dim(M: int, out_format: int) -> int:
     return M + (0, 1, 1, 2)[out_format]
 
 
+def _check_mfcc_tables(K: int, Cn: int, W: Tensor, M: int) -> None:
+    """Table shapes the kernels index without bounds checks: ``H [K, C]``, ``W [C, C]``, lifter ``[M + 1]``."""
+    if W.dim() != 2 or W.shape[0] != Cn or W.shape[1] != Cn:   # the kernels read W with row pitch C (dct.py:135-137)
+        raise ValueError(f"DCT matrix must be [{Cn}, {Cn}] for a {Cn}-channel filter bank, got {tuple(W.shape)}.")
+    if M + 1 > Cn:   # mfcc.py:165-166
+        raise ValueError("mfcc_order must be less than n_channel.")
+
+
 @torch.library.custom_op(f"{_NS}::mfcc", mutates_args=(), device_types="cuda")
 def mfcc(x: Tensor, H: Tensor, col_begin: Optional[Tensor], col_end: Optional[Tensor], W: Tensor,
          lifter: Tensor, floor: float, gamma: float, out_format: int) -> Tensor:
@@ -338,6 +346,9 @@ def mfcc(x: Tensor, H: Tensor, col_begin: Optional[Tensor], col_end: Optional[Te
     xc, Hc, Wc, lc = _prep(x, dt), _prep(H, dt), _prep(W, dt), _prep(lifter, dt)
     K, Cn = Hc.shape
     M = lc.shape[-1] - 1
+    _check_mfcc_tables(K, Cn, Wc, M)
+    if xc.shape[-1] != K:   # mfcc.py:243 -> fbank.py:305 check_size
+        raise ValueError(f"dimension of input must be {K}, but got {xc.shape[-1]}.")
     rows = xc.numel() // max(K, 1)
     y = torch.empty((*xc.shape[:-1], _mfcc_dim(M, out_format)), device=x.device, dtype=dt)
     p = N.MfccParams(N.FbankParams(2 * (K - 1), Cn, 0, 0, float(floor), float(gamma)), M, out_format)
@@ -352,32 +363,96 @@ def _(x, H, col_begin, col_end, W, lifter, floor, gamma, out_format):
     return x.new_empty((*x.shape[:-1], _mfcc_dim(lifter.shape[-1] - 1, out_format)), dtype=_native_dtype(x, H))
 
 
-@torch.library.custom_op(f"{_NS}::mfcc_wave", mutates_args=(), device_types="cuda")
-def mfcc_wave(x: Tensor, window: Tensor, H: Tensor, col_begin: Optional[Tensor], col_end: Optional[Tensor],
-              W: Tensor, lifter: Tensor, frame_period: int, fft_length: int, center: bool, zmean: bool,
-              pad_mode: int, eps: float, floor: float, gamma: float, out_format: int) -> Tensor:
+MAX_GATHER_PEERS = 8   # destinations of one feature row in dsb200_mfcc_wave_ex
+
+
+def mfcc_plan(col_begin: Optional[Tensor], col_end: Optional[Tensor], n_bins: int) -> Optional[Tensor]:
+    """Segment plan of the fused MFCC kernel's filter-bank stage (``dsb200_mfcc_plan_build``): built on the host
+    from the filter supports (one device->host copy of 2 C integers), cached on the ``col_begin`` tensor object, so
+    a module or a memoised functional table pays for it once.  None when there is no support or no plan."""
+    if col_begin is None or col_end is None:
+        return None
+    cached = getattr(col_begin, "_dsb200_plan", None)
+    if cached is not None and cached[0] is col_end:
+        return cached[1]
+    cb = col_begin.detach().to("cpu", torch.int32).contiguous()
+    ce = col_end.detach().to("cpu", torch.int32).contiguous()
+    Cn = cb.numel()
+    lib = N.load()
+    plan = torch.zeros(int(lib.dsb200_mfcc_plan_ints(Cn)), dtype=torch.int32)
+    i32p = C.POINTER(C.c_int32)
+    N.check(lib.dsb200_mfcc_plan_build(C.cast(cb.data_ptr(), i32p), C.cast(ce.data_ptr(), i32p), Cn, int(n_bins),
+                                       C.cast(plan.data_ptr(), i32p)))
+    out = plan.to(col_begin.device) if int(plan[0]) > 0 else None
+    try:
+        col_begin._dsb200_plan = (col_end, out)
+    except Exception:
+        pass
+    return out
+
+
+def _mfcc_wave_call(x, window, H, col_begin, col_end, W, lifter, plan, dst_ptrs, row_offset, frame_period,
+                    fft_length, center, zmean, pad_mode, eps, floor, gamma, out_format):
+    """Shared launcher of ``mfcc_wave`` (one destination) and ``mfcc_wave_gather`` (one per rank)."""
     dt = _native_dtype(x, window, H)
     xc, wc, Hc, Wc, lc = (_prep(t, dt) for t in (x, window, H, W, lifter))
     T = xc.shape[-1]
     B = xc.numel() // max(T, 1)
-    n = num_frames(T, frame_period)
     K, Cn = Hc.shape
     M = lc.shape[-1] - 1
-    y = torch.empty((*xc.shape[:-1], n, _mfcc_dim(M, out_format)), device=x.device, dtype=dt)
+    _check_mfcc_tables(K, Cn, Wc, M)
+    if K != fft_length // 2 + 1:   # the reference's MFCC raises when its fft_length differs from the STFT's (fbank.py:305)
+        raise ValueError(f"dimension of input must be {K}, but got {fft_length // 2 + 1}.")
     sp = N.StftParams(_frame_params(wc.shape[-1], frame_period, center, zmean, pad_mode),
                       _spec_params(fft_length, 3, eps, None))
     mp = N.MfccParams(N.FbankParams(fft_length, Cn, 0, 0, float(floor), float(gamma)), M, out_format)
-    N.check(N.typed("dsb200_mfcc_wave", dt == torch.float64)(
-        _ptr(xc), _ptr(wc), _ptr(Hc), _ptr(col_begin), _ptr(col_end), _ptr(Wc), _ptr(lc), _ptr(y), B, T,
-        C.byref(sp), C.byref(mp), _dev(x), _stream(x)))
+    dst = (C.c_void_p * len(dst_ptrs))(*dst_ptrs)
+    N.check(N.typed("dsb200_mfcc_wave_ex", dt == torch.float64)(
+        _ptr(xc), _ptr(wc), _ptr(Hc), _ptr(col_begin), _ptr(col_end), _ptr(Wc), _ptr(lc), _ptr(plan), dst,
+        len(dst_ptrs), int(row_offset), B, T, C.byref(sp), C.byref(mp), _dev(x), _stream(x)))
+
+
+@torch.library.custom_op(f"{_NS}::mfcc_wave", mutates_args=(), device_types="cuda")
+def mfcc_wave(x: Tensor, window: Tensor, H: Tensor, col_begin: Optional[Tensor], col_end: Optional[Tensor],
+              W: Tensor, lifter: Tensor, frame_period: int, fft_length: int, center: bool, zmean: bool,
+              pad_mode: int, eps: float, floor: float, gamma: float, out_format: int,
+              plan: Optional[Tensor] = None) -> Tensor:
+    dt = _native_dtype(x, window, H)
+    n = num_frames(x.shape[-1], frame_period)
+    y = torch.empty((*x.shape[:-1], n, _mfcc_dim(lifter.shape[-1] - 1, out_format)), device=x.device, dtype=dt)
+    if y.numel():
+        _mfcc_wave_call(x, window, H, col_begin, col_end, W, lifter, plan, [y.data_ptr()], 0, frame_period,
+                        fft_length, center, zmean, pad_mode, eps, floor, gamma, out_format)
     return y
 
 
 @mfcc_wave.register_fake
 def _(x, window, H, col_begin, col_end, W, lifter, frame_period, fft_length, center, zmean, pad_mode, eps,
-      floor, gamma, out_format):
+      floor, gamma, out_format, plan=None):
     return x.new_empty((*x.shape[:-1], num_frames(x.shape[-1], frame_period),
                         _mfcc_dim(lifter.shape[-1] - 1, out_format)), dtype=_native_dtype(x, window, H))
+
+
+def mfcc_wave_gather(x: Tensor, out: Tensor, dst_ptrs, row_offset: int, window: Tensor, H: Tensor, col_begin, col_end,
+                     W: Tensor, lifter: Tensor, frame_period: int, fft_length: int, center: bool, zmean: bool,
+                     pad_mode: int, eps: float, floor: float, gamma: float, out_format: int, plan=None) -> Tensor:
+    """Forward-only ``mfcc_wave`` whose rows land at row ``row_offset`` of ``out`` as mapped on every address in
+    ``dst_ptrs`` (this rank's own tensor, its peers' mappings, or one multicast address): the all-gather of
+    batch-sharded features inside the kernel's stores (``dsb200_mfcc_wave_ex``).  Synchronisation across ranks is
+    the caller's (``distributed.FusedGatherMfcc``)."""
+    if not 1 <= len(dst_ptrs) <= MAX_GATHER_PEERS:
+        raise ValueError(f"between 1 and {MAX_GATHER_PEERS} destinations")
+    if out.dtype != torch.float32 or not out.is_contiguous() or x.dim() != 2:
+        raise ValueError("out must be a contiguous float32 tensor and x a [batch, T] tensor")
+    n = num_frames(x.shape[-1], frame_period)
+    D = _mfcc_dim(lifter.shape[-1] - 1, out_format)
+    if out.shape[-1] != D or (row_offset + x.shape[0] * n) * D > out.numel():
+        raise ValueError("out is too small for the rows of this call")
+    _no_grad_check(x, window, H)
+    if x.numel():
+        _mfcc_wave_call(x, window, H, col_begin, col_end, W, lifter, plan, [int(p) for p in dst_ptrs], row_offset,
+                        frame_period, fft_length, center, zmean, pad_mode, eps, floor, gamma, out_format)
+    return out
 
 
 # ------------------------------------------------------------------------- host-buffer pipeline
@@ -390,6 +465,9 @@ class HostStftPipeline:
         if not window.is_cuda:
             raise RuntimeError("the window table must live on the CUDA device")
         self.window = window.contiguous()
+        # the pipeline runs on its own non-blocking streams: make sure the table (possibly just produced on the
+        # current torch stream) is complete before any of them can read it
+        torch.cuda.current_stream(window.device).synchronize()
         self.is_f64 = window.dtype == torch.float64
         self.T, self.N, self.K = T, num_frames(T, frame_period), fft_length // 2 + 1
         self.out_format = out_format
@@ -700,7 +778,7 @@ torch.library.register_autograd(f"{_NS}::mfcc", _mfcc_bwd, setup_context=_mfcc_s
 
 def _mfcc_wave_setup(ctx, inputs, output):
     (x, window, H, cb, ce, W, lifter, frame_period, fft_length, center, zmean, pad_mode, eps, floor, gamma,
-     out_format) = inputs
+     out_format, _plan) = inputs
     ctx.save_for_backward(x, window, H, cb, ce, W, lifter)
     ctx.stft_args = (frame_period, fft_length, center, zmean, pad_mode, eps, -1.0, 3)
     ctx.rest = (floor, gamma, out_format)
@@ -715,7 +793,7 @@ def _mfcc_wave_bwd(ctx, g):
         gP, gH = _mfcc_grad_to_spectrum(g, P, H, cb, ce, W, lifter, *ctx.rest, want_gH=ctx.needs_input_grad[2])
         need_gw = ctx.needs_input_grad[1]
         gx, gw = stft_backward(x, window, gP, *ctx.stft_args, need_gw)
-    return (_like_input(gx, x), gw.to(window.dtype) if need_gw else None, gH) + (None,) * 13
+    return (_like_input(gx, x), gw.to(window.dtype) if need_gw else None, gH) + (None,) * 14
 
 
 torch.library.register_autograd(f"{_NS}::mfcc_wave", _mfcc_wave_bwd, setup_context=_mfcc_wave_setup)

@@ -200,6 +200,28 @@ DSB200_DECL2(dsb200_mfcc_wave, (const void* x, const void* window, const void* H
                                 int64_t batch, int64_t T, const dsb200_stft_params* sp,
                                 const dsb200_mfcc_params* mp, int device, void* stream))
 
+/* dsb200_mfcc_wave with two extras of the B200 build.
+ *  (1) `plan`: optional device copy of dsb200_mfcc_plan_build()'s output -- where each filter's support is cut and
+ *      which lane walks which piece, chosen on the host so that the kernel's shared-memory loads are free of bank
+ *      conflicts (NULL: the kernel cuts the supports in order).
+ *  (2) `y_dst[0 .. n_dst)` (HOST array of DEVICE pointers) + `row_offset`: every feature row r of this call is
+ *      written to y_dst[d] + (row_offset + r) * D for all d.  With n_dst = 1 this is dsb200_mfcc_wave.  With the
+ *      output tensor mapped on several GPUs (CUDA IPC / symmetric memory peer pointers, or ONE NVSwitch multicast
+ *      pointer) the all-gather of batch-sharded features happens inside the kernel's
+ *      epilogue: 128-bit stores over NVLink, quad by quad, overlapped with the remaining math.  The caller owns
+ *      the cross-rank synchronisation (a barrier before the buffers are rewritten and after the kernel ends). */
+DSB200_DECL2(dsb200_mfcc_wave_ex, (const void* x, const void* window, const void* H, const int32_t* col_begin,
+                                   const int32_t* col_end, const void* W, const void* lifter, const int32_t* plan,
+                                   void* const* y_dst, int32_t n_dst, int64_t row_offset, int64_t batch, int64_t T,
+                                   const dsb200_stft_params* sp, const dsb200_mfcc_params* mp, int device,
+                                   void* stream))
+/* Host-side planner for (1): col_begin / col_end are HOST copies of the filter supports (fbank.py:233-293 builds
+ * H; its non-zero rows per column), n_bins = L/2+1; `plan` receives dsb200_mfcc_plan_ints(n_channel) int32 values
+ * (plan[0] = slots used, 0 = "no plan possible", plan[2] = bank conflicts the planner could not avoid). */
+DSB200_API int32_t dsb200_mfcc_plan_ints(int32_t n_channel);
+DSB200_API int dsb200_mfcc_plan_build(const int32_t* col_begin, const int32_t* col_end, int32_t n_channel,
+                                      int32_t n_bins, int32_t* plan);
+
 /* ---- backward (vector-Jacobian products; SURVEY.md section 8f rank 1: the reference is differentiable) ----
  * The forward kernels are fused, so torch autograd cannot see inside them; these are their adjoints.  Nothing
  * is saved by the forward pass: each row's spectrum is recomputed on chip.  gx / gw are overwritten. */

@@ -15,17 +15,29 @@ def _run(extra_env, *args):
                           text=True, timeout=600, cwd=ROOT)
 
 
-def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    r = _run({}, "--impl", "reference", "--workload", "lpc2par", "--steps", "1", "--warmup", "1")
+import pytest
+
+
+@pytest.mark.parametrize("port", [True, False])
+def test_reference_arm_prints_one_json_line_with_the_contract_keys(port):
+    """Both CPU arms (the numpy oracle port; the reference's own modules when baseline/_ref or
+    $DIFFSPTK_REFERENCE_ROOT holds the package) print the contract's line with the native arm's config keys."""
+    sys.path.insert(0, ROOT)
+    import bench
+    r = _run({}, "--impl", "reference", "--workload", "lpc2par", "--steps", "1", "--warmup", "1",
+             *(["--port"] if port else []))
     assert r.returncode == 0, r.stderr[-500:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["unit"] == "frames/s" and j["higher_is_better"] is True
     assert j["metric"].startswith("frames/sec") and j["value"] > 0 and j["n_gpus"] == 1
-    assert j["vs_baseline"] is None and j["data"] == "synthetic" and "workload" in j["config"]
+    assert j["vs_baseline"] is None and j["data"] == "synthetic"
+    assert j["config"] == bench.workload_config("lpc2par")        # identical keys and values in both arms
     cb = j["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == j["value"]
+    have_ref = bench.load_reference_package()[0] is not None
+    assert cb["kind"] == ("port" if port or not have_ref else "reference")
+    assert cb["cores"] >= 1 and cb["sample"] and cb["value"] == j["value"]
     assert j["e2e"] == {"value": j["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

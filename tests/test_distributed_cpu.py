@@ -24,6 +24,18 @@ def test_shard_bounds_partition():
         shard_bounds(4, 2, 2)
 
 
+def test_shard_rows_is_a_partition_in_gather_order():
+    from diffsptk_b200.distributed import shard_rows
+    for n, w, k in ((8, 2, 1), (8, 2, 2), (24, 4, 3), (6, 2, 3), (8192, 8, 4)):
+        rows = [shard_rows(n, r, w, k) for r in range(w)]
+        assert sorted(torch.cat(rows).tolist()) == list(range(n))
+        assert all(len(x) == n // w for x in rows)
+        if k == 1:
+            assert all(rows[r].tolist() == list(range(r * n // w, (r + 1) * n // w)) for r in range(w))
+    with pytest.raises(ValueError):
+        shard_rows(7, 0, 2)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -34,7 +46,7 @@ def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from diffsptk_b200.distributed import shard, sharded_features
+        from diffsptk_b200.distributed import shard, shard_rows, sharded_features
         from oracle import np_oracle as O
 
         g = torch.Generator().manual_seed(0)
@@ -44,12 +56,18 @@ def _worker(rank, world, port, q):
             P = O.stft(xl.numpy(), frame_length=400, frame_period=80, fft_length=512)
             return torch.from_numpy(O.mfcc(P, 13, 40, 16000))
 
+        want = feat(x)
         xl = shard(x)
         assert xl.shape[0] == 3
-        full = sharded_features(feat, xl, n_chunks=2)
         local = sharded_features(feat, xl, gather=False)
-        want = feat(x)
-        ok = bool(torch.equal(full, want)) and bool(torch.equal(local, want[rank * 3:(rank + 1) * 3]))
+        ok = bool(torch.equal(local, want[rank * 3:(rank + 1) * 3]))
+        # one chunk: the contiguous partition, one in-place all_gather_into_tensor
+        ok = ok and bool(torch.equal(sharded_features(feat, xl, n_chunks=1), want))
+        # chunked gathers overlap compute; their slabs are contiguous under the block-cyclic partition
+        for n_chunks in (2, 3):
+            rows = shard_rows(6, rank, world, n_chunks)
+            full = sharded_features(feat, x[rows], n_chunks=n_chunks)
+            ok = ok and bool(torch.equal(full, want))
         q.put((rank, ok, tuple(full.shape)))
     finally:
         dist.destroy_process_group()
