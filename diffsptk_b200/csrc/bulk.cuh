@@ -76,4 +76,31 @@ __device__ __forceinline__ bool stage_span(const float* xb, int T, int s0, int s
   return false;
 }
 
+// Out-of-line copy of stage_span<true> for the pipelines' hot loops: interior spans (all but the first and last
+// few of an utterance) take a ten-instruction bulk-copy path inline, everything else -- zero fill, the four pad
+// modes, unaligned waveforms -- lives behind one call instead of being inlined into the loop (round 1: the inlined
+// general path was ~20 % of stft512's static code and most of its per-quad branch and integer overhead).
+static __device__ __noinline__ void stage_span_slow(const float* xb, int T, int s0, int span, int pad_mode, bool bulk_ok,
+                                             float* dst, uint64_t* bar, int lane) {
+  stage_span<true>(xb, T, s0, span, pad_mode, bulk_ok, dst, bar, lane);
+}
+
+__device__ __forceinline__ void stage_span_fast(const float* xb, int T, int s0, int span, int pad_mode, bool bulk_ok,
+                                                float* dst, uint64_t* bar, int lane) {
+#ifdef DSB200_STAGE_INLINE   // A/B knob: the round-1 code shape (general path inlined into the loop)
+  stage_span<true>(xb, T, s0, span, pad_mode, bulk_ok, dst, bar, lane);
+  return;
+#endif
+  if (bulk_ok && s0 >= 0 && s0 + span <= T) {
+    if (lane == 0) {
+      fence_async_smem();
+      const uint32_t bytes = static_cast<uint32_t>(span) * 4u;
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(dst, xb + s0, bytes, bar);
+    }
+  } else {
+    stage_span_slow(xb, T, s0, span, pad_mode, bulk_ok, dst, bar, lane);
+  }
+}
+
 }  // namespace dsb200

@@ -40,7 +40,7 @@ constexpr int kK = 257;
 constexpr int kDM = 25;              // max cepstral dimension (M + 1)
 constexpr int kJS = 49;              // row stride of Hm in shared memory (odd: conflict-free), = 2 * 24 + 1
 constexpr int kPS = 25;              // row stride of P0 in shared memory (odd)
-constexpr int kWarpFloats = kDM * 8 + 4 * kJS * 2 + 256 + 256 + 8;   // per-warp scratch: mc, rt, pivot column, solution, rhs
+constexpr int kWarpFloats = kDM * 8 + 4 * kJS * 2 + 512 + 256 + 8;   // per-warp scratch: mc, rt, pivot column, solution, rhs
 
 struct MArgs {
   const float* x;    // [rows, 257] power spectrum
@@ -95,7 +95,7 @@ __device__ __forceinline__ float fast_rcp(float x) {  // MUFU.RCP + one Newton s
 }
 
 // kMW warps per CTA (12: 168 registers per thread, 16: 128); kQ packed frame pairs eliminated per pass.
-template <int kMW, int kQ>
+template <int kMW, int kQ, bool ROLLED>
 __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
   constexpr int kMT = kMW * 32;
   constexpr int kH = kQ / 2;           // float4 groups (two pairs each) exchanged through shared memory
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
   float* wbase = avs + 32 + warp * kWarpFloats;
   float* mcs = wbase;                                    // [kDM][8]   mc[m][frame]
   float2* rts = reinterpret_cast<float2*>(mcs + kDM * 8);   // [4][kJS]  rt[pair][j] = (frame 2p, frame 2p+1)
-  float4* col = reinterpret_cast<float4*>(rts + 4 * kJS);   // [2][32] pivot column (= pivot row, by symmetry), 8 systems
-  float4* xs = col + 64;                                 // [2][32] solution broadcast
+  float4* col = reinterpret_cast<float4*>(rts + 4 * kJS);   // [2][64] pivot column (= pivot row, by symmetry), 8 systems; [32, 64) stay zero
+  float4* xs = col + 128;                                // [2][32] solution broadcast
   float4* pb = xs + 64;                                  // [2]     pivot right-hand sides
 
   // tables -> shared memory (zero padded to 288 bins so that the tail lanes contribute nothing)
@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
   if (tid < 32) avs[tid] = tid < D ? A.av[tid] : 0.0f;
   __syncthreads();
 
+  for (int g = 0; g < 2; ++g) col[64 * g + 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  __syncwarp();
   const int64_t n_oct = (A.rows + 7) / 8;
   for (int64_t oct = static_cast<int64_t>(blockIdx.x) * kMW + warp; oct < n_oct;
        oct += static_cast<int64_t>(gridDim.x) * kMW) {
@@ -256,6 +258,64 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
             b[q] = f2(0, 0);
           }
         }
+        if constexpr (ROLLED) {
+          // ---- Gauss-Jordan in a ROLLED pivot loop (round 2).  The fully unrolled elimination below is ~1 700
+          // instructions per pass, the Newton step ~4 000 = 64 KB of code for 12 warps at different places of it:
+          // `stall_no_inst` was 20 % (profiles/r2_mcep_fast_v2).  Here every row shifts its registers left by one
+          // column per pivot -- register k always holds column pv + k -- so the same ~150 instructions serve all 25
+          // pivots.  Eliminating above the diagonal as well keeps every lane in the loop to the end and removes the
+          // back substitution: x_i = b_i / pivot_i.  The trailing block stays symmetric, so the pivot row is still
+          // read from the column the lanes publish.
+          float2 dinv[kQ];
+#pragma unroll
+          for (int q = 0; q < kQ; ++q) dinv[q] = f2(1, 1);
+#pragma unroll 1
+          for (int pv = 0; pv < kDM; ++pv) {
+#pragma unroll
+            for (int g = 0; g < kH; ++g)
+              col[64 * g + lane] = make_float4(a[2 * g][0].x, a[2 * g][0].y, a[2 * g + 1][0].x, a[2 * g + 1][0].y);
+            if (lane == pv) {
+#pragma unroll
+              for (int g = 0; g < kH; ++g) pb[g] = make_float4(b[2 * g].x, b[2 * g].y, b[2 * g + 1].x, b[2 * g + 1].y);
+            }
+            __syncwarp();
+            const bool piv = lane == pv;
+            float2 f[kQ];
+#pragma unroll
+            for (int g = 0; g < kH; ++g) {
+              const float4 p = col[64 * g + pv];
+              const float2 r0 = f2(fast_rcp(p.x), fast_rcp(p.y)), r1 = f2(fast_rcp(p.z), fast_rcp(p.w));
+              f[2 * g] = piv ? f2(0, 0) : __fmul2_rn(a[2 * g][0], f2(-r0.x, -r0.y));        // -a_ip / a_pp
+              f[2 * g + 1] = piv ? f2(0, 0) : __fmul2_rn(a[2 * g + 1][0], f2(-r1.x, -r1.y));
+              dinv[2 * g] = sel2(piv, r0, dinv[2 * g]);
+              dinv[2 * g + 1] = sel2(piv, r1, dinv[2 * g + 1]);
+            }
+            const int n_left = kDM - 1 - pv;                 // columns pv + 1 .. 24 remain
+#pragma unroll
+            for (int k = 0; k < kDM - 1; ++k) {
+              if ((k & 3) == 0 && k >= n_left) break;        // warp-uniform exit, four columns at a time
+#pragma unroll
+              for (int g = 0; g < kH; ++g) {
+                const float4 cv = col[64 * g + pv + 1 + k];  // entries past column 24 are zero (lanes 25.., padding)
+                a[2 * g][k] = __ffma2_rn(f[2 * g], f2(cv.x, cv.y), a[2 * g][k + 1]);
+                a[2 * g + 1][k] = __ffma2_rn(f[2 * g + 1], f2(cv.z, cv.w), a[2 * g + 1][k + 1]);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < kH; ++g) {
+              const float4 bv = pb[g];
+              b[2 * g] = __ffma2_rn(f[2 * g], f2(bv.x, bv.y), b[2 * g]);
+              b[2 * g + 1] = __ffma2_rn(f[2 * g + 1], f2(bv.z, bv.w), b[2 * g + 1]);
+            }
+            __syncwarp();
+          }
+#pragma unroll
+          for (int g = 0; g < kH; ++g) {
+            const float2 x0 = __fmul2_rn(b[2 * g], dinv[2 * g]), x1 = __fmul2_rn(b[2 * g + 1], dinv[2 * g + 1]);
+            xs[32 * g + lane] = make_float4(x0.x, x0.y, x1.x, x1.y);
+          }
+          __syncwarp();
+        } else {
         // Elimination.  The sub-matrix stays symmetric, so pivot-row entry c == column entry held by lane c:
         // one parallel store publishes the whole pivot row (float4 = two frame pairs).
         float2 dinv[kQ];                                   // 1 / (this lane's own pivot)
@@ -265,7 +325,7 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
           constexpr int pv = decltype(pv_c)::value;
 #pragma unroll
           for (int g = 0; g < kH; ++g)
-            col[32 * g + lane] = make_float4(a[2 * g][pv].x, a[2 * g][pv].y, a[2 * g + 1][pv].x, a[2 * g + 1][pv].y);
+            col[64 * g + lane] = make_float4(a[2 * g][pv].x, a[2 * g][pv].y, a[2 * g + 1][pv].x, a[2 * g + 1][pv].y);
           if (lane == pv) {
 #pragma unroll
             for (int g = 0; g < kH; ++g) pb[g] = make_float4(b[2 * g].x, b[2 * g].y, b[2 * g + 1].x, b[2 * g + 1].y);
@@ -275,7 +335,7 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
           float2 f[kQ];
 #pragma unroll
           for (int g = 0; g < kH; ++g) {
-            const float4 p = col[32 * g + pv];
+            const float4 p = col[64 * g + pv];
             const float2 r0 = f2(fast_rcp(p.x), fast_rcp(p.y)), r1 = f2(fast_rcp(p.z), fast_rcp(p.w));
             f[2 * g] = act ? __fmul2_rn(a[2 * g][pv], f2(-r0.x, -r0.y)) : f2(0, 0);       // -a_ip / a_pp
             f[2 * g + 1] = act ? __fmul2_rn(a[2 * g + 1][pv], f2(-r1.x, -r1.y)) : f2(0, 0);
@@ -287,7 +347,7 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
             for (int c = pv + 1; c < kDM; ++c) {
 #pragma unroll
               for (int g = 0; g < kH; ++g) {
-                const float4 cv = col[32 * g + c];
+                const float4 cv = col[64 * g + c];
                 a[2 * g][c] = __ffma2_rn(f[2 * g], f2(cv.x, cv.y), a[2 * g][c]);
                 a[2 * g + 1][c] = __ffma2_rn(f[2 * g + 1], f2(cv.z, cv.w), a[2 * g + 1][c]);
               }
@@ -323,6 +383,7 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
           }
         });
         __syncwarp();
+        }
         if (i < D) {  // mc += g for the frames of this pass
           float4* mp = reinterpret_cast<float4*>(mcs + i * 8 + pass * kQ * 2);
 #pragma unroll
@@ -347,16 +408,16 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
 
 }  // namespace
 
-template <int kMW, int kQ>
+template <int kMW, int kQ, bool ROLLED>
 static int launch_mcep_fast(const MArgs& A, int device, cudaStream_t stream) {
   const size_t smem = (static_cast<size_t>(kDM) * kKS + kKS * kJS + kKS * kPS + 32 +
                        static_cast<size_t>(kMW) * kWarpFloats) * sizeof(float);
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
-  DSB_CUDA(cudaFuncSetAttribute(mcep_fast_kernel<kMW, kQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DSB_CUDA(cudaFuncSetAttribute(mcep_fast_kernel<kMW, kQ, ROLLED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const int64_t n_oct = (A.rows + 7) / 8;
   const int blocks = static_cast<int>(std::min<int64_t>((n_oct + kMW - 1) / kMW, sm_count(device)));
-  mcep_fast_kernel<kMW, kQ><<<blocks, kMW * 32, smem, stream>>>(A);
+  mcep_fast_kernel<kMW, kQ, ROLLED><<<blocks, kMW * 32, smem, stream>>>(A);
   return after_launch("mcep_fast_kernel");
 }
 
@@ -375,14 +436,16 @@ int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_para
   A.D = p->cep_order + 1;
   A.J = 2 * p->cep_order + 1;
   A.n_iter = p->n_iter;
-  // DSB200_MCEP_V=8x4 | 12x2 | 16x2 (tuning knob, read once): warps per CTA x frame pairs per elimination pass
+  // DSB200_MCEP_V=8 | 120 | 12 | 16 (tuning knob, read once): warps per CTA (x frame pairs per elimination pass:
+  // 4 at 8 warps, else 2); 8 and 120 keep the fully unrolled elimination + back substitution for A/B runs
   static const int variant = [] {
     const char* e = getenv("DSB200_MCEP_V");
     return e != nullptr ? atoi(e) : 12;
   }();
-  if (variant == 8) return launch_mcep_fast<8, 4>(A, device, stream);
-  if (variant == 16) return launch_mcep_fast<16, 2>(A, device, stream);
-  return launch_mcep_fast<12, 2>(A, device, stream);
+  if (variant == 8) return launch_mcep_fast<8, 4, false>(A, device, stream);      // round-1 shape
+  if (variant == 120) return launch_mcep_fast<12, 2, false>(A, device, stream);   // 12 warps, unrolled elimination
+  if (variant == 16) return launch_mcep_fast<16, 2, true>(A, device, stream);
+  return launch_mcep_fast<12, 2, true>(A, device, stream);
 }
 
 }  // namespace dsb200

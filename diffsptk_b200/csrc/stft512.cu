@@ -90,9 +90,10 @@ constexpr int kAmpPitch = kPlanAmpPitch; // float2 units per staged amplitude ro
 constexpr int kSlotsPerCh = kPlanSlotsPerCh;
 
 // shared-memory tables of the MFCC epilogue: W^T [C][M+1] | lifter [M+1] | seg_start [kMaxSeg] | channel_slots
-// [C][kSlotsPerCh] | segment weights [kSegLen][kMaxSeg] | info [4]
+// [C][kSlotsPerCh] (bytes) | segment weights [kSegLen][kMaxSeg] | info [4]
+__host__ __device__ constexpr int mf_slot_words(int C) { return (C * kSlotsPerCh + 3) / 4; }
 __host__ __device__ constexpr int mf_table_floats(int C, int M) {
-  return (C * (M + 1) + (M + 1) + kMaxSeg + C * kSlotsPerCh + kSegLen * kMaxSeg + 4 + 3) & ~3;
+  return (C * (M + 1) + (M + 1) + kMaxSeg + mf_slot_words(C) + kSegLen * kMaxSeg + 4 + 3) & ~3;
 }
 // per-warp scratch of the epilogue, in floats: two amplitude rows, segment sums (+ one zero entry), mel rows, and
 // the quad's finished feature rows
@@ -153,12 +154,17 @@ constexpr int kVPair2 = 1;
 // kernel does not respond to occupancy (nor to a start stagger of the warps that share a scheduler, tried and
 // removed), so variant 1 stays the default and this one is kept as an A/B knob (DSB200_STFT_V=7).
 constexpr int kVSingleBuf = 2, kVTwSmem = 4;
+// 8 = the window slice and the split twiddles of a lane live in registers (26 + 16) instead of being re-read from
+// shared memory for every quad: -21 LDS.64 = -42 shared-memory wavefronts per quad (of ~300); needs the 168-register
+// budget of a 12-warp CTA (round 2 experiment, DSB200_STFT_V=9).
+constexpr int kVRegTables = 8;
 constexpr int kShift = 5;   // 2 * 80 / 32
 
 template <int NJ, bool MASK_ALL, int FMT, int W, int V = 0>
 __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   constexpr int kWarps = W, kThreads = W * 32;
   constexpr bool PAIR2 = (V & kVPair2) != 0, SB = (V & kVSingleBuf) != 0, TWS = (V & kVTwSmem) != 0;
+  constexpr bool RT = (V & kVRegTables) != 0;
   constexpr int kBufs = SB ? 1 : 2;
   constexpr int kFB = PAIR2 ? 2 : 1;        // frame B = frame A + kFB
   constexpr int kRowB = kFB * 257;          // its staged row
@@ -212,8 +218,8 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   }
   float* mfL = mfW + A.mf_C * (A.mf_M + 1);
   int* seg_k0 = reinterpret_cast<int*>(mfL + (A.mf_M + 1));   // [kMaxSeg] first bin a segment reads
-  int* ch_slots = seg_k0 + kMaxSeg;                            // [C][kSlotsPerCh] segments of each filter (kMaxSeg = none)
-  float* wT = reinterpret_cast<float*>(ch_slots + A.mf_C * kSlotsPerCh);   // [kSegLen][kMaxSeg] segment weights
+  uint8_t* ch_slots = reinterpret_cast<uint8_t*>(seg_k0 + kMaxSeg);   // [C][kSlotsPerCh] segments of each filter (kMaxSeg = none)
+  float* wT = reinterpret_cast<float*>(seg_k0 + kMaxSeg + mf_slot_words(A.mf_C));   // [kSegLen][kMaxSeg] segment weights
   int* mf_info = reinterpret_cast<int*>(wT + kSegLen * kMaxSeg);   // [0] number of slots, 0 = dense fallback
   if (FMT == kFmtMfcc) {
     const int C = A.mf_C, M1 = A.mf_M + 1;
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         seg_b[i] = P[4 + 2 * kMaxSeg + i];
         seg_c[i] = P[4 + 3 * kMaxSeg + i];
       }
-      for (int i = tid; i < C * kSlotsPerCh; i += kThreads) ch_slots[i] = P[4 + 4 * kMaxSeg + i];
+      for (int i = tid; i < C * kSlotsPerCh; i += kThreads) ch_slots[i] = static_cast<uint8_t>(P[4 + 4 * kMaxSeg + i]);
       if (tid == 0) mf_info[0] = (P[1] == C) ? P[0] : 0;
     } else if (tid == 0) {
       // no plan: cut every filter's support [cb, ce) in order into segments of <= kSegLen bins
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
             seg_a[n] = k;
             seg_b[n] = (k + kSegLen < ce) ? k + kSegLen : ce;
             seg_c[n] = c;
-            ch_slots[c * kSlotsPerCh + t] = n;
+            ch_slots[c * kSlotsPerCh + t] = static_cast<uint8_t>(n);
           } else {
             fits = false;
           }
@@ -269,6 +275,13 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   }
   __syncthreads();  // last CTA-wide barrier (tables + mbarrier init); the main loop has none
 
+  float2 wreg[RT ? NJ : 1], hreg[RT ? 8 : 1];
+  if (RT) {
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) wreg[RT ? j : 0] = *reinterpret_cast<const float2*>(win + 2 * l + 32 * j);
+#pragma unroll
+    for (int k1 = 0; k1 < 8; ++k1) hreg[RT ? k1 : 0] = htw[16 * k1 + l];
+  }
   const int n_warps = gridDim.x * kWarps;
   int q = blockIdx.x * kWarps + warp;   // consecutive warps take consecutive quads (L2 locality)
   int b = q / A.quads_per_utt;
@@ -276,8 +289,8 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   const int db = n_warps / A.quads_per_utt, dg = n_warps - db * A.quads_per_utt;
 
   auto stage = [&](int bq, int gq, float* dst, uint64_t* bar) {
-    stage_span<true>(A.x + static_cast<int64_t>(bq) * A.T, A.T, 4 * gq * A.P - A.left, A.span, A.pad_mode,
-                     A.bulk_in != 0, dst, bar, lane);
+    stage_span_fast(A.x + static_cast<int64_t>(bq) * A.T, A.T, 4 * gq * A.P - A.left, A.span, A.pad_mode,
+                    A.bulk_in != 0, dst, bar, lane);
   };
 
   // Every staging completes one phase of its buffer's barrier (bulk copy or plain arrive), so the parity of
@@ -320,7 +333,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
           xa = *reinterpret_cast<const float2*>(pa + 32 * j);
           xb2 = *reinterpret_cast<const float2*>(pb + 32 * j);
         }
-        const float2 wv = *reinterpret_cast<const float2*>(win + 2 * l + 32 * j);
+        const float2 wv = RT ? wreg[RT ? j : 0] : *reinterpret_cast<const float2*>(win + 2 * l + 32 * j);
         if (MASK_ALL || j == NJ - 1) {  // never let samples past the frame end in (0 * inf = nan)
           const int p0 = 2 * l + 32 * j;
           if (p0 >= A.L) { xa.x = 0.0f; xb2.x = 0.0f; }
@@ -408,7 +421,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       const C2 z = a[dig(k1)], m = r[7 - k1];
       const float2 sr = add2(z.re, m.re), dr = sub2(z.re, m.re);
       const float2 si = add2(z.im, m.im), di = sub2(z.im, m.im);
-      const float2 hw = htw[16 * k1 + l];                          // W512^k / 2
+      const float2 hw = RT ? hreg[RT ? k1 : 0] : htw[16 * k1 + l];   // W512^k / 2
       const float2 tr = fma2s(dr, hw.y, mul2s(si, hw.x));          // T = (W/2) (si, -dr)
       const float2 ti = fma2s(dr, -hw.x, mul2s(si, hw.y));
       xr_ = fma2s(sr, 0.5f, tr);                                   // X[k]     = E + T
@@ -483,8 +496,8 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       const float* mfW = reinterpret_cast<const float*>(smem_raw + tbl_off);
       const float* mfL = mfW + C * M1;
       const int* seg_k0 = reinterpret_cast<const int*>(mfL + M1);
-      const int* ch_slots = seg_k0 + kMaxSeg;
-      const float* wT = reinterpret_cast<const float*>(ch_slots + C * kSlotsPerCh);
+      const uint8_t* ch_slots = reinterpret_cast<const uint8_t*>(seg_k0 + kMaxSeg);
+      const float* wT = reinterpret_cast<const float*>(seg_k0 + kMaxSeg + mf_slot_words(C));
       const int* mf_info = reinterpret_cast<const int*>(wT + kSegLen * kMaxSeg);
       const float2* amp0 = reinterpret_cast<const float2*>(ostage);
       const float2* amp1 = amp0 + kAmpPitch;
@@ -522,7 +535,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         __syncwarp();
         for (int c = lane; c < C; c += 32) {
           float2 u = make_float2(0.0f, 0.0f), v = u;
-          const int* sl = ch_slots + c * kSlotsPerCh;
+          const uint8_t* sl = ch_slots + c * kSlotsPerCh;
 #pragma unroll 2
           for (int t = 0; t < kSlotsPerCh && sl[t] < kMaxSeg; ++t) {
             const float4 q4 = segsum[sl[t]];
@@ -757,6 +770,9 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
         return launch_fmt<13, false, kWarpsSpectrum, 7>(A, p->spec.out_format, smem_bytes(A, 0, kWarpsSpectrum, 7),
                                                         device, stream);
       }
+      if (v & kVRegTables)
+        return launch_fmt<13, false, kWarpsMfcc, kVPair2 | kVRegTables>(A, p->spec.out_format, smem_bytes(A, 0, kWarpsMfcc),
+                                                                       device, stream);
       return launch_fmt<13, false, kWarpsSpectrum, kVPair2>(A, p->spec.out_format, smem, device, stream);
     }
     return launch_fmt<13, false, kWarpsSpectrum, 0>(A, p->spec.out_format, smem, device, stream);
@@ -781,12 +797,13 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   // amplitude rows, segment sums, mel rows and the quad's feature rows live inside the per-warp exchange region
   if (mf_warp_floats(C, D) * 4 > kXchBytesPerWarp) return DSB200_E_UNSUPPORTED;
   const size_t smem_max = static_cast<size_t>(max_dynamic_smem(device));
-  // 16 warps (128 registers) when the tables fit next to 16 warp pipelines, else 12
+  // 12 warps (168 registers) by default: with the planned filter bank the epilogue is short enough that the extra
+  // registers beat the extra warps (round 2, 1024 x 10 s: 1.39 ms at 12 warps, 1.44 ms at 16).
   static const int warps_knob = [] {   // DSB200_MFCC_WARPS=12|16 (tuning knob, read once)
     const char* e = getenv("DSB200_MFCC_WARPS");
-    return e != nullptr ? atoi(e) : 0;
+    return e != nullptr ? atoi(e) : 12;
   }();
-  const bool w16 = NJ == 13 && warps_knob != 12 && smem_bytes(A, mf_floats, kWarpsSpectrum) <= smem_max;
+  const bool w16 = NJ == 13 && warps_knob == 16 && smem_bytes(A, mf_floats, kWarpsSpectrum) <= smem_max;
   const int kWarps = w16 ? kWarpsSpectrum : kWarpsMfcc;
   const size_t smem = smem_bytes(A, mf_floats, kWarps);
   if (smem > smem_max) return DSB200_E_UNSUPPORTED;
@@ -819,7 +836,8 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   int rc;
   if (w16) rc = pair2 ? launch(stft512_kernel<13, false, kFmtMfcc, kWarpsSpectrum, kVPair2>)
                       : launch(stft512_kernel<13, false, kFmtMfcc, kWarpsSpectrum, 0>);
-  else if (NJ == 13) rc = launch(stft512_kernel<13, false, kFmtMfcc, kWarpsMfcc>);
+  else if (NJ == 13) rc = pair2 ? launch(stft512_kernel<13, false, kFmtMfcc, kWarpsMfcc, kVPair2>)
+                                : launch(stft512_kernel<13, false, kFmtMfcc, kWarpsMfcc, 0>);
   else rc = launch(stft512_kernel<16, true, kFmtMfcc, kWarpsMfcc>);
   if (rc != DSB200_OK) return rc;
   return after_launch("stft512_kernel<mfcc>");

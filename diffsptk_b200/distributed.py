@@ -137,7 +137,7 @@ class FusedGatherMfcc:
             self.out = symm.empty((self.world * B_local, self.N, self.D), dtype=torch.float32, device=device)
             self.hdl = symm.rendezvous(self.out, self.group)
             self.peers = [int(p) for p in self.hdl.buffer_ptrs]
-            mc = int(self.hdl.multicast_ptr) if self.hdl.has_multicast_support(device.type, device.index) else 0
+            mc = int(getattr(self.hdl, "multicast_ptr", 0) or 0)   # 0: no NVSwitch multicast object for this buffer
         except Exception as e:  # no peer access / no symmetric memory in this build
             self.reason = f"symmetric memory unavailable: {e!r}"[:200]
             return

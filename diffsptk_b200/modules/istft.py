@@ -66,13 +66,12 @@ class InverseShortTimeFourierTransform(BaseFunctionalModule):
     @staticmethod
     def _forward(y: torch.Tensor, out_length: int | None, *, frame_period: int, center: bool, fft_length: int,
                  ifftr=None, unframe=None, window_table: torch.Tensor | None = None) -> torch.Tensor:
-        table = window_table if window_table is not None else unframe.window
+        table = (window_table if window_table is not None else unframe.window).reshape(-1)
         if not y.is_complex():
             raise ValueError("the input spectrogram must be complex")
         if y.dim() <= 1:
             raise ValueError("Input must be at least 2D tensor.")
         if 2 * (y.size(-1) - 1) != fft_length:
             raise ValueError(f"Unexpected dimension of spectrum (input {y.size(-1)} vs target {fft_length // 2 + 1}).")
-        ops._no_grad_check(table)  # gradients flow to the spectrogram, not to a learnable synthesis window
         T = ops.unframe_length(y.size(-2), table.shape[-1], frame_period, center, out_length)
         return ops.istft(y, table, T, frame_period, center)

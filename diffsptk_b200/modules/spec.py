@@ -64,5 +64,30 @@ class Spectrum(BaseFunctionalModule):
                  relative_floor: float | None, out_format: int) -> torch.Tensor:
         if b is None and a is None:
             raise ValueError("Either b or a must be specified.")
-        ops._no_grad_check(a)  # only the numerator spectrum is differentiable
-        return ops.spec(b, a, fft_length, eps, -1.0 if relative_floor is None else relative_floor, out_format)
+        rf = -1.0 if relative_floor is None else relative_floor
+        needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (b, a))
+        if a is not None and needs_grad:
+            return _polezero_differentiable(b, a, fft_length, eps, relative_floor, out_format)
+        return ops.spec(b, a, fft_length, eps, rf, out_format)
+
+
+def _polezero_differentiable(b, a, fft_length, eps, relative_floor, out_format):
+    """``K |B| / |A|`` spectra under autograd (spec.py:162-178 of the reference): the fused kernel of the forward-only
+    path differentiates the numerator only, so with a denominator that (or whose partner) needs a gradient the two
+    power spectra come from the differentiable numerator kernel (``|B|^2``, ``|A|^2`` with the gain removed) and the
+    ratio, floor and formatter are element-wise torch ops -- gradients reach both ``b`` and ``a``."""
+    K, a1 = torch.split(a, [1, a.size(-1) - 1], dim=-1)
+    a1 = torch.nn.functional.pad(a1, (1, 0), value=1.0)                      # utils/private.py:200-209 remove_gain
+    s = torch.square(K) / ops.spec(a1, None, fft_length, 0.0, -1.0, 3)
+    if b is not None:
+        s = s * ops.spec(b, None, fft_length, 0.0, -1.0, 3)
+    s = s + eps
+    if relative_floor is not None:
+        s = torch.maximum(s, torch.amax(s, dim=-1, keepdim=True) * relative_floor)
+    if out_format == 0:
+        return 10 * torch.log10(s)
+    if out_format == 1:
+        return 0.5 * torch.log(s)
+    if out_format == 2:
+        return torch.sqrt(s)
+    return s

@@ -49,13 +49,14 @@ class Unframe(BaseFunctionalModule):
         if dtype is not None and not dtype.is_floating_point:
             dtype = None
         table = tables.make_window(frame_length, window, norm, symmetric, device=device, dtype=dtype)
-        return Precomputed(values=dict(frame_period=frame_period, center=center), tensors={"window": table})
+        # same shape as the reference's buffer / parameter (1, L, 1) (unframe.py:150-152): state_dicts interchange
+        return Precomputed(values=dict(frame_period=frame_period, center=center),
+                           tensors={"window": table.view(1, -1, 1)})
 
     @staticmethod
     def _forward(y: torch.Tensor, out_length: int | None, *, frame_period: int, center: bool,
                  window: torch.Tensor) -> torch.Tensor:
         if y.dim() <= 1:
             raise ValueError("Input must be at least 2D tensor.")
-        ops._no_grad_check(window)  # gradients flow to the frames, not to a learnable synthesis window
         T = ops.unframe_length(y.size(-2), y.size(-1), frame_period, center, out_length)
-        return ops.unframe(y, window, T, frame_period, center)
+        return ops.unframe(y, window.reshape(-1), T, frame_period, center)   # differentiable in y and in the window

@@ -9,6 +9,7 @@ CUDA only: a CPU tensor fails in the dispatcher -- there is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -60,8 +61,8 @@ def _no_grad_check(*ts):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
         raise NotImplementedError(
             "this diffsptk_b200 op is forward-only for that input (differentiable: every op with respect to its signal "
-            "input, learnable analysis windows and filter banks included; not the Spectrum denominator, learnable "
-            "synthesis windows, or a learnable DFT basis): wrap the call in torch.no_grad() or detach() the inputs."
+            "input, learnable analysis / synthesis windows and filter banks included; not a learnable DFT basis): "
+            "wrap the call in torch.no_grad() or detach() the inputs."
         )
 
 
@@ -370,7 +371,7 @@ def mfcc_plan(col_begin: Optional[Tensor], col_end: Optional[Tensor], n_bins: in
     """Segment plan of the fused MFCC kernel's filter-bank stage (``dsb200_mfcc_plan_build``): built on the host
     from the filter supports (one device->host copy of 2 C integers), cached on the ``col_begin`` tensor object, so
     a module or a memoised functional table pays for it once.  None when there is no support or no plan."""
-    if col_begin is None or col_end is None:
+    if col_begin is None or col_end is None or os.environ.get("DSB200_MFCC_PLAN") == "0":   # knob: A/B timing
         return None
     cached = getattr(col_begin, "_dsb200_plan", None)
     if cached is not None and cached[0] is col_end:
@@ -645,8 +646,10 @@ def _(b, gy, fft_length, eps, relative_floor, out_format):
 
 def _spec_setup(ctx, inputs, output):
     b, a, *rest = inputs
-    if a is not None:
-        raise NotImplementedError("gradients through the denominator spectrum (a) are not implemented")
+    if a is not None and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+        # modules.Spectrum routes such calls to its differentiable composite; a direct call of the fused op cannot
+        raise NotImplementedError("the fused pole-zero spectrum is forward-only: use modules.Spectrum / functional.spec, "
+                                  "which differentiate b and a through the numerator kernel")
     ctx.save_for_backward(b)
     ctx.rest = rest
 
@@ -1041,24 +1044,42 @@ def _unframe_grad_signal(g: Tensor, window: Tensor, n_frames: int, frame_period:
     return u
 
 
+def _synthesis_window_grad(u: Tensor, fr_u: Tensor, frames: Tensor, out: Tensor, w: Tensor, Nf: int, P: int,
+                           center: bool) -> Tensor:
+    """d/dw of out = fold(frames * w) / (fold(w^2) + 1e-16)  (unframe.py:198-204 of the reference).
+
+    With u = g / den and t(n, j) the output sample that frame n's sample j lands on:
+    dL/dw[j] = sum_n u[t(n, j)] (frames[n, j] - 2 w[j] out[t(n, j)]).  Both sums are framings of signals
+    (native frame kernel); ``fr_u`` is the framed ``u`` the caller already has."""
+    L = w.shape[-1]
+    v = u.clone()
+    To = out.shape[-1]
+    v[..., :To] *= out
+    v[..., To:] = 0
+    fr_v = frame(v, L, P, center, False, 0)[..., :Nf, :]
+    lead = tuple(range(fr_u.dim() - 1))
+    return (fr_u * frames).sum(dim=lead) - 2.0 * w * fr_v.sum(dim=lead)
+
+
 def _unframe_setup(ctx, inputs, output):
     y, window_t, out_length, frame_period, center = inputs
-    ctx.save_for_backward(y, window_t)
+    ctx.save_for_backward(y, window_t, output)
     ctx.args = (frame_period, center)
 
 
 def _unframe_bwd(ctx, g):
-    y, w = ctx.saved_tensors
+    y, w, out = ctx.saved_tensors
     P, center = ctx.args
     Nf, L = y.shape[-2], y.shape[-1]
-    if ctx.needs_input_grad[1]:
-        raise NotImplementedError("gradients with respect to a learnable synthesis window are not implemented")
+    gw = None
     with torch.no_grad():
         u = _unframe_grad_signal(g, w, Nf, P, center)
         # d out[t] / d y[n, j] = w[j] / den(t) at t = n P + j - s: frame the scaled gradient, apply the window
         fr = frame(u, L, P, center, False, 0)[..., :Nf, :]
         gy = window(fr, w, L)
-    return _like_input(gy, y), None, None, None, None
+        if ctx.needs_input_grad[1]:   # learnable synthesis window
+            gw = _synthesis_window_grad(u, fr, _prep(y, fr.dtype), out, w, Nf, P, center).to(w.dtype)
+    return _like_input(gy, y), gw, None, None, None
 
 
 torch.library.register_autograd(f"{_NS}::unframe", _unframe_bwd, setup_context=_unframe_setup)
@@ -1066,7 +1087,10 @@ torch.library.register_autograd(f"{_NS}::unframe", _unframe_bwd, setup_context=_
 
 def _istft_setup(ctx, inputs, output):
     y, window_t, out_length, frame_period, center = inputs
-    ctx.save_for_backward(window_t)
+    if ctx.needs_input_grad[1]:
+        ctx.save_for_backward(window_t, y, output)
+    else:
+        ctx.save_for_backward(window_t)
     ctx.meta = (y.shape[-2], 2 * (y.shape[-1] - 1), y.dtype == torch.complex64)
     ctx.args = (frame_period, center)
 
@@ -1074,16 +1098,20 @@ def _istft_setup(ctx, inputs, output):
 def _istft_bwd(ctx, g):
     # unframe's adjoint is window * frame(g / den), irfft's is (c_k / n) rfft: together, the complex STFT of
     # g / den -- the fused forward kernel -- scaled per bin.
-    (w,) = ctx.saved_tensors
+    w = ctx.saved_tensors[0]
     Nf, n, is_c64 = ctx.meta
     P, center = ctx.args
-    if ctx.needs_input_grad[1]:
-        raise NotImplementedError("gradients with respect to a learnable synthesis window are not implemented")
+    gw = None
     with torch.no_grad():
         u = _unframe_grad_signal(g, w, Nf, P, center)
         G = stft(u, w, P, n, center, False, 0, 0.0, -1.0, 4)[..., :Nf, :, :]
         out = _scale_half_spectrum(G, n)
-    return out.to(torch.complex64 if is_c64 else torch.complex128), None, None, None, None
+        if ctx.needs_input_grad[1]:   # learnable synthesis window: the frames are ifftr(Y), recomputed here
+            _, Y, x_out = ctx.saved_tensors
+            L = w.shape[-1]
+            fr_u = frame(u, L, P, center, False, 0)[..., :Nf, :]
+            gw = _synthesis_window_grad(u, fr_u, ifftr(Y, L), x_out, w, Nf, P, center).to(w.dtype)
+    return out.to(torch.complex64 if is_c64 else torch.complex128), gw, None, None, None
 
 
 torch.library.register_autograd(f"{_NS}::istft", _istft_bwd, setup_context=_istft_setup)

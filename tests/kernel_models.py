@@ -42,6 +42,55 @@ def fft16(a):
     return out
 
 
+def fft16_fma(a):
+    """fft16.cuh, round 2: the W16^(c r) twiddles of the second radix-4 layer folded into the butterflies'
+    multiply-adds -- a twiddle cos (1 - i tan) is a rotation-by-tan (two multiply-adds) whose cosine rides on the
+    following +/-; R (1 -+ i) is two additions whose R rides likewise.  Real-level formulas as in the kernel
+    (layer2<R>), result in natural order."""
+    R, C8, T8 = np.sqrt(0.5), np.cos(np.pi / 8), np.tan(np.pi / 8)
+    a = [complex(v) for v in a]
+    for c in range(4):
+        a[c], a[c + 4], a[c + 8], a[c + 12] = radix4(a[c], a[c + 4], a[c + 8], a[c + 12])
+
+    def pm_s(x, y, s_):
+        return x + s_ * y, x - s_ * y
+
+    def pm_is(x, y, s_):
+        return x - 1j * s_ * y, x + 1j * s_ * y
+
+    def layer2(r, x0, x1, x2, x3):
+        if r == 0:
+            return radix4(x0, x1, x2, x3)
+        if r == 2:
+            t0, t1 = x0 - 1j * x2, x0 + 1j * x2
+            s_, d = x1 + x3, x1 - x3
+            o0, o2 = pm_s(t0, d - 1j * s_, R)
+            o1, o3 = pm_is(t1, s_ - 1j * d, R)
+            return o0, o1, o2, o3
+        if r == 1:
+            q = complex(x2.real + x2.imag, x2.imag - x2.real)                  # (1 - i) b2
+            t0, t1 = pm_s(x0, q, R)
+            u = complex(x1.imag * T8 + x1.real, -x1.real * T8 + x1.imag)       # (1 - i t) b1
+            v = complex(x3.real * T8 + x3.imag, x3.imag * T8 - x3.real)        # (t - i) b3
+            p, m = u + v, u - v
+        else:
+            q = complex(x2.real - x2.imag, x2.imag + x2.real)                  # (1 + i) b2
+            t1, t0 = pm_s(x0, q, R)
+            u = complex(x1.real * T8 + x1.imag, x1.imag * T8 - x1.real)        # (t - i) b1
+            v = complex(x3.imag * T8 + x3.real, -x3.real * T8 + x3.imag)       # (1 - i t) b3
+            p, m = u - v, u + v
+        o0, o2 = pm_s(t0, p, C8)
+        o1, o3 = pm_is(t1, m, C8)
+        return o0, o1, o2, o3
+
+    out = [None] * 16
+    for r in range(4):
+        y = layer2(r, a[4 * r], a[4 * r + 1], a[4 * r + 2], a[4 * r + 3])
+        for t in range(4):
+            out[r + 4 * t] = y[t]
+    return out
+
+
 def stft512_frame_model(frame512):
     """512 windowed (zero-padded) real samples -> 257 complex bins, following the kernel's lanes."""
     x = np.asarray(frame512, dtype=np.float64)

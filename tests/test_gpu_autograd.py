@@ -649,3 +649,87 @@ def test_composite_consumer_gradients():
         scale = float(num.abs().max())
         err = float((gx - num).abs().max())
         assert err <= 2e-5 * scale + 1e-7, (name, err, scale)
+
+
+@pytest.mark.parametrize("fmt,rf", [("power", None), ("db", -40.0), ("magnitude", None)])
+def test_polezero_spectrum_gradients_reach_numerator_and_denominator(fmt, rf):
+    """Spectrum(b, a) = K |B| / |A| under autograd (spec.py:162-178): ADVICE round 1 -- the fused kernel differentiates
+    the numerator only; the module now routes such calls through the differentiable numerator kernel so that gradients
+    reach both polynomials.  Checker: a float64 torch composite (rfft + abs), used only here."""
+    import diffsptk_b200 as B
+    g = torch.Generator().manual_seed(9)
+    b0 = torch.randn(3, 5, generator=g, dtype=torch.float64)
+    a0 = torch.randn(3, 7, generator=g, dtype=torch.float64) * 0.3
+    a0[:, 0] = a0[:, 0].abs() + 1.0
+    a0[:, 1:] *= 0.2
+    gy = torch.randn(3, 17, generator=g, dtype=torch.float64)
+    mod = B.Spectrum(32, eps=1e-6, relative_floor=rf, out_format=fmt)
+
+    def ref(b, a):
+        K, a1 = a[..., :1], TF.pad(a[..., 1:], (1, 0), value=1.0)
+        X = K * (torch.fft.rfft(b, n=32).abs() / torch.fft.rfft(a1, n=32).abs())
+        s = X.square() + 1e-6
+        if rf is not None:
+            s = torch.maximum(s, s.amax(-1, keepdim=True) * 10 ** (rf / 10))
+        return {"db": lambda v: 10 * torch.log10(v), "magnitude": torch.sqrt, "power": lambda v: v}[fmt](s)
+
+    br, ar = b0.clone().requires_grad_(True), a0.clone().requires_grad_(True)
+    (ref(br, ar) * gy).sum().backward()
+    for which in ("both", "b_only", "a_only"):
+        b = b0.to(dev()).requires_grad_(which != "a_only")
+        a = a0.to(dev()).requires_grad_(which != "b_only")
+        y = mod(b, a)
+        assert torch.allclose(y.detach().cpu(), ref(b0, a0), rtol=1e-9, atol=1e-10)
+        (y * gy.to(dev())).sum().backward()
+        if b.requires_grad:
+            assert torch.allclose(b.grad.cpu(), br.grad, rtol=1e-7, atol=1e-9)
+        if a.requires_grad:
+            assert torch.allclose(a.grad.cpu(), ar.grad, rtol=1e-7, atol=1e-9)
+    # without gradients the fused pole-zero kernel runs, and agrees
+    with torch.no_grad():
+        assert torch.allclose(mod(b0.to(dev()), a0.to(dev())).cpu(), ref(b0, a0), rtol=1e-9, atol=1e-10)
+
+
+@pytest.mark.parametrize("center", [True, False])
+def test_learnable_synthesis_window_gradients(center):
+    """Unframe / ISTFT with learnable=True (unframe.py:150-152, istft.py:186-193 of the reference): the window is a
+    (1, L, 1) parameter like the reference's and receives its gradient (it used to raise).  Checker:
+    the reference's fold formula restated in float64 torch."""
+    import diffsptk_b200 as B
+    L, P, Nf = 12, 5, 9
+    g = torch.Generator().manual_seed(13)
+    y0 = torch.randn(2, Nf, L, generator=g, dtype=torch.float64)
+
+    def ref(y, w, out_length):
+        span = (Nf - 1) * P + L
+        x = TF.fold((y * w).transpose(-2, -1), (1, span), (1, L), stride=(1, P))[..., 0, 0, :]
+        d = TF.fold((w * w).reshape(1, L, 1).expand(1, L, Nf), (1, span), (1, L), stride=(1, P))[..., 0, 0, :]
+        s = L // 2 if center else 0
+        return (x / (d + 1e-16))[..., s:s + out_length]
+
+    un = B.Unframe(L, P, center=center, window="hanning", norm="none", learnable=True, dtype=torch.float64).to(dev())
+    assert tuple(un.window.shape) == (1, L, 1) and isinstance(un.window, torch.nn.Parameter)
+    T = Nf * P if center else (Nf - 1) * P + 3
+    gy = torch.randn(2, T, generator=g, dtype=torch.float64)
+    w_ref = un.window.detach().cpu().reshape(-1).clone().requires_grad_(True)
+    y_ref = y0.clone().requires_grad_(True)
+    (ref(y_ref, w_ref, T) * gy).sum().backward()
+    y = y0.to(dev()).requires_grad_(True)
+    out = un(y, T)
+    assert torch.allclose(out.detach().cpu(), ref(y0, w_ref.detach(), T), rtol=1e-10, atol=1e-12)
+    (out * gy.to(dev())).sum().backward()
+    assert torch.allclose(y.grad.cpu(), y_ref.grad, rtol=1e-9, atol=1e-11)
+    assert torch.allclose(un.window.grad.cpu().reshape(-1), w_ref.grad, rtol=1e-9, atol=1e-11)
+
+    # ISTFT: frames = irfft(Y); the synthesis window of the unframe sub-layer is the learnable one
+    ist = B.ISTFT(L, P, 16, center=center, window="hanning", norm="none", learnable=["window"],
+                  dtype=torch.float64).to(dev())
+    Y0 = torch.randn(2, Nf, 9, generator=g, dtype=torch.complex128)
+    w_ref = ist.unframe.window.detach().cpu().reshape(-1).clone().requires_grad_(True)
+    Y_ref = Y0.clone().requires_grad_(True)
+    (ref(torch.fft.irfft(Y_ref, n=16)[..., :L], w_ref, T) * gy).sum().backward()
+    Y = Y0.to(dev()).requires_grad_(True)
+    (ist(Y, T) * gy.to(dev())).sum().backward()
+    assert torch.allclose(ist.unframe.window.grad.cpu().reshape(-1), w_ref.grad, rtol=1e-9, atol=1e-11)
+    # torch's irfft ignores the imaginary parts of DC / Nyquist and so does the kernel: compare the rest
+    assert torch.allclose(torch.view_as_real(Y.grad.cpu()), torch.view_as_real(Y_ref.grad), rtol=1e-9, atol=1e-11)

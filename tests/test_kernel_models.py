@@ -12,6 +12,16 @@ def test_fft16_model():
     np.testing.assert_allclose(KM.fft16(list(a)), np.fft.fft(a), rtol=1e-12, atol=1e-12)
 
 
+def test_fft16_fma_form_model():
+    """Round 2: twiddles folded into the butterflies' multiply-adds (fft16.cuh layer2) -- same transform."""
+    rng = np.random.default_rng(5)
+    for _ in range(4):
+        a = rng.standard_normal(16) + 1j * rng.standard_normal(16)
+        np.testing.assert_allclose(KM.fft16_fma(list(a)), np.fft.fft(a), rtol=1e-12, atol=1e-12)
+    pruned = np.concatenate([a[:13], np.zeros(3)])            # the first pass sees structural zeros for j >= 13
+    np.testing.assert_allclose(KM.fft16_fma(list(pruned)), np.fft.fft(pruned), rtol=1e-12, atol=1e-12)
+
+
 def test_stft512_lane_model_matches_oracle():
     rng = np.random.default_rng(1)
     x = rng.standard_normal(1200)
