@@ -79,9 +79,12 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
   int b = u / A.units_per_utt, g = u - b * A.units_per_utt;
   const int db = n_warps / A.units_per_utt, dg = n_warps - db * A.units_per_utt;
   uint32_t phase = 0u;
+  // every staging completes one phase of the warp's barrier (bulk copy, or a plain arrive on the out-of-line
+  // general path), so the wait below is unconditional
   auto stage_half = [&](int bq, int gq, int half) {
-    return stage_span(A.x + static_cast<int64_t>(bq) * A.T, A.T, (kUnit * gq + kHalfUnit * half) * A.P - A.left,
-                      A.span, A.pad_mode, A.bulk_in != 0, span, mbar, lane);
+    stage_span_fast(A.x + static_cast<int64_t>(bq) * A.T, A.T, (kUnit * gq + kHalfUnit * half) * A.P - A.left,
+                    A.span, A.pad_mode, A.bulk_in != 0, span, mbar, lane);
+    return true;
   };
   bool cur_bulk = false;
   if (u < A.n_units) cur_bulk = stage_half(b, g, 0);
