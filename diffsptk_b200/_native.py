@@ -90,6 +90,7 @@ _PLAIN = {
     "dsb200_version": (C.c_int, []),
     "dsb200_last_error": (C.c_char_p, []),
     "dsb200_launch_count": (C.c_int64, []),
+    "dsb200_last_kernel": (C.c_char_p, []),
     "dsb200_num_frames": (C.c_int64, [_I64, _I32]),
     "dsb200_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p), _INT, _I64, _I64, C.POINTER(StftParams), _INT]),
     "dsb200_pipeline_stft_host": (C.c_int, [_P, _P, _P, _P, _I64]),
@@ -155,3 +156,8 @@ def typed(base: str, is_f64: bool):
 
 def launch_count() -> int:
     return int(load().dsb200_launch_count())
+
+
+def last_kernel() -> str:
+    """Name of the kernel this thread launched last (which path served the call)."""
+    return load().dsb200_last_kernel().decode()

@@ -27,6 +27,9 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static thread_local const char* g_last_kernel = "";
+void note_kernel(const char* name) { g_last_kernel = name; }
+
 static std::mutex g_mu;
 static std::map<int, cudaDeviceProp> g_props;
 
@@ -95,6 +98,8 @@ int dsb200_version(void) { return DSB200_VERSION; }
 const char* dsb200_last_error(void) { return dsb200::g_err; }
 
 int64_t dsb200_launch_count(void) { return dsb200::g_launches.load(std::memory_order_relaxed); }
+
+const char* dsb200_last_kernel(void) { return dsb200::g_last_kernel; }
 
 int64_t dsb200_num_frames(int64_t T, int32_t frame_period) {
   if (T <= 0 || frame_period <= 0) return 0;

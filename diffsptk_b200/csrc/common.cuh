@@ -14,6 +14,7 @@ namespace dsb200 {
 int fail(int code, const char* fmt, ...);          // records the message, returns `code`
 int cuda_fail(cudaError_t e, const char* what);    // DSB200_E_CUDA with cudaGetErrorString
 void count_launch(int n = 1);
+void note_kernel(const char* name);               // name of the kernel this thread launched last (string literal)
 
 #define DSB_CUDA(call)                                            \
   do {                                                            \
@@ -29,6 +30,7 @@ void count_launch(int n = 1);
 // Checks the launch that was just issued (cudaPeekAtLastError keeps sticky errors visible).
 static inline int after_launch(const char* what) {
   count_launch();
+  note_kernel(what);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, what);
   return DSB200_OK;

@@ -40,7 +40,9 @@ constexpr int kK = 257;
 constexpr int kDM = 25;              // max cepstral dimension (M + 1)
 constexpr int kJS = 49;              // row stride of Hm in shared memory (odd: conflict-free), = 2 * 24 + 1
 constexpr int kPS = 25;              // row stride of P0 in shared memory (odd)
-constexpr int kWarpFloats = kDM * 8 + 4 * kJS * 2 + 512 + 256 + 8;   // per-warp scratch: mc, rt, pivot column, solution, rhs
+constexpr int kJO = kDM - 1;          // rt is kept symmetric about its origin, rt[-j] = rt[j] (j <= 24): |i - c| needs no abs
+constexpr int kJSE = kJO + kJS;      // 73 values per frame pair
+constexpr int kWarpFloats = kDM * 8 + 4 * kJSE * 2 + 512 + 256 + 8;   // per-warp scratch: mc, rt, pivot column, solution, rhs
 
 struct MArgs {
   const float* x;    // [rows, 257] power spectrum
@@ -95,8 +97,10 @@ __device__ __forceinline__ float fast_rcp(float x) {  // MUFU.RCP + one Newton s
 }
 
 // kMW warps per CTA (12: 168 registers per thread, 16: 128); kQ packed frame pairs eliminated per pass.
-template <int kMW, int kQ, bool ROLLED>
+template <int kMW, int kQ, int SOLVE>
 __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
+  constexpr bool ROLLED = SOLVE != 0;  // SOLVE: 0 unrolled elimination + back substitution, 1 rolled Gauss-Jordan with
+                                       // lane = row and two frame pairs per pass, 2 four rows of one system per lane
   constexpr int kMT = kMW * 32;
   constexpr int kH = kQ / 2;           // float4 groups (two pairs each) exchanged through shared memory
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -109,8 +113,8 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
   float* avs = Ps + kKS * kPS;                           // [32]
   float* wbase = avs + 32 + warp * kWarpFloats;
   float* mcs = wbase;                                    // [kDM][8]   mc[m][frame]
-  float2* rts = reinterpret_cast<float2*>(mcs + kDM * 8);   // [4][kJS]  rt[pair][j] = (frame 2p, frame 2p+1)
-  float4* col = reinterpret_cast<float4*>(rts + 4 * kJS);   // [2][64] pivot column (= pivot row, by symmetry), 8 systems; [32, 64) stay zero
+  float2* rts = reinterpret_cast<float2*>(mcs + kDM * 8);   // [4][kJSE] rt[pair][kJO + j] = (frame 2p, frame 2p+1), j = -24..48
+  float4* col = reinterpret_cast<float4*>(rts + 4 * kJSE);   // [2][64] pivot column (= pivot row, by symmetry), 8 systems; [32, 64) stay zero
   float4* xs = col + 128;                                // [2][32] solution broadcast
   float4* pb = xs + 64;                                  // [2]     pivot right-hand sides
 
@@ -219,7 +223,17 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
         for (int u = 0; u < NC; ++u) {
           const float v = reduce8(acc[u], lane);
           if ((lane & 3) == 0)
-            reinterpret_cast<float*>(rts)[((lane >> 3) * kJS + j0 + u) * 2 + ((lane >> 2) & 1)] = v;
+          {
+            if constexpr (SOLVE == 2) {      // one scalar row per frame: rtf[frame][kJO + j]
+              float* rp = reinterpret_cast<float*>(rts) + (lane >> 2) * kJSE + kJO;
+              rp[j0 + u] = v;
+              if (j0 + u <= kJO) rp[-(j0 + u)] = v;
+            } else {
+              float* rp = reinterpret_cast<float*>(rts) + ((lane >> 3) * kJSE + kJO) * 2 + ((lane >> 2) & 1);
+              rp[2 * (j0 + u)] = v;
+              if (j0 + u <= kJO) rp[-2 * (j0 + u)] = v;     // mirror (j = 0 rewrites itself)
+            }
+          }
         }
       };
       {
@@ -229,23 +243,105 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
       }
       __syncwarp();
 
+      if constexpr (SOLVE == 2) {
+        // ---- Newton systems, variant 2: FOUR ROWS OF ONE SYSTEM PER LANE, four systems per pass ------------------
+        // With lane = row and two packed frame pairs per register (variant 1) every multiply-add needs a pivot-row
+        // entry of ITS system: a 16-byte shared-memory broadcast (four systems) per two FFMA2 -- the kernel was bound
+        // by the shared-memory pipe (70 %, profiles/r2_mcep_rolled.txt).  Here a float2 holds two ROWS of the same
+        // system, so the pivot-row entry is one scalar that FFMA2 broadcasts to both halves: a 4-byte load (four
+        // distinct addresses, one wavefront) per two FFMA2.  lane = 8 s + r: system s of the pass, rows r, r + 7,
+        // r + 14, r + 21 (r < 7; rows 25..27 are zero rows).  Same rolled Gauss-Jordan, same shifting registers.
+        const int s4 = lane >> 3, r = lane & 7;
+        const bool lane_on = r < 7;
+        float* colf = reinterpret_cast<float*>(col) + s4 * 33;     // [4][33] published pivot column per system (odd pitch:
+                                                                   // the four systems' entries sit in different banks)
+        float* pbf = reinterpret_cast<float*>(col) + 136 + s4;     // [4] pivot right-hand side per system
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+          const int sys = 4 * pass + s4;
+          const float* rt = reinterpret_cast<const float*>(rts) + sys * kJSE + kJO;
+          float2 lo[kDM], hi[kDM], blo, bhi;
+          auto elem = [&](int row, int c) -> float {      // A[row][c]; rows D..24 are identity rows, rows >= 25 zero
+            const bool real = lane_on && row < D;
+            float v = (lane_on && row == c && row >= D) ? 1.0f : 0.0f;
+            if (real && c < D) v = rt[row - c] + rt[row + c];
+            return v;
+          };
+#pragma unroll
+          for (int c = 0; c < kDM; ++c) {
+            lo[c] = f2(elem(r, c), elem(r + 7, c));
+            hi[c] = f2(elem(r + 14, c), elem(r + 21, c));
+          }
+          auto rhs = [&](int row) -> float { return (lane_on && row < D) ? rt[row] - avs[row] : 0.0f; };
+          blo = f2(rhs(r), rhs(r + 7));
+          bhi = f2(rhs(r + 14), rhs(r + 21));
+          float2 dlo = f2(1, 1), dhi = f2(1, 1);
+          int pvr = 0, pvt = 0;                                   // pivot row = 7 pvt + pvr
+          auto pivot_step = [&](auto nc_c, int pv) {
+            constexpr int NC = decltype(nc_c)::value;
+            if (lane_on) {
+              colf[r] = lo[0].x;
+              colf[r + 7] = lo[0].y;
+              colf[r + 14] = hi[0].x;
+              colf[r + 21] = hi[0].y;
+            }
+            const bool mine = lane_on && r == pvr;
+            {
+              const float2 bsel = pvt < 2 ? blo : bhi;
+              const float bval = (pvt & 1) ? bsel.y : bsel.x;
+              if (mine) *pbf = bval;
+            }
+            __syncwarp();
+            const float rinv = fast_rcp(colf[pv]);
+            const bool p0 = mine && pvt == 0, p1 = mine && pvt == 1, p2 = mine && pvt == 2, p3 = mine && pvt == 3;
+            const float2 flo = f2(p0 ? 0.0f : -lo[0].x * rinv, p1 ? 0.0f : -lo[0].y * rinv);
+            const float2 fhi = f2(p2 ? 0.0f : -hi[0].x * rinv, p3 ? 0.0f : -hi[0].y * rinv);
+            dlo = f2(p0 ? rinv : dlo.x, p1 ? rinv : dlo.y);
+            dhi = f2(p2 ? rinv : dhi.x, p3 ? rinv : dhi.y);
+            const float* cp = colf + pv + 1;
+#pragma unroll
+            for (int k = 0; k < NC; ++k) {
+              const float rc = cp[k];
+              lo[k] = __ffma2_rn(flo, f2(rc, rc), lo[k + 1]);
+              hi[k] = __ffma2_rn(fhi, f2(rc, rc), hi[k + 1]);
+            }
+            const float bp = *pbf;
+            blo = __ffma2_rn(flo, f2(bp, bp), blo);
+            bhi = __ffma2_rn(fhi, f2(bp, bp), bhi);
+            __syncwarp();
+            if (++pvr == 7) { pvr = 0; ++pvt; }
+          };
+          static_for<0, (kDM - 1) / 4>([&](auto ph_c) {
+            constexpr int ph = decltype(ph_c)::value;
+#pragma unroll 1
+            for (int pv = 4 * ph; pv < 4 * ph + 4; ++pv) pivot_step(std::integral_constant<int, kDM - 1 - 4 * ph>{}, pv);
+          });
+          pivot_step(std::integral_constant<int, 0>{}, kDM - 1);
+          // mc += g: x_row = b_row / pivot_row
+          const float2 xlo = __fmul2_rn(blo, dlo), xhi = __fmul2_rn(bhi, dhi);
+          if (lane_on) {
+            if (r < D) mcs[r * 8 + sys] += xlo.x;
+            if (r + 7 < D) mcs[(r + 7) * 8 + sys] += xlo.y;
+            if (r + 14 < D) mcs[(r + 14) * 8 + sys] += xhi.x;
+            if (r + 21 < D) mcs[(r + 21) * 8 + sys] += xhi.y;
+          }
+          __syncwarp();
+        }
+      } else {
       // ---- Newton systems, kQ packed frame pairs per pass (default: all 8 frames in one pass): lane = row ----
 #pragma unroll 1
       for (int pass = 0; pass < 4 / kQ; ++pass) {
         const int i = lane;
-        const float2* rt0 = rts + pass * kQ * kJS;
+        const float2* rt0 = rts + pass * kQ * kJSE + kJO + i;   // (rt0 + q kJSE)[+-c] = rt[i +- c]
         float2 a[kQ][kDM], b[kQ];
         if (i < D) {
           const float alpha_i = avs[i];
 #pragma unroll
           for (int q = 0; q < kQ; ++q) {
-            const float2* rt = rt0 + q * kJS;
+            const float2* rt = rt0 + q * kJSE;
 #pragma unroll
-            for (int c = 0; c < kDM; ++c) {
-              const int d = i > c ? i - c : c - i;
-              a[q][c] = (c < D) ? __fadd2_rn(rt[d], rt[i + c]) : f2(0, 0);
-            }
-            b[q] = __fadd2_rn(rt[i], f2(-alpha_i, -alpha_i));
+            for (int c = 0; c < kDM; ++c) a[q][c] = (c < D) ? __fadd2_rn(rt[-c], rt[c]) : f2(0, 0);
+            b[q] = __fadd2_rn(rt[0], f2(-alpha_i, -alpha_i));
           }
         } else {
           // Rows D..24 are identity rows with a zero right-hand side (lanes >= 25 are all-zero rows that are
@@ -269,8 +365,12 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
           float2 dinv[kQ];
 #pragma unroll
           for (int q = 0; q < kQ; ++q) dinv[q] = f2(1, 1);
-#pragma unroll 1
-          for (int pv = 0; pv < kDM; ++pv) {
+          // One pivot.  NC = number of columns right of the pivot that are updated: a compile-time multiple of four
+          // (>= 24 - pv; the surplus columns multiply the zeros that lanes 25.. publish), so the pivot loop is six
+          // short rolled loops of four pivots each with a fixed trip count -- no exit tests inside the update, and
+          // no register moves to merge exit paths (first rolled version: 8 % of the kernel's instructions).
+          auto pivot_step = [&](auto nc_c, int pv) {
+            constexpr int NC = decltype(nc_c)::value;
 #pragma unroll
             for (int g = 0; g < kH; ++g)
               col[64 * g + lane] = make_float4(a[2 * g][0].x, a[2 * g][0].y, a[2 * g + 1][0].x, a[2 * g + 1][0].y);
@@ -290,13 +390,56 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
               dinv[2 * g] = sel2(piv, r0, dinv[2 * g]);
               dinv[2 * g + 1] = sel2(piv, r1, dinv[2 * g + 1]);
             }
-            const int n_left = kDM - 1 - pv;                 // columns pv + 1 .. 24 remain
+            const float4* cp = col + pv + 1;
 #pragma unroll
-            for (int k = 0; k < kDM - 1; ++k) {
-              if ((k & 3) == 0 && k >= n_left) break;        // warp-uniform exit, four columns at a time
+            for (int k = 0; k < NC; ++k) {
 #pragma unroll
               for (int g = 0; g < kH; ++g) {
-                const float4 cv = col[64 * g + pv + 1 + k];  // entries past column 24 are zero (lanes 25.., padding)
+                const float4 cv = cp[64 * g + k];            // entries past column 24 are zero (lanes 25.., padding)
+                a[2 * g][k] = __ffma2_rn(f[2 * g], f2(cv.x, cv.y), a[2 * g][k + 1]);
+                a[2 * g + 1][k] = __ffma2_rn(f[2 * g + 1], f2(cv.z, cv.w), a[2 * g + 1][k + 1]);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < kH; ++g) {
+              const float4 bv = pb[g];
+              b[2 * g] = __ffma2_rn(f[2 * g], f2(bv.x, bv.y), b[2 * g]);
+              b[2 * g + 1] = __ffma2_rn(f[2 * g + 1], f2(bv.z, bv.w), b[2 * g + 1]);
+            }
+            __syncwarp();
+          };
+#if defined(DSB200_MCEP_SINGLE_LOOP)   // A/B knob: one rolled loop over all 25 pivots, every update 24 columns wide
+#pragma unroll 1
+          for (int pv = 0; pv < kDM; ++pv) pivot_step(std::integral_constant<int, kDM - 1>{}, pv);
+#elif !defined(DSB200_MCEP_PHASED)     // default: one rolled loop, warp-uniform exit from the update every four columns
+#pragma unroll 1
+          for (int pv = 0; pv < kDM; ++pv) {
+#pragma unroll
+            for (int g = 0; g < kH; ++g)
+              col[64 * g + lane] = make_float4(a[2 * g][0].x, a[2 * g][0].y, a[2 * g + 1][0].x, a[2 * g + 1][0].y);
+            if (lane == pv) {
+#pragma unroll
+              for (int g = 0; g < kH; ++g) pb[g] = make_float4(b[2 * g].x, b[2 * g].y, b[2 * g + 1].x, b[2 * g + 1].y);
+            }
+            __syncwarp();
+            const bool piv = lane == pv;
+            float2 f[kQ];
+#pragma unroll
+            for (int g = 0; g < kH; ++g) {
+              const float4 p = col[64 * g + pv];
+              const float2 r0 = f2(fast_rcp(p.x), fast_rcp(p.y)), r1 = f2(fast_rcp(p.z), fast_rcp(p.w));
+              f[2 * g] = piv ? f2(0, 0) : __fmul2_rn(a[2 * g][0], f2(-r0.x, -r0.y));
+              f[2 * g + 1] = piv ? f2(0, 0) : __fmul2_rn(a[2 * g + 1][0], f2(-r1.x, -r1.y));
+              dinv[2 * g] = sel2(piv, r0, dinv[2 * g]);
+              dinv[2 * g + 1] = sel2(piv, r1, dinv[2 * g + 1]);
+            }
+            const int n_left = kDM - 1 - pv;
+#pragma unroll
+            for (int k = 0; k < kDM - 1; ++k) {
+              if ((k & 3) == 0 && k >= n_left) break;
+#pragma unroll
+              for (int g = 0; g < kH; ++g) {
+                const float4 cv = col[64 * g + pv + 1 + k];
                 a[2 * g][k] = __ffma2_rn(f[2 * g], f2(cv.x, cv.y), a[2 * g][k + 1]);
                 a[2 * g + 1][k] = __ffma2_rn(f[2 * g + 1], f2(cv.z, cv.w), a[2 * g + 1][k + 1]);
               }
@@ -309,6 +452,15 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
             }
             __syncwarp();
           }
+#else   // A/B knob DSB200_MCEP_PHASED: six rolled loops of four pivots with static update widths (no exit tests; measured
+        // slower: the seven instantiations of the step spill 400 bytes at 168 registers)
+          static_for<0, (kDM - 1) / 4>([&](auto ph_c) {
+            constexpr int ph = decltype(ph_c)::value;
+#pragma unroll 1
+            for (int pv = 4 * ph; pv < 4 * ph + 4; ++pv) pivot_step(std::integral_constant<int, kDM - 1 - 4 * ph>{}, pv);
+          });
+          pivot_step(std::integral_constant<int, 0>{}, kDM - 1);
+#endif
 #pragma unroll
           for (int g = 0; g < kH; ++g) {
             const float2 x0 = __fmul2_rn(b[2 * g], dinv[2 * g]), x1 = __fmul2_rn(b[2 * g + 1], dinv[2 * g + 1]);
@@ -396,6 +548,7 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
         }
         __syncwarp();
       }
+      }
     }
     // ---- store the 8 x D block (contiguous in HBM) ----------------------------------------------
     for (int idx = lane; idx < nf * D; idx += 32) {
@@ -408,16 +561,16 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
 
 }  // namespace
 
-template <int kMW, int kQ, bool ROLLED>
+template <int kMW, int kQ, int SOLVE>
 static int launch_mcep_fast(const MArgs& A, int device, cudaStream_t stream) {
   const size_t smem = (static_cast<size_t>(kDM) * kKS + kKS * kJS + kKS * kPS + 32 +
                        static_cast<size_t>(kMW) * kWarpFloats) * sizeof(float);
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
-  DSB_CUDA(cudaFuncSetAttribute(mcep_fast_kernel<kMW, kQ, ROLLED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  DSB_CUDA(cudaFuncSetAttribute(mcep_fast_kernel<kMW, kQ, SOLVE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   const int64_t n_oct = (A.rows + 7) / 8;
   const int blocks = static_cast<int>(std::min<int64_t>((n_oct + kMW - 1) / kMW, sm_count(device)));
-  mcep_fast_kernel<kMW, kQ, ROLLED><<<blocks, kMW * 32, smem, stream>>>(A);
+  mcep_fast_kernel<kMW, kQ, SOLVE><<<blocks, kMW * 32, smem, stream>>>(A);
   return after_launch("mcep_fast_kernel");
 }
 
@@ -436,16 +589,18 @@ int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_para
   A.D = p->cep_order + 1;
   A.J = 2 * p->cep_order + 1;
   A.n_iter = p->n_iter;
-  // DSB200_MCEP_V=8 | 120 | 12 | 16 (tuning knob, read once): warps per CTA (x frame pairs per elimination pass:
+  // DSB200_MCEP_V=8 | 120 | 12 | 16 | 122 | 162 (tuning knob, read once): warps per CTA (x frame pairs per elimination pass:
   // 4 at 8 warps, else 2); 8 and 120 keep the fully unrolled elimination + back substitution for A/B runs
   static const int variant = [] {
     const char* e = getenv("DSB200_MCEP_V");
     return e != nullptr ? atoi(e) : 12;
   }();
-  if (variant == 8) return launch_mcep_fast<8, 4, false>(A, device, stream);      // round-1 shape
-  if (variant == 120) return launch_mcep_fast<12, 2, false>(A, device, stream);   // 12 warps, unrolled elimination
-  if (variant == 16) return launch_mcep_fast<16, 2, true>(A, device, stream);
-  return launch_mcep_fast<12, 2, true>(A, device, stream);
+  if (variant == 8) return launch_mcep_fast<8, 4, 0>(A, device, stream);      // round-1 shape
+  if (variant == 120) return launch_mcep_fast<12, 2, 0>(A, device, stream);   // 12 warps, unrolled elimination
+  if (variant == 122) return launch_mcep_fast<12, 2, 2>(A, device, stream);   // four rows of one system per lane
+  if (variant == 162) return launch_mcep_fast<16, 2, 2>(A, device, stream);
+  if (variant == 16) return launch_mcep_fast<16, 2, 1>(A, device, stream);
+  return launch_mcep_fast<12, 2, 1>(A, device, stream);                        // rolled Gauss-Jordan, lane = row, 12 warps
 }
 
 }  // namespace dsb200

@@ -22,9 +22,9 @@
 //     then the real-input split.  The split needs Z[k] and Z[256-k], which live in lanes l and
 //     16-l: they swap 8 registers by shuffle (lane 0 pairs bins with itself).
 //
-// Envelope: float32, fft_length == 512, frame_length <= 512, even frame_period, no zmean, no relative
-// floor (bulk copies additionally need 16-byte aligned spans, else guarded loads are used).  Anything else returns DSB200_E_UNSUPPORTED and the
-// generic kernel (spectral.cu) runs.
+// Envelope: float32, fft_length == 512, frame_length <= 512, even frame_period; zmean and the relative floor are
+// template variants since round 2 (bulk copies additionally need 16-byte aligned spans, else guarded loads are
+// used).  Anything else returns DSB200_E_UNSUPPORTED and the generic kernel (spectral.cu) runs.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>
@@ -65,7 +65,7 @@ struct Args {
   int in_floats;        // floats per input buffer (>= span, multiple of 4)
   int bulk_in;          // waveform layout allows bulk copies (alignment)
   int bulk_out;         // output layout allows bulk stores
-  float eps;
+  float eps, rel_floor;  // rel_floor: linear relative floor (RF variants)
   // MFCC epilogue (FMT == kFmtMfcc): fbank.py:315-320, dct.py:135-137, mfcc.py:252-256
   const float* mf_H;       // [257, C] filter bank
   const int32_t* mf_cb;    // [C] first non-zero row of each filter
@@ -158,6 +158,13 @@ constexpr int kVSingleBuf = 2, kVTwSmem = 4;
 // shared memory for every quad: -21 LDS.64 = -42 shared-memory wavefronts per quad (of ~300); needs the 168-register
 // budget of a 12-warp CTA (round 2 experiment, DSB200_STFT_V=9).
 constexpr int kVRegTables = 8;
+// 16 = zmean (frame.py:139-140: every frame minus its own mean over the frame_length samples, before the window):
+// the lanes of a half-warp sum their samples of both frames, four shuffles spread the sums, one subtraction per
+// sample.  32 = relative floor (spec.py:174-176: s = max(s, amax(s) * floor) per frame, before the formatter): the
+// power row is staged unformatted, every half-warp takes the maxima of its two rows (17 values per lane, four
+// shuffles) and formats the row in place.  Both were outside the fast envelope in round 1 (pitch.py:245-256 and
+// the WORLD spectra use them).
+constexpr int kVZmean = 16, kVRelFloor = 32;
 constexpr int kShift = 5;   // 2 * 80 / 32
 
 template <int NJ, bool MASK_ALL, int FMT, int W, int V = 0>
@@ -165,6 +172,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   constexpr int kWarps = W, kThreads = W * 32;
   constexpr bool PAIR2 = (V & kVPair2) != 0, SB = (V & kVSingleBuf) != 0, TWS = (V & kVTwSmem) != 0;
   constexpr bool RT = (V & kVRegTables) != 0;
+  constexpr bool ZM = (V & kVZmean) != 0, RF = (V & kVRelFloor) != 0;
   constexpr int kBufs = SB ? 1 : 2;
   constexpr int kFB = PAIR2 ? 2 : 1;        // frame B = frame A + kFB
   constexpr int kRowB = kFB * 257;          // its staged row
@@ -322,6 +330,34 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
 #pragma unroll
       for (int j = 0; j < NJ + kShift; ++j) raw[PAIR2 ? j : 0] = *reinterpret_cast<const float2*>(pa + 32 * j);
     }
+    float2 mean2 = make_float2(0.0f, 0.0f);   // (mean of frame A, mean of frame B), ZM only
+    if (ZM) {
+      float2 sum2 = make_float2(0.0f, 0.0f);
+#pragma unroll
+      for (int j = 0; j < NJ; ++j) {
+        float2 xa, xb2;
+        if (PAIR2) {
+          xa = raw[PAIR2 ? j : 0];
+          xb2 = raw[PAIR2 ? j + kShift : 0];
+        } else {
+          xa = *reinterpret_cast<const float2*>(pa + 32 * j);
+          xb2 = *reinterpret_cast<const float2*>(pb + 32 * j);
+        }
+        if (MASK_ALL || j == NJ - 1) {
+          const int p0 = 2 * l + 32 * j;
+          if (p0 >= A.L) { xa.x = 0.0f; xb2.x = 0.0f; }
+          if (p0 + 1 >= A.L) { xa.y = 0.0f; xb2.y = 0.0f; }
+        }
+        sum2 = add2(sum2, make_float2(xa.x + xa.y, xb2.x + xb2.y));
+      }
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        sum2.x += __shfl_xor_sync(0xffffffffu, sum2.x, o);
+        sum2.y += __shfl_xor_sync(0xffffffffu, sum2.y, o);
+      }
+      const float inv_len = 1.0f / static_cast<float>(A.L);
+      mean2 = make_float2(sum2.x * inv_len, sum2.y * inv_len);
+    }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       if (j < NJ) {
@@ -332,6 +368,10 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         } else {
           xa = *reinterpret_cast<const float2*>(pa + 32 * j);
           xb2 = *reinterpret_cast<const float2*>(pb + 32 * j);
+        }
+        if (ZM) {
+          xa.x -= mean2.x; xa.y -= mean2.x;
+          xb2.x -= mean2.y; xb2.y -= mean2.y;
         }
         const float2 wv = RT ? wreg[RT ? j : 0] : *reinterpret_cast<const float2*>(win + 2 * l + 32 * j);
         if (MASK_ALL || j == NJ - 1) {  // never let samples past the frame end in (0 * inf = nan)
@@ -398,9 +438,11 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       r[j].im.y = __shfl_sync(0xffffffffu, s.im.y, partner);
     }
 
-    const bool staged = (FMT == kFmtMfcc) ||
-                        ((FMT != DSB200_SPEC_COMPLEX) && A.bulk_out && rows == 4 &&
-                         (((static_cast<int64_t>(b) * A.n_frames + 4 * g) & 3) == 0));
+    const bool bulk_ok = (FMT != DSB200_SPEC_COMPLEX) && A.bulk_out && rows == 4 &&
+                         (((static_cast<int64_t>(b) * A.n_frames + 4 * g) & 3) == 0);
+    // the relative floor needs whole rows on chip: those builds always stage (and copy out by hand when the bulk
+    // store's alignment conditions do not hold)
+    const bool staged = (FMT == kFmtMfcc) || bulk_ok || (RF && FMT != DSB200_SPEC_COMPLEX);
     const int64_t row0 = static_cast<int64_t>(b) * A.n_frames + 4 * g;
     constexpr int kStride = (FMT == DSB200_SPEC_COMPLEX) ? 514 : 257;
     float* rowA;
@@ -445,6 +487,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         float* m2 = rowA + 256 - l + (swM ? 16 : 0);
         auto fmt2 = [&](float2 re, float2 im) {
           const float2 s = fma2(re, re, fma2(im, im, make_float2(A.eps, A.eps)));
+          if (RF) return s;                                   // formatted after the floor, below
           return make_float2(fmt1<FMT>(s.x), fmt1<FMT>(s.y));
         };
 #pragma unroll
@@ -477,8 +520,40 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
           put_bin<FMT, ST>(rowA, rowB, vB, 256 - k, mr, mi, A.eps);
         }
       }
-      if (l == 0)  // bin 128 pairs with itself: X[128] = conj(Z[128])
-        put_bin<FMT, ST>(rowA, rowB, vB, 128, a[dig(8)].re, make_float2(-a[dig(8)].im.x, -a[dig(8)].im.y), A.eps);
+      if (l == 0) {  // bin 128 pairs with itself: X[128] = conj(Z[128])
+        if constexpr (ST && RF && FMT != DSB200_SPEC_COMPLEX && FMT != kFmtMfcc) {
+          const C2 z8 = a[dig(8)];
+          const float2 s = fma2(z8.re, z8.re, fma2(z8.im, z8.im, make_float2(A.eps, A.eps)));
+          rowA[128] = s.x;
+          rowB[128] = s.y;
+        } else {
+          put_bin<FMT, ST>(rowA, rowB, vB, 128, a[dig(8)].re, make_float2(-a[dig(8)].im.x, -a[dig(8)].im.y), A.eps);
+        }
+      }
+      if constexpr (ST && RF && FMT != DSB200_SPEC_COMPLEX && FMT != kFmtMfcc) {
+        // relative floor + formatter on the two staged rows of this half-warp
+        __syncwarp();
+#pragma unroll 1
+        for (int rr = 0; rr < 2; ++rr) {
+          float* row = rr ? rowB : rowA;
+          float v[17];
+          float m = 0.0f;                                      // powers are >= 0
+#pragma unroll
+          for (int i = 0; i < 17; ++i) {
+            const int k = l + 16 * i;
+            v[i] = k < 257 ? row[k] : 0.0f;
+            m = fmaxf(m, v[i]);
+          }
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          const float fl = m * A.rel_floor;
+#pragma unroll
+          for (int i = 0; i < 17; ++i) {
+            const int k = l + 16 * i;
+            if (k < 257) row[k] = fmt1<FMT>(fmaxf(v[i], fl));
+          }
+        }
+      }
     };
 
     if (FMT == kFmtMfcc) {
@@ -642,10 +717,16 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       __syncwarp();
     } else if (staged) {
       split(std::true_type{});
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) bulk_s2g(A.y + row0 * 257, ostage, kOutFloats * 4u);
-      store_pending = true;
+      if (bulk_ok) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) bulk_s2g(A.y + row0 * 257, ostage, kOutFloats * 4u);
+        store_pending = true;
+      } else {   // RF builds only: partial quad or unaligned rows
+        __syncwarp();
+        for (int i = lane; i < rows * 257; i += 32) A.y[row0 * 257 + i] = ostage[i];
+        __syncwarp();
+      }
     } else if (vA) {
       split(std::false_type{});
     }
@@ -687,8 +768,7 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
   const dsb200_frame_params& f = p->frame;
   const dsb200_spec_params& s = p->spec;
   const int left = f.center ? f.frame_length / 2 : 0;
-  if (s.fft_length != 512 || f.frame_length > 512 || (f.frame_period & 1) || f.zmean || s.has_relative_floor ||
-      T_len > (1 << 30))
+  if (s.fft_length != 512 || f.frame_length > 512 || (f.frame_period & 1) || T_len > (1 << 30))
     return DSB200_E_UNSUPPORTED;
   const int64_t N = dsb200_num_frames(T_len, f.frame_period);
   const int64_t Q = (N + 3) / 4;
@@ -718,6 +798,7 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
   A.bulk_in = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (T_len % 4 == 0) && (left % 4 == 0) &&
               (f.frame_period % 4 == 0);
   A.eps = static_cast<float>(s.eps);
+  A.rel_floor = s.has_relative_floor ? static_cast<float>(s.relative_floor) : 0.0f;
   return DSB200_OK;
 }
 
@@ -754,6 +835,23 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
     return kDefaultBulkStore;
   }();
   A.bulk_out = store_mode && ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  const bool zm = p->frame.zmean != 0;
+  const bool rf = p->spec.has_relative_floor != 0 && p->spec.out_format != DSB200_SPEC_COMPLEX;
+  if (zm || rf) {
+    // zmean / relative-floor builds of the two main shapes: the BASELINE frame geometry (16 warps, frame pairing)
+    // and everything else (12 warps, every column masked)
+    const int fmt = p->spec.out_format;
+    if (NJ == 13 && A.P == 80) {
+      if (zm && rf) return launch_fmt<13, false, kWarpsSpectrum, kVPair2 | kVZmean | kVRelFloor>(A, fmt, smem, device, stream);
+      if (zm) return launch_fmt<13, false, kWarpsSpectrum, kVPair2 | kVZmean>(A, fmt, smem, device, stream);
+      return launch_fmt<13, false, kWarpsSpectrum, kVPair2 | kVRelFloor>(A, fmt, smem, device, stream);
+    }
+    const size_t sm12 = smem_bytes(A, 0, kWarpsMfcc);
+    if (sm12 > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
+    if (zm && rf) return launch_fmt<16, true, kWarpsMfcc, kVZmean | kVRelFloor>(A, fmt, sm12, device, stream);
+    if (zm) return launch_fmt<16, true, kWarpsMfcc, kVZmean>(A, fmt, sm12, device, stream);
+    return launch_fmt<16, true, kWarpsMfcc, kVRelFloor>(A, fmt, sm12, device, stream);
+  }
   if (NJ == 13) {
     const int v = stft_variant_knob();
     if ((v & kVPair2) && A.P == 80) {

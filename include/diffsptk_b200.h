@@ -113,6 +113,9 @@ DSB200_API int dsb200_version(void);
 DSB200_API const char* dsb200_last_error(void);
 /* Kernel launches issued by this library since load (all threads); the bench's `gpu_launches`. */
 DSB200_API int64_t dsb200_launch_count(void);
+/* Name of the kernel the calling thread launched last ("" if none): lets a test assert WHICH path served a call
+ * (the specialised kernel or the general one).  Never NULL; points to a string literal. */
+DSB200_API const char* dsb200_last_kernel(void);
 
 /* Number of frames for a waveform of T samples: (T-1)/P + 1 (frame.py:138); 0 if T <= 0. */
 DSB200_API int64_t dsb200_num_frames(int64_t T, int32_t frame_period);

@@ -195,6 +195,34 @@ def test_stft_baseline_against_oracle_all_formats(prec):
         H.assert_close(got, want, prec, what=f"stft {fmt} {prec}", scale_atol=fmt in ("db", "log-magnitude"))
 
 
+@pytest.mark.parametrize("kw", [
+    dict(zmean=True),
+    dict(zmean=True, window="hanning", norm="none", out_format="db"),          # pitch.py:245-256 (at fft_length 512)
+    dict(relative_floor=-40.0, out_format="db"),
+    dict(relative_floor=-30.0, eps=1e-6, out_format="power"),                  # the WORLD-style floored spectra
+    dict(zmean=True, relative_floor=-50.0, out_format="log-magnitude"),
+    dict(zmean=True, relative_floor=-40.0, frame_length=320, frame_period=160, out_format="magnitude"),
+    dict(zmean=True, out_format="complex"),
+    dict(relative_floor=-40.0, mode="reflect", out_format="power"),
+])
+def test_zmean_and_relative_floor_run_on_the_fused_kernel(kw):
+    """Round 2: Frame(zmean=True) and Spectrum(relative_floor=...) no longer leave the fast envelope.  Ragged batch
+    (partial quads, unaligned rows) against the oracle; the kernel that served the call must be stft512."""
+    import diffsptk_b200.functional as F
+    from diffsptk_b200 import _native
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(31)
+    x = (rng.standard_normal((3, 4321)) + 0.3).astype(np.float32)      # a DC offset makes zmean matter
+    got = F.stft(to_dev(x, "f32"), **kw)
+    assert _native.last_kernel() == "stft512_kernel", _native.last_kernel()
+    want = O.stft(x.astype(np.float64), **kw)
+    H.assert_close(to_np(got), want, "f32", what=f"stft {kw}", scale_atol=True)
+    # the general kernel computes the same thing (it still serves float64 and other FFT lengths)
+    got64 = F.stft(to_dev(x, "f64"), **kw)
+    assert _native.last_kernel() == "rowfft_kernel"
+    H.assert_close(to_np(got64), want, "f64", what=f"stft f64 {kw}", scale_atol=True)
+
+
 def test_full_size_batch_sampled_against_oracle():
     """BASELINE.json config 2 at full size (256 x 10 s): every utterance is computed on the GPU, a
     sample of utterances is recomputed by the oracle; plus size-independent properties."""
