@@ -55,3 +55,18 @@ def test_workload_table_matches_the_scope_contract():
     assert bench.WORKLOADS["lpc"][1:] == (1024, 80000, 320, 100)      # config 3: 420 B / frame
     assert bench.WORKLOADS["mcep"][3] + bench.WORKLOADS["mcep"][4] == 1128
     assert bench.WORKLOADS["mfcc"][3] + bench.WORKLOADS["mfcc"][4] == 372
+
+
+def test_ncu_traffic_is_tied_to_the_kernel_sources():
+    """roofline.traffic comes from profiles/traffic.json ONLY while the kernel sources are the ones the ncu capture was
+    made from (it was a constant); a stale entry must read as None, not as a number."""
+    sys.path.insert(0, ROOT)
+    import bench
+    db = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    for wl, rec in db.items():
+        if wl.startswith("_"):
+            continue
+        assert set(rec) >= {"dram_bytes_per_launch", "capture", "sources", "source_digest"}
+        fresh = rec["source_digest"] == bench.kernel_source_digest(rec["sources"])
+        assert (bench.ncu_record(wl) is not None) == fresh
+    assert bench.ncu_record("no-such-workload") is None

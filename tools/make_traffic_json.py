@@ -20,6 +20,11 @@ PACKED = ("FADD2", "FFMA2", "FMUL2")
 SCALAR = ("FADD", "FFMA", "FMUL")
 
 
+def _us(m):
+    scale = {"nsecond": 1e-3, "ns": 1e-3, "usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "second": 1e6, "s": 1e6}
+    return None if not m else m["value"] * scale.get(m.get("unit", "us"), 1.0)
+
+
 def main():
     wl, summary = sys.argv[1], json.load(open(sys.argv[2]))
     out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "profiles", "traffic.json")
@@ -34,7 +39,7 @@ def main():
     db[wl] = {
         "dram_bytes_per_launch": summary.get("dram_traffic_bytes"),
         "capture": f"ncu --set full --clock-control none, one launch of {summary.get('kernel')} ({os.path.basename(sys.argv[2])})",
-        "kernel_us_under_ncu": summary["metrics"].get("gpu__time_duration.sum", {}).get("value"),
+        "kernel_us_under_ncu": _us(summary["metrics"].get("gpu__time_duration.sum", {})),
         "fma_lane_slots_per_frame": slots / frames_per_unit if slots else None,
         "sources": SOURCES[wl],
         "source_digest": bench.kernel_source_digest(SOURCES[wl]),
