@@ -49,17 +49,24 @@ WORKLOADS = {
                 100, 100),
     "lpc2lsp": ("LPC -> line spectral pairs (M=24) on the LPC rows of config 3: 1024 utt x 5 s", 1024, 80000,
                 100, 100),
+    "stft1024": ("STFT power at frame length = fft length = 1024, hop 160 (the reference's CREPE front end, pitch.py:"
+                 "245-256): 256 utt x 10 s", 256, 160000, 640, 2052),
+    "stft2048": ("STFT power at frame length = fft length = 2048, hop 441 (yingram.py:97): 256 utt x 10 s", 256, 160000,
+                 1764, 4100),
     "istft": ("Inverse STFT (ifftr -> window -> overlap-add, one kernel): 256 utt x 10 s of complex spectra", 256,
               160000, 2056, 320),
 }
 
 # utterances per step of the CPU arms (a bounded sample of the workload; frames/s is batch-size-flat on the CPU)
-CPU_SAMPLE = {"stft": 64, "lpc": 64, "mfcc": 64, "mcep": 4, "stft_grad": 32, "delta": 256, "lpc2par": 64,
+CPU_SAMPLE = {"stft1024": 32, "stft2048": 32, "stft": 64, "lpc": 64, "mfcc": 64, "mcep": 4, "stft_grad": 32, "delta": 256, "lpc2par": 64,
               "lpc2lsp": 1, "istft": 32}
 
 
-def n_frames(T):
-    return (T - 1) // FP + 1
+_HOPS = {"stft1024": 160, "stft2048": 441}
+
+
+def n_frames(T, hop=FP):
+    return (T - 1) // hop + 1
 
 
 def workload_config(workload, collective="none (batch-sharded)"):
@@ -416,6 +423,10 @@ def make_step(workload, B, T, dev):
         return xs, grad_step
     if workload == "stft":
         m = D.STFT(FL, FP, NFFT).to(dev)
+        return xs, lambda i: m(xs[i & 1])
+    if workload in ("stft1024", "stft2048"):
+        nn = 1024 if workload == "stft1024" else 2048
+        m = D.STFT(nn, _HOPS[workload], nn, window="hanning", norm="none").to(dev)
         return xs, lambda i: m(xs[i & 1])
     if workload == "lpc":
         return xs, lambda i: F.lpc_from_waveform(xs[i & 1], lpc_order=24)

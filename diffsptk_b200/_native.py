@@ -91,6 +91,7 @@ _PLAIN = {
     "dsb200_last_error": (C.c_char_p, []),
     "dsb200_launch_count": (C.c_int64, []),
     "dsb200_last_kernel": (C.c_char_p, []),
+    "dsb200_set_sm_margin": (C.c_int, [_I32]),
     "dsb200_num_frames": (C.c_int64, [_I64, _I32]),
     "dsb200_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p), _INT, _I64, _I64, C.POINTER(StftParams), _INT]),
     "dsb200_pipeline_stft_host": (C.c_int, [_P, _P, _P, _P, _I64]),
@@ -156,6 +157,15 @@ def typed(base: str, is_f64: bool):
 
 def launch_count() -> int:
     return int(load().dsb200_launch_count())
+
+
+def set_sm_margin(n_sms: int) -> int:
+    """Leave ``n_sms`` SMs free of this library's persistent kernels (for a collective that overlaps them); returns
+    the previous margin."""
+    rc = int(load().dsb200_set_sm_margin(int(n_sms)))
+    if rc < 0:
+        check(rc)
+    return rc
 
 
 def last_kernel() -> str:

@@ -44,9 +44,12 @@ static const cudaDeviceProp* props(int device) {
   return &it->second;
 }
 
+static std::atomic<int> g_sm_margin{0};
+
 int sm_count(int device) {
   const cudaDeviceProp* p = props(device);
-  return p ? p->multiProcessorCount : 148;
+  const int n = (p ? p->multiProcessorCount : 148) - g_sm_margin.load(std::memory_order_relaxed);
+  return n > 1 ? n : 1;
 }
 
 int max_dynamic_smem(int device) {
@@ -100,6 +103,11 @@ const char* dsb200_last_error(void) { return dsb200::g_err; }
 int64_t dsb200_launch_count(void) { return dsb200::g_launches.load(std::memory_order_relaxed); }
 
 const char* dsb200_last_kernel(void) { return dsb200::g_last_kernel; }
+
+int dsb200_set_sm_margin(int32_t n_sms) {
+  if (n_sms < 0) return dsb200::fail(DSB200_E_BAD_PARAM, "sm margin must be non-negative");
+  return dsb200::g_sm_margin.exchange(n_sms, std::memory_order_relaxed);
+}
 
 int64_t dsb200_num_frames(int64_t T, int32_t frame_period) {
   if (T <= 0 || frame_period <= 0) return 0;

@@ -10,6 +10,7 @@
 // Reference semantics: diffsptk/modules/frame.py:120-141, window.py:185-193,
 // fftr.py:136-151, spec.py:152-178, stft.py:237-241.
 #include <algorithm>
+#include <cstdlib>
 
 #include "rowfft.cuh"
 
@@ -387,6 +388,10 @@ int spec_impl(const void* b, int32_t b_length, const void* a, int32_t a_length, 
 int stft512_try(const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
                 const dsb200_stft_params* p, int device, cudaStream_t stream);
 
+// The shared-memory radix-16 kernel for fft_length 1024 / 2048 (stftn.cu), same contract.
+int stftn_try(const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
+              const dsb200_stft_params* p, int device, cudaStream_t stream);
+
 template <typename T>
 int stft_generic(const void* x, const void* window, void* y, int64_t batch, int64_t T_len,
                  const dsb200_stft_params* p, int device, void* stream) {
@@ -426,6 +431,12 @@ int stft_impl(const void* x, const void* window, void* y, int64_t batch, int64_t
     const int rc = stft512_try(static_cast<const float*>(x), static_cast<const float*>(window),
                                static_cast<float*>(y), batch, T_len, p, device, static_cast<cudaStream_t>(stream));
     if (rc != DSB200_E_UNSUPPORTED) return rc;
+    static const bool generic_only = getenv("DSB200_STFT_GENERIC") != nullptr;   // A/B knob (read once)
+    if (!generic_only) {
+      const int rn = stftn_try(static_cast<const float*>(x), static_cast<const float*>(window), static_cast<float*>(y),
+                               batch, T_len, p, device, static_cast<cudaStream_t>(stream));
+      if (rn != DSB200_E_UNSUPPORTED) return rn;
+    }
   }
   return stft_generic<T>(x, window, y, batch, T_len, p, device, stream);
 }

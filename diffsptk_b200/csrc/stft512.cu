@@ -80,6 +80,9 @@ struct Args {
   // tensor in every rank's memory (NVLink peer mappings) or its NVSwitch multicast address.
   float* y_dst[kMaxDst];
   int n_dst, mf_vec;       // mf_vec: every destination is 16-byte aligned (128-bit stores of whole quads)
+  int mf_run;              // consecutive quads a warp takes before it stores their rows in one burst (1 or 4)
+  int mf_tail;             // floats per warp BEHIND the exchange planes: the run's parked feature rows (the planes
+                           // are overwritten by the next quad's transposes, the rows must survive them)
   int64_t mf_row_off;
 };
 
@@ -95,10 +98,10 @@ __host__ __device__ constexpr int mf_slot_words(int C) { return (C * kSlotsPerCh
 __host__ __device__ constexpr int mf_table_floats(int C, int M) {
   return (C * (M + 1) + (M + 1) + kMaxSeg + mf_slot_words(C) + kSegLen * kMaxSeg + 4 + 3) & ~3;
 }
-// per-warp scratch of the epilogue, in floats: two amplitude rows, segment sums (+ one zero entry), mel rows, and
-// the quad's finished feature rows
-__host__ __device__ constexpr int mf_warp_floats(int C, int D) {
-  return 4 * kAmpPitch + 4 * (kMaxSeg + 1) + 4 * C + ((4 * D + 3) & ~3);
+// per-warp scratch of the epilogue inside the exchange planes, in floats: two amplitude rows, segment sums (+ one
+// zero entry), mel rows
+__host__ __device__ constexpr int mf_warp_floats(int C) {
+  return 4 * kAmpPitch + 4 * (kMaxSeg + 1) + 4 * C;
 }
 
 template <int FMT>
@@ -194,7 +197,8 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   const int mf_floats = (FMT == kFmtMfcc) ? mf_table_floats(A.mf_C, A.mf_M) : 0;
   unsigned char* wbase = smem_raw + 16 * kWarps + 512 * sizeof(float) + (128 + (TWS ? 256 : 0)) * sizeof(float2) +
                          static_cast<size_t>(mf_floats) * 4 +
-                         static_cast<size_t>(warp) * (kBufs * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
+                         static_cast<size_t>(warp) * (kBufs * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp +
+                                                      static_cast<size_t>(FMT == kFmtMfcc ? A.mf_tail : 0) * 4);
   float* in0 = reinterpret_cast<float*>(wbase);
   float2* xch = reinterpret_cast<float2*>(wbase + kBufs * static_cast<size_t>(A.in_floats) * 4);
   float* ostage = reinterpret_cast<float*>(xch);            // aliases the exchange planes (see loop)
@@ -291,10 +295,17 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
     for (int k1 = 0; k1 < 8; ++k1) hreg[RT ? k1 : 0] = htw[16 * k1 + l];
   }
   const int n_warps = gridDim.x * kWarps;
-  int q = blockIdx.x * kWarps + warp;   // consecutive warps take consecutive quads (L2 locality)
+  // consecutive warps take consecutive quads (L2 locality); the MFCC build takes them in RUNS of `run` quads per warp
+  // so that the feature rows of a run (contiguous in the output) leave in one burst -- with the all-gather fused in,
+  // NVLink sees 832-byte writes instead of 208-byte ones (round 2: at N = 8 the 208-byte multicast writes arrived at
+  // ~400 GB/s per GPU and the step was bound by them)
+  const int run = (FMT == kFmtMfcc) ? A.mf_run : 1;
+  int q = run * (blockIdx.x * kWarps + warp);
   int b = q / A.quads_per_utt;
   int g = q - b * A.quads_per_utt;
   const int db = n_warps / A.quads_per_utt, dg = n_warps - db * A.quads_per_utt;
+  int64_t run_off = 0;   // MFCC: element offset of the rows parked in the staging tile, and how many floats
+  int run_n = 0;
 
   auto stage = [&](int bq, int gq, float* dst, uint64_t* bar) {
     stage_span_fast(A.x + static_cast<int64_t>(bq) * A.T, A.T, 4 * gq * A.P - A.left, A.span, A.pad_mode,
@@ -309,9 +320,18 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
   for (int it = 0; q < A.n_quads; ++it) {
     const int buf = it & 1;
     // next quad of this warp
-    const int qn = q + n_warps;
-    int bn = b + db, gn = g + dg;
-    if (gn >= A.quads_per_utt) { gn -= A.quads_per_utt; ++bn; }
+    int qn, bn, gn;
+    if (FMT == kFmtMfcc && run > 1) {
+      const bool last_of_run = (it % run) == run - 1;
+      qn = last_of_run ? q + run * n_warps - (run - 1) : q + 1;
+      bn = qn / A.quads_per_utt;
+      gn = qn - bn * A.quads_per_utt;
+    } else {
+      qn = q + n_warps;
+      bn = b + db;
+      gn = g + dg;
+      if (gn >= A.quads_per_utt) { gn -= A.quads_per_utt; ++bn; }
+    }
     if (!SB && qn < A.n_quads) stage(bn, gn, in0 + (buf ^ 1) * A.in_floats, &mbar[buf ^ 1]);
     mbar_wait(&mbar[SB ? 0 : buf], static_cast<uint32_t>(SB ? it : (it >> 1)) & 1u);
     __syncwarp();  // zero-fill / guarded stores of the other lanes
@@ -578,7 +598,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       const float2* amp1 = amp0 + kAmpPitch;
       float4* segsum = reinterpret_cast<float4*>(ostage + 4 * kAmpPitch);   // [kMaxSeg + 1] partial sums, 4 frames
       float4* mel4 = segsum + kMaxSeg + 1;                                   // [C] log filter-bank outputs
-      float* orow = reinterpret_cast<float*>(mel4 + C);                      // [4][D] the quad's feature rows
+      float* orow = ostage + kXchBytesPerWarp / 4;                           // [run][4][D] parked feature rows (behind the planes)
       auto fb_out = [&](int c, float2 u, float2 v) {                         // fbank.py:195-202
         u.x = fmaxf(u.x, A.mf_floor); u.y = fmaxf(u.y, A.mf_floor);
         v.x = fmaxf(v.x, A.mf_floor); v.y = fmaxf(v.y, A.mf_floor);
@@ -652,7 +672,28 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
       __syncwarp();
       // DCT-II columns 0..M (lane l), the channel range split between the half-warps, then lifter and
       // y | yE | yc | ycE packing into the quad's staged rows; half-warp h owns frames hf, hf + kFB.
-      float* outA = orow + hf * D;
+      const int64_t off = (A.mf_row_off + row0) * D;
+      auto flush = [&]() {
+        // the parked rows are contiguous in the output: 128-bit stores, 32 lanes x 16 bytes per instruction, to every
+        // destination (the local tensor; with the all-gather fused in, every rank's copy over NVLink, or the
+        // multicast address that the switch replicates)
+        if (A.mf_vec && ((run_off & 3) == 0) && ((run_n & 3) == 0)) {
+          for (int i = lane; i < (run_n >> 2); i += 32) {
+            const float4 v4 = reinterpret_cast<const float4*>(orow)[i];
+            for (int d = 0; d < A.n_dst; ++d) reinterpret_cast<float4*>(A.y_dst[d] + run_off)[i] = v4;
+          }
+        } else {
+          for (int i = lane; i < run_n; i += 32) {
+            const float v1 = orow[i];
+            for (int d = 0; d < A.n_dst; ++d) A.y_dst[d][run_off + i] = v1;
+          }
+        }
+        run_n = 0;
+        __syncwarp();
+      };
+      if (run_n > 0 && off != run_off + run_n) flush();     // the run broke (utterance end with a partial quad)
+      if (run_n == 0) run_off = off;
+      float* outA = orow + run_n + hf * D;
       float* outB = outA + kFB * D;
       const int ch = (C + 1) >> 1, c0 = h * ch, c1 = (c0 + ch < C) ? c0 + ch : C;
       for (int m0 = 0; m0 < M1; m0 += 16) {
@@ -699,22 +740,8 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
         outB[pos] = En.y;
       }
       __syncwarp();
-      // The quad's rows are contiguous in the output (4 D floats at row row0): whole quads leave as 128-bit
-      // stores, D lanes x 16 bytes, to every destination (the local tensor; with the all-gather fused in, every
-      // rank's copy over NVLink, or the multicast address that the switch replicates).
-      const int64_t off = (A.mf_row_off + row0) * D;
-      if (A.mf_vec && rows == 4 && ((off & 3) == 0)) {
-        for (int i = lane; i < D; i += 32) {
-          const float4 v4 = reinterpret_cast<const float4*>(orow)[i];
-          for (int d = 0; d < A.n_dst; ++d) reinterpret_cast<float4*>(A.y_dst[d] + off)[i] = v4;
-        }
-      } else {
-        for (int i = lane; i < rows * D; i += 32) {
-          const float v1 = orow[i];
-          for (int d = 0; d < A.n_dst; ++d) A.y_dst[d][off + i] = v1;
-        }
-      }
-      __syncwarp();
+      run_n += rows * D;
+      if (rows < 4 || (it % run) == run - 1 || qn >= A.n_quads) flush();
     } else if (staged) {
       split(std::true_type{});
       if (bulk_ok) {
@@ -814,7 +841,8 @@ static int stft_variant_knob() {
 static size_t smem_bytes(const Args& A, int mf_floats, int kWarps, int variant = 0) {
   const size_t bufs = (variant & kVSingleBuf) ? 1 : 2, tws = (variant & kVTwSmem) ? 256 : 0;
   return 16 * kWarps + 512 * sizeof(float) + (128 + tws) * sizeof(float2) + static_cast<size_t>(mf_floats) * 4 +
-         static_cast<size_t>(kWarps) * (bufs * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp);
+         static_cast<size_t>(kWarps) * (bufs * static_cast<size_t>(A.in_floats) * 4 + kXchBytesPerWarp +
+                                        static_cast<size_t>(A.mf_tail) * 4);
 }
 
 int stft512_try(const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
@@ -893,8 +921,18 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   const int mf_floats = mf_table_floats(C, M);
   const int D = M + (mp->out_format == DSB200_MFCC_Y ? 0 : (mp->out_format == DSB200_MFCC_YCE ? 2 : 1));
   // amplitude rows, segment sums, mel rows and the quad's feature rows live inside the per-warp exchange region
-  if (mf_warp_floats(C, D) * 4 > kXchBytesPerWarp) return DSB200_E_UNSUPPORTED;
+  if (mf_warp_floats(C) * 4 > kXchBytesPerWarp) return DSB200_E_UNSUPPORTED;
+  static const int run_knob = [] {   // DSB200_MFCC_RUN=1|4 (tuning knob, read once)
+    const char* e = getenv("DSB200_MFCC_RUN");
+    return e != nullptr ? atoi(e) : 4;
+  }();
   const size_t smem_max = static_cast<size_t>(max_dynamic_smem(device));
+  int mf_run = run_knob == 4 ? 4 : 1;
+  A.mf_tail = (mf_run * 4 * D + 3) & ~3;
+  if (mf_run > 1 && smem_bytes(A, mf_floats, kWarpsMfcc) > smem_max) {   // wide rows: park one quad only
+    mf_run = 1;
+    A.mf_tail = (4 * D + 3) & ~3;
+  }
   // 12 warps (168 registers) by default: with the planned filter bank the epilogue is short enough that the extra
   // registers beat the extra warps (round 2, 1024 x 10 s: 1.39 ms at 12 warps, 1.44 ms at 16).
   static const int warps_knob = [] {   // DSB200_MFCC_WARPS=12|16 (tuning knob, read once)
@@ -916,6 +954,7 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   A.mf_D = D;
   A.mf_plan = (cb != nullptr && ce != nullptr) ? plan : nullptr;
   A.n_dst = n_dst;
+  A.mf_run = mf_run;
   A.mf_row_off = row_off;
   A.mf_vec = 1;
   for (int d = 0; d < n_dst; ++d) {
@@ -924,7 +963,8 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   }
   A.mf_floor = static_cast<float>(mp->fbank.floor);
   A.mf_gamma = static_cast<float>(mp->fbank.gamma);
-  const int blocks = static_cast<int>(std::min<int64_t>((A.n_quads + kWarps - 1) / kWarps, sm_count(device)));
+  const int64_t n_runs = (A.n_quads + mf_run - 1) / mf_run;
+  const int blocks = static_cast<int>(std::min<int64_t>((n_runs + kWarps - 1) / kWarps, sm_count(device)));
   auto launch = [&](auto kern) -> int {
     DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<blocks, kWarps * 32, smem, stream>>>(A);

@@ -116,6 +116,11 @@ DSB200_API int64_t dsb200_launch_count(void);
 /* Name of the kernel the calling thread launched last ("" if none): lets a test assert WHICH path served a call
  * (the specialised kernel or the general one).  Never NULL; points to a string literal. */
 DSB200_API const char* dsb200_last_kernel(void);
+/* The persistent kernels of this library launch one CTA per SM.  A collective that should run WHILE they run (the
+ * chunked NCCL all-gather of batch-sharded features) finds no SM free until they finish; with a
+ * margin of n SMs the kernels launch on (SM count - n) SMs and leave the rest to it.  Process-wide; returns the
+ * previous margin (>= 0), or DSB200_E_BAD_PARAM. */
+DSB200_API int dsb200_set_sm_margin(int32_t n_sms);
 
 /* Number of frames for a waveform of T samples: (T-1)/P + 1 (frame.py:138); 0 if T <= 0. */
 DSB200_API int64_t dsb200_num_frames(int64_t T, int32_t frame_period);

@@ -131,6 +131,45 @@ def stft512_frame_model(frame512):
     return X
 
 
+def stftn_frame_model(xw):
+    """stftn.cu: fft_length 1024 / 2048 as an in-place decimation-in-frequency FFT of the Nc = n/2 packed points in
+    shared memory -- radix 16, radix 16, radix R3 -- with one pad element per M = Nc/16 elements, digit-reversed
+    result, and the real-input split reading Z[k] and Z[Nc - k] through the position map.  Same index arithmetic as
+    the kernel (pass loops, twiddle indices into the W_n table, padded positions)."""
+    x = np.asarray(xw, dtype=np.float64)
+    n = len(x)
+    Nc, M = n // 2, n // 32
+    R3, pitch = M // 16, M + 1
+    tw = np.exp(-2j * np.pi * np.arange(n) / n)                  # the library's table W_n^k
+    z = x[0::2] + 1j * x[1::2]
+    work = np.zeros(16 * pitch, dtype=np.complex128)
+    for j in range(M):                                            # pass 1: lane = j
+        u = np.array(fft16_fma([z[j + M * s] for s in range(16)]))
+        for t in range(16):
+            work[j + pitch * t] = u[t] * (tw[(2 * j * t) & (n - 1)] if t else 1.0)
+    for t in range(16):                                           # pass 2: lane = (t, j2)
+        for j2 in range(R3):
+            base = j2 + pitch * t
+            v = np.array(fft16_fma([work[base + R3 * s2] for s2 in range(16)]))
+            for t2 in range(16):
+                work[base + R3 * t2] = v[t2] * (tw[((n // M) * j2 * t2) & (n - 1)] if t2 else 1.0)
+    for t in range(16):                                           # pass 3: the contiguous groups (t, t2)
+        for t2 in range(16):
+            base = R3 * t2 + pitch * t
+            work[base:base + R3] = np.fft.fft(work[base:base + R3])
+
+    def zpos(k):
+        return (k >> 8) + R3 * ((k >> 4) & 15) + pitch * (k & 15)
+
+    X = np.zeros(Nc + 1, dtype=np.complex128)
+    for k in range(Nc + 1):
+        a, b = work[zpos(k & (Nc - 1))], work[zpos((Nc - k) & (Nc - 1))]
+        sr, dr, si, di = a.real + b.real, a.real - b.real, a.imag + b.imag, a.imag - b.imag
+        hx, hy = 0.5 * tw[k].real, 0.5 * tw[k].imag
+        X[k] = complex(0.5 * sr + (dr * hy + si * hx), 0.5 * di + (si * hy - dr * hx))
+    return X
+
+
 def lpc_wave_model(frame, M, eps):
     """Windowed frame -> [K, a_1..a_M] with time-domain lag sums and the Levinson recursion."""
     x = np.asarray(frame, dtype=np.float64)

@@ -51,6 +51,15 @@ def test_parameter_errors_without_gpu(native_lib):
     assert native_lib.dsb200_window_f32(None, None, None, 0, 8, 8, 0, None) == 0
 
 
+def test_sm_margin_setter(native_lib):
+    """Process-wide setter (no GPU needed): returns the previous value, rejects negatives."""
+    from diffsptk_b200 import _native as N
+    assert N.set_sm_margin(8) == 0
+    assert N.set_sm_margin(0) == 8
+    assert native_lib.dsb200_set_sm_margin(-1) == N.E_BAD_PARAM
+    assert N.set_sm_margin(0) == 0
+
+
 def test_sass_is_sm100a(native_lib):
     from diffsptk_b200 import _native
     out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True)

@@ -223,6 +223,68 @@ def test_zmean_and_relative_floor_run_on_the_fused_kernel(kw):
     H.assert_close(to_np(got64), want, "f64", what=f"stft f64 {kw}", scale_atol=True)
 
 
+@pytest.mark.parametrize("kw", [
+    # pitch.py:245-256 -- the CREPE front end: frame length = fft length = 1024, hop 160, zmean, hanning, dB
+    # (eps 1e-3 instead of 1e-9: after the mean removal the lowest bins are differences of nearly equal numbers, whose
+    #  dB is noise in any float32 implementation; the floor keeps the comparison on well-conditioned values)
+    dict(frame_length=1024, frame_period=160, fft_length=1024, zmean=True, window="hanning", norm="none", out_format="db",
+         eps=1e-3),
+    # yingram.py:97 -- 2048-sample frames, hop 441 (odd)
+    dict(frame_length=2048, frame_period=441, fft_length=2048),
+    # pitch_spec.py:244-248 / ap.py:542-543 -- WORLD-style spectra: floored power at a larger FFT size
+    dict(frame_length=400, frame_period=80, fft_length=1024, eps=1e-6, relative_floor=-60.0, out_format="power"),
+    dict(frame_length=1536, frame_period=240, fft_length=2048, relative_floor=-40.0, out_format="log-magnitude"),
+    dict(frame_length=800, frame_period=200, fft_length=1024, mode="reflect", out_format="magnitude"),
+    dict(frame_length=1024, frame_period=256, fft_length=2048, center=False, out_format="complex"),
+    dict(frame_length=1000, frame_period=333, fft_length=1024, zmean=True, mode="circular", out_format="complex"),
+])
+def test_large_fft_lengths_run_on_the_shared_memory_radix16_kernel(kw):
+    """Round 2: fft_length 1024 / 2048 (the sizes the reference's pitch / WORLD modules use) no longer fall to the
+    one-row-per-warp kernel.  Ragged batch, odd frame count, all pad modes against the oracle; kernel name checked."""
+    import diffsptk_b200.functional as F
+    from diffsptk_b200 import _native
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(41)
+    x = (rng.standard_normal((3, 9001)) + 0.2).astype(np.float32)
+    got = F.stft(to_dev(x, "f32"), **kw)
+    assert _native.last_kernel() == "stftn_kernel", _native.last_kernel()
+    want = O.stft(x.astype(np.float64), **kw)
+    # zmean: the zero-frequency bin is sum(w x) - mean sum(w), two sums of magnitude ~100 here (offset 0.2 x sum w)
+    # whose difference is ~1: 1e-5 relative in any float32 implementation, the reference's included
+    am = 50.0 if kw.get("zmean") else 1.0
+    H.assert_close(to_np(got), want, "f32", what=f"stft {kw}", scale_atol=True, atol_mul=am)
+    # the nn.Module route (window table built on the CPU and moved, as in the reference) launches the same kernel
+    m = diffsptk_module_stft(kw)(to_dev(x, "f32"))
+    assert _native.last_kernel() == "stftn_kernel"
+    H.assert_close(to_np(m), want, "f32", what=f"STFT module {kw}", scale_atol=True, atol_mul=am)
+
+
+def diffsptk_module_stft(kw):
+    import diffsptk_b200 as B
+    kw = dict(kw)
+    return B.STFT(kw.pop("frame_length"), kw.pop("frame_period"), kw.pop("fft_length"), **kw).to(dev())
+
+
+def test_large_fft_length_full_size_sampled():
+    """The CREPE-sized workload at scale: 256 utterances x 10 s, frame = fft = 1024, hop 160 -- sampled utterances
+    against the oracle, and the general kernel (DSB200_STFT_GENERIC route is the float64 path) agrees."""
+    import diffsptk_b200.functional as F
+    from diffsptk_b200 import _native
+    from oracle import np_oracle as O
+    kw = dict(frame_length=1024, frame_period=160, fft_length=1024, window="hanning", norm="none")
+    g = torch.Generator(device=dev()).manual_seed(43)
+    x = torch.randn(256, 160000, generator=g, device=dev())
+    P = F.stft(x, **kw)
+    assert _native.last_kernel() == "stftn_kernel"
+    assert P.shape == (256, 1000, 513) and bool(torch.isfinite(P).all())
+    for b in (0, 128, 255):
+        want = O.stft(to_np(x[b]).astype(np.float64), **kw)
+        H.assert_close(to_np(P[b]), want, "f32", what=f"utterance {b}", scale_atol=True)
+    P64 = F.stft(x[:2].double(), **kw)
+    assert _native.last_kernel() == "rowfft_kernel"
+    assert torch.allclose(P[:2].double(), P64, rtol=1e-4, atol=1e-6 * float(P64.max()))
+
+
 def test_full_size_batch_sampled_against_oracle():
     """BASELINE.json config 2 at full size (256 x 10 s): every utterance is computed on the GPU, a
     sample of utterances is recomputed by the oracle; plus size-independent properties."""

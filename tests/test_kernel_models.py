@@ -22,6 +22,17 @@ def test_fft16_fma_form_model():
     np.testing.assert_allclose(KM.fft16_fma(list(pruned)), np.fft.fft(pruned), rtol=1e-12, atol=1e-12)
 
 
+def test_stftn_shared_memory_fft_model_matches_oracle():
+    """Round 2: fft_length 1024 / 2048 (stftn.cu) -- pass structure, padded positions, digit-reversed split."""
+    rng = np.random.default_rng(6)
+    for n, L in ((1024, 1024), (1024, 400), (2048, 2048)):
+        x = rng.standard_normal(L + 7 * 160)
+        fr = O.window(O.frame(x, L, 160), n)
+        want = O.fftr(fr, n)
+        got = np.stack([KM.stftn_frame_model(f) for f in fr[:3]])
+        np.testing.assert_allclose(got, want[:3], rtol=1e-10, atol=1e-10)
+
+
 def test_stft512_lane_model_matches_oracle():
     rng = np.random.default_rng(1)
     x = rng.standard_normal(1200)

@@ -21,7 +21,7 @@ def main():
     xs, step = bench.make_step(wl, B, T, dev)
     _, per = bench.timed_steps(step, steps, 3, False)
     ms = statistics.mean(per)
-    frames = B * bench.n_frames(T)
+    frames = B * bench.n_frames(T, bench._HOPS.get(wl, bench.FP))
     knobs = {k: v for k, v in os.environ.items() if k.startswith("DSB200_")}
     print(json.dumps({"workload": wl, "ms": ms, "min_ms": min(per), "frames_per_s": frames / (ms / 1e3),
                       "hbm_frac": frames * (rd + wr) / (ms / 1e3) / 1e9 / bench.hbm_peak()[0], "knobs": knobs}))
