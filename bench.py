@@ -73,7 +73,8 @@ def workload_config(workload, collective="none (batch-sharded)"):
     """The ``config`` object of the JSON line -- built by ONE function so that both arms print identical keys."""
     cfg, B, T, _, _ = WORKLOADS[workload]
     return {"workload": cfg, "frame_length": FL, "frame_period": FP, "fft_length": NFFT,
-            "utterances_per_gpu": B, "samples_per_utterance": T, "frames_per_step_per_gpu": B * n_frames(T),
+            "utterances_per_gpu": B, "samples_per_utterance": T,
+            "frames_per_step_per_gpu": B * n_frames(T, _HOPS.get(workload, FP)),
             "l2": "per-step inputs + outputs exceed the 126 MB L2; two rotating input buffers",
             "collective": collective}
 
@@ -192,6 +193,10 @@ def reference_step(ref, workload, utterances, T, device="cpu", seed=1234):
     stft = ref.STFT(FL, FP, NFFT, **kw)
     if workload == "stft":
         return utterances * N, lambda: stft(x)
+    if workload in ("stft1024", "stft2048"):
+        nn, hop = (1024, 160) if workload == "stft1024" else (2048, 441)
+        big = ref.STFT(nn, hop, nn, window="hanning", norm="none", **kw)
+        return utterances * n_frames(T, hop), lambda: big(x)
     if workload == "lpc":
         fr, wi, lp = ref.Frame(FL, FP), ref.Window(FL, **kw), ref.LPC(FL, 24, **kw)
         return utterances * N, lambda: lp(wi(fr(x)))
@@ -270,6 +275,9 @@ def _cpu_task(args):
     x = _CPU_X[lo:hi]
     if workload == "stft":
         y = O.stft(x)
+    elif workload in ("stft1024", "stft2048"):
+        nn = 1024 if workload == "stft1024" else 2048
+        y = O.stft(x, frame_length=nn, frame_period=_HOPS[workload], fft_length=nn, window="hanning", norm="none")
     elif workload == "lpc":
         y = O.lpc(O.window(O.frame(x, FL, FP), None), 24)
     elif workload == "mfcc":
@@ -317,7 +325,7 @@ def port_cpu_throughput(workload, utterances, T, steps, warmup, budget_s=25.0):
         _CPU_X = rng.standard_normal((utterances, T)).astype(np.float32)
     per = max(1, utterances // (cores * 2))
     tasks = [(workload, lo, min(utterances, lo + per)) for lo in range(0, utterances, per)]
-    frames = utterances * n_frames(T)
+    frames = utterances * n_frames(T, _HOPS.get(workload, FP))
     ctx = mp.get_context("fork")
     with ctx.Pool(min(cores, len(tasks))) as pool:
         ms, n = time_cpu(lambda: pool.map(_cpu_task, tasks, chunksize=1), steps, warmup, budget_s)
@@ -597,7 +605,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 
     cfg, B, T, rd, wr = WORKLOADS[args.workload]
-    N = n_frames(T)
+    N = n_frames(T, _HOPS.get(args.workload, FP))
     frames_per_step = B * N
     xs, step = make_step(args.workload, B, T, dev)
     collective = "none (batch-sharded)"

@@ -42,4 +42,14 @@ class Frame(BaseFunctionalModule):
     @staticmethod
     def _forward(x: torch.Tensor, *, frame_length: int, frame_period: int, center: bool, zmean: bool,
                  mode: str) -> torch.Tensor:
-        return ops.frame(x, frame_length, frame_period, center, zmean, pad_mode_id(mode))
+        if x.dtype in (torch.float32, torch.float64):
+            return ops.frame(x, frame_length, frame_period, center, zmean, pad_mode_id(mode))
+        # The reference's Frame is pad + unfold, which keeps the input dtype (half / bfloat16 / integer waveforms stay
+        # what they are, frame.py:130-141).  The gather is exact in a wider float type, so run it there and cast back:
+        # float32 holds half / bfloat16 / int8 / int16 exactly, float64 holds int32 (and int64 up to 2^53).  With zmean
+        # the reference's mean of a half tensor is a half computation; the wider result rounded back is at least as close.
+        wide = torch.float32 if (x.dtype.is_floating_point or x.element_size() <= 2) else torch.float64
+        y = ops.frame(x.to(wide), frame_length, frame_period, center, zmean, pad_mode_id(mode))
+        if zmean and not x.dtype.is_floating_point:
+            return y.to(torch.float32)          # the reference raises for integer zmean (mean of a Long tensor)
+        return y.to(x.dtype)

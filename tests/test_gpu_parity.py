@@ -375,6 +375,13 @@ def test_edge_cases():
     assert F.stft(torch.randn(2, 1000, device=d, dtype=torch.float16)).dtype == torch.float32
     m32 = B.STFT(400, 80, 512).to(d)
     assert m32(torch.randn(2, 1000, device=d, dtype=torch.float64)).dtype == torch.float64
+    # Frame alone is pad + unfold in the reference: it keeps the input dtype, bit-exactly
+    for dt in (torch.int16, torch.int32, torch.float16, torch.bfloat16):
+        xv = (torch.randn(2, 1000, device=d) * 100).to(dt)
+        fr = F.frame(xv, frame_length=40, frame_period=16, mode="constant")
+        assert fr.dtype == dt
+        want = torch.nn.functional.pad(xv.double(), (20, 19)).unfold(-1, 40, 16).to(dt)
+        assert torch.equal(fr, want)
     # frame_length > fft_length truncates each windowed frame (window.py:190-192)
     xx = np.random.default_rng(2).standard_normal((2, 600))
     got = to_np(F.stft(to_dev(xx, "f64"), frame_length=40, frame_period=10, fft_length=32))
