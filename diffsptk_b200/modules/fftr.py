@@ -46,16 +46,37 @@ class RealValuedFastFourierTransform(BaseFunctionalModule):
                     device: torch.device | None, dtype: torch.dtype | None) -> Precomputed:
         RealValuedFastFourierTransform._check(fft_length)
         fmt = _format_id(out_format)
+        tensors = {}
         if learnable:
-            # The reference switches to a DFT-by-matmul with a trainable basis (fftr.py:123-131,146-150);
-            # that is a dense contraction outside this repo's path.
-            raise NotImplementedError("learnable DFT basis is not part of the B200 hot path")
-        return Precomputed(values={"fft_length": fft_length, "out_format": fmt})
+            # The reference switches to a DFT-by-matmul with a trainable basis (fftr.py:123-131,146-150): W is
+            # [fft_length, 2 (L/2+1)] = (cos | -sin), built in double like the reference's fft(eye) and cast.
+            if fft_length is None:
+                raise ValueError("fft_length must be specified when learnable is True.")
+            W = torch.fft.fft(torch.eye(fft_length, dtype=torch.double))[..., : fft_length // 2 + 1]
+            W = torch.cat([W.real, W.imag], dim=-1)
+            tensors["W"] = W.to(device=device, dtype=dtype if dtype is not None and dtype.is_floating_point
+                                else torch.get_default_dtype())
+        return Precomputed(values={"fft_length": fft_length, "out_format": fmt}, tensors=tensors)
 
     @staticmethod
-    def _forward(x: torch.Tensor, *, fft_length: int | None, out_format: int) -> torch.Tensor:
+    def _forward(x: torch.Tensor, *, fft_length: int | None, out_format: int,
+                 W: torch.Tensor | None = None) -> torch.Tensor:
         n = x.size(-1) if fft_length is None else fft_length
         if n % 2 == 1:
             raise ValueError("fft_length must be positive even.")
+        if W is not None:
+            # trainable basis: a dense product on the native row-times-matrix kernel (differentiable in x and W),
+            # then the formatter as element-wise torch ops
+            if x.size(-1) != n:
+                x = torch.nn.functional.pad(x, (0, n - x.size(-1)))
+            re, im = torch.tensor_split(ops.rowmat(x, W), 2, dim=-1)
+            if out_format == 0:
+                return torch.complex(re, im)
+            if out_format == 1:
+                return re
+            if out_format == 2:
+                return im
+            p2 = re * re + im * im
+            return torch.sqrt(p2) if out_format == 3 else p2
         y = ops.rfft(x, n, out_format)
         return torch.view_as_complex(y) if out_format == 0 else y

@@ -49,13 +49,21 @@ class RealValuedInverseFastFourierTransform(BaseFunctionalModule):
     def _precompute(fft_length: int, out_length: int | None, learnable: bool, device: torch.device | None,
                     dtype: torch.dtype | None) -> Precomputed:
         RealValuedInverseFastFourierTransform._check(fft_length, out_length)
+        tensors = {}
         if learnable:
-            # the reference switches to a trainable inverse-DFT matrix (ifftr.py:117-124): a dense contraction
-            raise NotImplementedError("learnable DFT basis is not part of the B200 hot path")
-        return Precomputed(values={"fft_length": fft_length, "out_length": out_length})
+            # the reference switches to a trainable inverse-DFT matrix (ifftr.py:117-124): [2 (L/2+1), out_length]
+            W = torch.fft.ifft(torch.eye(fft_length, dtype=torch.double))[: fft_length // 2 + 1, :out_length]
+            W[1:-1] *= 2
+            W = torch.cat([W.real, -W.imag], dim=0)
+            tensors["W"] = W.to(device=device, dtype=dtype if dtype is not None and dtype.is_floating_point
+                                else torch.get_default_dtype())
+        return Precomputed(values={"fft_length": fft_length, "out_length": out_length}, tensors=tensors)
 
     @staticmethod
-    def _forward(y: torch.Tensor, *, fft_length: int, out_length: int | None) -> torch.Tensor:
+    def _forward(y: torch.Tensor, *, fft_length: int, out_length: int | None,
+                 W: torch.Tensor | None = None) -> torch.Tensor:
         if not y.is_complex():
             raise ValueError("the input spectrum must be complex")
+        if W is not None:   # trainable inverse basis: dense product on the native row-times-matrix kernel
+            return ops.rowmat(torch.cat([y.real, y.imag], dim=-1).to(W.dtype), W)
         return ops.ifftr(y, fft_length if out_length is None else out_length)

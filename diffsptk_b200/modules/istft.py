@@ -47,10 +47,9 @@ class InverseShortTimeFourierTransform(BaseFunctionalModule):
                     dtype: torch.dtype | None, module: bool = True) -> Precomputed:
         InverseShortTimeFourierTransform._check(learnable)
         keys = LEARNABLES if learnable is True else (() if learnable is False else tuple(learnable))
-        if "basis" in keys:
-            raise NotImplementedError("learnable DFT basis is not part of the B200 hot path")
+        basis = "basis" in keys and module
         RealValuedInverseFastFourierTransform._check(fft_length, frame_length)
-        values = dict(frame_period=frame_period, center=center, fft_length=fft_length)
+        values = dict(frame_period=frame_period, center=center, fft_length=fft_length, basis=basis)
         un_params = dict(frame_length=frame_length, frame_period=frame_period, center=center, window=window,
                          norm=norm, symmetric=symmetric, learnable="window" in keys, device=device, dtype=dtype)
         if not module:
@@ -58,14 +57,17 @@ class InverseShortTimeFourierTransform(BaseFunctionalModule):
             table = Unframe._precompute(**un_params).tensors["window"]
             return Precomputed(values=values, tensors={"window_table": table})
         ifftr = get_layer(True, RealValuedInverseFastFourierTransform,
-                          dict(fft_length=fft_length, out_length=frame_length, learnable=False, device=device,
+                          dict(fft_length=fft_length, out_length=frame_length, learnable=basis, device=device,
                                dtype=dtype))
         unframe = get_layer(True, Unframe, un_params)
         return Precomputed(values=values, layers={"ifftr": ifftr, "unframe": unframe})
 
     @staticmethod
     def _forward(y: torch.Tensor, out_length: int | None, *, frame_period: int, center: bool, fft_length: int,
-                 ifftr=None, unframe=None, window_table: torch.Tensor | None = None) -> torch.Tensor:
+                 basis: bool = False, ifftr=None, unframe=None,
+                 window_table: torch.Tensor | None = None) -> torch.Tensor:
+        if basis:   # trainable inverse DFT basis: the reference's cascade (istft.py:186-193)
+            return unframe(ifftr(y), out_length=out_length)
         table = (window_table if window_table is not None else unframe.window).reshape(-1)
         if not y.is_complex():
             raise ValueError("the input spectrogram must be complex")

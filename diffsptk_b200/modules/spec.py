@@ -53,17 +53,29 @@ class Spectrum(BaseFunctionalModule):
     def _precompute(fft_length: int, eps: float, relative_floor: float | None, out_format: str | int,
                     learnable: bool = False, module: bool = True) -> Precomputed:
         Spectrum._check(fft_length, eps, relative_floor)
-        if learnable:
-            raise NotImplementedError("learnable DFT basis is not part of the B200 hot path")
         linear_floor = None if relative_floor is None else 10 ** (relative_floor / 10)  # spec.py:121-122
+        layers = {}
+        if learnable and module:
+            # trainable DFT basis (spec.py:134-142 -> fftr.py:123-131): the amplitude comes from the sub-layer's dense
+            # product instead of the fused kernel; same sub-layer name as the reference (``spec.fftr.W``)
+            from .fftr import RealValuedFastFourierTransform
+            layers["fftr"] = RealValuedFastFourierTransform(fft_length, out_format="amplitude", learnable=True)
         return Precomputed(values={"fft_length": fft_length, "eps": eps, "relative_floor": linear_floor,
-                                   "out_format": spec_format_id(out_format)})
+                                   "out_format": spec_format_id(out_format)}, layers=layers)
 
     @staticmethod
     def _forward(b: torch.Tensor | None, a: torch.Tensor | None, *, fft_length: int, eps: float,
-                 relative_floor: float | None, out_format: int) -> torch.Tensor:
+                 relative_floor: float | None, out_format: int, fftr=None) -> torch.Tensor:
         if b is None and a is None:
             raise ValueError("Either b or a must be specified.")
+        if fftr is not None:   # trainable basis: the reference's composite, spec.py:162-178
+            if a is not None:
+                K, a1 = torch.split(a, [1, a.size(-1) - 1], dim=-1)
+                a1 = torch.nn.functional.pad(a1, (1, 0), value=1.0)
+                X = K * (fftr(b) / fftr(a1)) if b is not None else K / fftr(a1)
+            else:
+                X = fftr(b)
+            return _format_power(torch.square(X) + eps, relative_floor, out_format)
         rf = -1.0 if relative_floor is None else relative_floor
         needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (b, a))
         if a is not None and needs_grad:
@@ -81,7 +93,11 @@ def _polezero_differentiable(b, a, fft_length, eps, relative_floor, out_format):
     s = torch.square(K) / ops.spec(a1, None, fft_length, 0.0, -1.0, 3)
     if b is not None:
         s = s * ops.spec(b, None, fft_length, 0.0, -1.0, 3)
-    s = s + eps
+    return _format_power(s + eps, relative_floor, out_format)
+
+
+def _format_power(s, relative_floor, out_format):
+    """Relative floor and formatter of spec.py:173-177 as element-wise torch ops (the differentiable composites)."""
     if relative_floor is not None:
         s = torch.maximum(s, torch.amax(s, dim=-1, keepdim=True) * relative_floor)
     if out_format == 0:

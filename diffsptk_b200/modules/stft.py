@@ -56,8 +56,7 @@ class ShortTimeFourierTransform(BaseFunctionalModule):
         ShortTimeFourierTransform._check(learnable)
         keys = LEARNABLES if learnable is True else (() if learnable is False else tuple(learnable))
         Frame._check(frame_length, frame_period)
-        if "basis" in keys:
-            raise NotImplementedError("learnable DFT basis is not part of the B200 hot path")
+        basis = "basis" in keys and module
         fmt = spec_format_id(out_format, allow_complex=True)
         if fmt == 4:
             RealValuedFastFourierTransform._check(fft_length)
@@ -66,7 +65,7 @@ class ShortTimeFourierTransform(BaseFunctionalModule):
             Spectrum._check(fft_length, eps, relative_floor)
             linear_floor = None if relative_floor is None else 10 ** (relative_floor / 10)
         values = dict(frame_period=frame_period, fft_length=fft_length, center=center, zmean=zmean,
-                      pad_mode=pad_mode_id(mode), eps=eps, relative_floor=linear_floor, out_format=fmt)
+                      pad_mode=pad_mode_id(mode), eps=eps, relative_floor=linear_floor, out_format=fmt, basis=basis)
         win_params = dict(in_length=frame_length, out_length=fft_length, window=window, norm=norm,
                           symmetric=symmetric, learnable="window" in keys, device=device, dtype=dtype)
         if not module:
@@ -78,17 +77,19 @@ class ShortTimeFourierTransform(BaseFunctionalModule):
         window_ = get_layer(True, Window, win_params)
         if fmt == 4:
             spec = get_layer(True, RealValuedFastFourierTransform,
-                             dict(fft_length=fft_length, out_format="complex", learnable=False, device=device,
+                             dict(fft_length=fft_length, out_format="complex", learnable=basis, device=device,
                                   dtype=dtype))
         else:
             spec = get_layer(True, Spectrum, dict(fft_length=fft_length, eps=eps, relative_floor=relative_floor,
-                                                  out_format=out_format, learnable=False))
+                                                  out_format=out_format, learnable=basis))
         return Precomputed(values=values, layers={"frame": frame, "window": window_, "spec": spec})
 
     @staticmethod
     def _forward(x: torch.Tensor, *, frame_period: int, fft_length: int, center: bool, zmean: bool,
-                 pad_mode: int, eps: float, relative_floor: float | None, out_format: int, frame=None,
-                 window=None, spec=None, window_table: torch.Tensor | None = None) -> torch.Tensor:
+                 pad_mode: int, eps: float, relative_floor: float | None, out_format: int, basis: bool = False,
+                 frame=None, window=None, spec=None, window_table: torch.Tensor | None = None) -> torch.Tensor:
+        if basis:   # trainable DFT basis: the reference's cascade (stft.py:237-241), every stage a native kernel
+            return spec(window(frame(x)))
         table = window_table if window_table is not None else window.window
         y = ops.stft(x, table, frame_period, fft_length, center, zmean, pad_mode, eps,
                      -1.0 if relative_floor is None else relative_floor, out_format)

@@ -733,3 +733,45 @@ def test_learnable_synthesis_window_gradients(center):
     assert torch.allclose(ist.unframe.window.grad.cpu().reshape(-1), w_ref.grad, rtol=1e-9, atol=1e-11)
     # torch's irfft ignores the imaginary parts of DC / Nyquist and so does the kernel: compare the rest
     assert torch.allclose(torch.view_as_real(Y.grad.cpu()), torch.view_as_real(Y_ref.grad), rtol=1e-9, atol=1e-11)
+
+
+def test_learnable_dft_basis_matches_the_fft_and_trains():
+    """fftr / ifftr / Spectrum / STFT / ISTFT with a trainable DFT basis (fftr.py:123-131,146-150, ifftr.py:117-124 of
+    the reference; round 1 raised NotImplementedError).  At initialisation the basis IS the DFT, so the outputs must
+    agree with the fused kernels; gradients must reach the basis."""
+    import diffsptk_b200 as B
+    d = dev()
+    g = torch.Generator().manual_seed(17)
+    x = torch.randn(3, 700, generator=g, dtype=torch.float64).to(d)
+    f_fix = B.RealValuedFastFourierTransform(32, dtype=torch.float64).to(d)
+    f_lrn = B.RealValuedFastFourierTransform(32, learnable=True, dtype=torch.float64).to(d)
+    assert isinstance(f_lrn.W, torch.nn.Parameter) and tuple(f_lrn.W.shape) == (32, 34)
+    fr = x[:, :32]
+    assert torch.allclose(torch.view_as_real(f_lrn(fr)), torch.view_as_real(f_fix(fr)), rtol=1e-9, atol=1e-11)
+    i_fix = B.RealValuedInverseFastFourierTransform(32, 20, dtype=torch.float64).to(d)
+    i_lrn = B.RealValuedInverseFastFourierTransform(32, 20, learnable=True, dtype=torch.float64).to(d)
+    Y = f_fix(fr)
+    assert torch.allclose(i_lrn(Y), i_fix(Y), rtol=1e-9, atol=1e-11)
+    torch.set_default_dtype(torch.float64)
+    try:
+        s_fix = B.Spectrum(32, eps=1e-6, out_format="db").to(d)
+        s_lrn = B.Spectrum(32, eps=1e-6, out_format="db", learnable=True).to(d)
+    finally:
+        torch.set_default_dtype(torch.float32)
+    b, a = x[:, :5], torch.cat([x[:, 5:6].abs() + 1, 0.1 * x[:, 6:9]], -1)
+    assert torch.allclose(s_lrn(b, a), s_fix(b, a), rtol=1e-8, atol=1e-9)
+    st_fix = B.STFT(40, 10, 64, dtype=torch.float64).to(d)
+    st_lrn = B.STFT(40, 10, 64, learnable=["basis"], dtype=torch.float64).to(d)
+    assert torch.allclose(st_lrn(x), st_fix(x), rtol=1e-8, atol=1e-10)
+    names = [n for n, _ in st_lrn.named_parameters()]
+    assert names == ["spec.fftr.W"], names
+    st_lrn(x).sum().backward()
+    W = st_lrn.spec.fftr.W
+    assert W.grad is not None and bool(torch.isfinite(W.grad).all()) and float(W.grad.abs().max()) > 0
+    is_lrn = B.ISTFT(40, 10, 64, learnable=True, dtype=torch.float64).to(d)
+    is_fix = B.ISTFT(40, 10, 64, dtype=torch.float64).to(d)
+    Yc = B.STFT(40, 10, 64, out_format="complex", dtype=torch.float64).to(d)(x)
+    out = is_lrn(Yc, out_length=700)
+    assert torch.allclose(out, is_fix(Yc, out_length=700), rtol=1e-8, atol=1e-10)
+    out.sum().backward()
+    assert sorted(n for n, p in is_lrn.named_parameters() if p.grad is not None) == ["ifftr.W", "unframe.window"]
