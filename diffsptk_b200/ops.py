@@ -61,8 +61,8 @@ def _no_grad_check(*ts):
     if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts):
         raise NotImplementedError(
             "this diffsptk_b200 op is forward-only for that input (differentiable: every op with respect to its signal "
-            "input, learnable analysis / synthesis windows and filter banks included; not a learnable DFT basis): "
-            "wrap the call in torch.no_grad() or detach() the inputs."
+            "input, learnable windows, filter banks and DFT bases included): wrap the call in torch.no_grad() or "
+            "detach() the inputs."
         )
 
 
