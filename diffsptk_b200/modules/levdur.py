@@ -27,7 +27,8 @@ class LevinsonDurbin(BaseFunctionalModule):
 
     The reference adds ``eps * I`` to a dense Toeplitz matrix and calls ``torch.linalg.solve``
     (levdur.py:113-127); the kernel runs the Levinson recursion on the same regularised system.
-    The ``eye`` buffer is kept (name and shape) for state compatibility; eps is read from it.
+    The ``eye`` buffer (``eps * I``) is kept under the reference's name and shape for state compatibility; the
+    kernel takes ``eps`` as the Python value the buffer was built from (changing the buffer in place has no effect).
     """
 
     _takes_input_size = True
