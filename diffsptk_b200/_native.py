@@ -92,6 +92,8 @@ _PLAIN = {
     "dsb200_launch_count": (C.c_int64, []),
     "dsb200_last_kernel": (C.c_char_p, []),
     "dsb200_set_sm_margin": (C.c_int, [_I32]),
+    "dsb200_set_knob": (C.c_int, [C.c_char_p, _I32]),
+    "dsb200_clear_knobs": (C.c_int, []),
     "dsb200_num_frames": (C.c_int64, [_I64, _I32]),
     "dsb200_pipeline_create": (C.c_int, [C.POINTER(C.c_void_p), _INT, _I64, _I64, C.POINTER(StftParams), _INT]),
     "dsb200_pipeline_stft_host": (C.c_int, [_P, _P, _P, _P, _I64]),
@@ -166,6 +168,16 @@ def set_sm_margin(n_sms: int) -> int:
     if rc < 0:
         check(rc)
     return rc
+
+
+def set_knob(name: str, value: int) -> None:
+    """Set a tuning knob of the kernels (README.md's table, without the ``DSB200_`` prefix); wins over the environment."""
+    check(load().dsb200_set_knob(name.encode(), int(value)))
+
+
+def clear_knobs() -> None:
+    """Forget every knob set through :func:`set_knob`."""
+    check(load().dsb200_clear_knobs())
 
 
 def last_kernel() -> str:

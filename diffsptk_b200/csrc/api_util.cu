@@ -3,7 +3,9 @@
 #include <cstdarg>
 #include <cstring>
 #include <map>
+#include <cstdlib>
 #include <mutex>
+#include <string>
 #include <tuple>
 
 #include "common.cuh"
@@ -50,6 +52,21 @@ int sm_count(int device) {
   const cudaDeviceProp* p = props(device);
   const int n = (p ? p->multiProcessorCount : 148) - g_sm_margin.load(std::memory_order_relaxed);
   return n > 1 ? n : 1;
+}
+
+// Tuning knobs: a value set through dsb200_set_knob wins over the environment variable DSB200_<name>, which wins over
+// the built-in default.  Looked up on every launch (one map probe + one getenv), so one process can sweep a knob.
+static std::map<std::string, int> g_knobs;
+
+int knob(const char* name, int dflt) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_knobs.find(name);
+    if (it != g_knobs.end()) return it->second;
+  }
+  const std::string env = std::string("DSB200_") + name;
+  const char* e = getenv(env.c_str());
+  return (e != nullptr && *e != '\0') ? atoi(e) : dflt;
 }
 
 int max_dynamic_smem(int device) {
@@ -107,6 +124,19 @@ const char* dsb200_last_kernel(void) { return dsb200::g_last_kernel; }
 int dsb200_set_sm_margin(int32_t n_sms) {
   if (n_sms < 0) return dsb200::fail(DSB200_E_BAD_PARAM, "sm margin must be non-negative");
   return dsb200::g_sm_margin.exchange(n_sms, std::memory_order_relaxed);
+}
+
+int dsb200_set_knob(const char* name, int32_t value) {
+  if (name == nullptr || *name == '\0') return dsb200::fail(DSB200_E_BAD_PARAM, "knob name is empty");
+  std::lock_guard<std::mutex> lk(dsb200::g_mu);
+  dsb200::g_knobs[name] = value;
+  return DSB200_OK;
+}
+
+int dsb200_clear_knobs(void) {
+  std::lock_guard<std::mutex> lk(dsb200::g_mu);
+  dsb200::g_knobs.clear();
+  return DSB200_OK;
 }
 
 int64_t dsb200_num_frames(int64_t T, int32_t frame_period) {

@@ -51,6 +51,7 @@ struct DeviceScope {  // selects `device` for the duration of one ABI call
 
 int sm_count(int device);               // cached multiProcessorCount
 int max_dynamic_smem(int device);       // cached sharedMemPerBlockOptin
+int knob(const char* name, int dflt);   // tuning knob: dsb200_set_knob > environment DSB200_<name> > dflt
 
 // Device twiddle table W_n^k = exp(-2*pi*i*k/n), k = 0..n-1, interleaved (re, im), built in
 // float64 with sincospi and cached per (device, n, dtype).  Returns nullptr on failure.
@@ -113,6 +114,18 @@ __device__ __forceinline__ int64_t pad_index(int64_t p, int64_t T, int mode) {
       return p < 0 ? p + T : p - T;
     default:
       return -1;
+  }
+}
+
+// Persistent kernels whose warps all run the same alternation of phases (a multiply-add phase, then a latency-bound
+// one) start in lockstep and stay there: the warps that share a scheduler then fight over the FP32 pipe in one phase
+// and leave it idle in the other.  Delaying the k-th warp of a scheduler (warp index / 4) by k * cycles at start-up
+// offsets the phases once; nothing re-synchronises them afterwards (no CTA barrier in the main loops).
+__device__ __forceinline__ void stagger_start(int cycles) {
+  const int slot = static_cast<int>(threadIdx.x >> 7);
+  if (cycles > 0 && slot > 0) {
+    const long long t0 = clock64(), span = static_cast<long long>(cycles) * slot;
+    while (clock64() - t0 < span) __nanosleep(64);
   }
 }
 

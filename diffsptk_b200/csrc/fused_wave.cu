@@ -35,6 +35,8 @@ constexpr int kHalfUnit = 16; // frames staged at a time
 constexpr int kCh = 25;       // samples per lane (16 lanes x 25 = 400 >= frame_length)
 constexpr int kLag = 25;      // lags 0..24
 constexpr int kHalo = kLag - 1;
+constexpr int kLpcVariant = 0;  // default of the knob LPC_V (kLv* bits)
+constexpr int kLpcStagger = 0;  // default of the knob LPC_STAGGER (cycles per scheduler slot)
 
 struct LArgs {
   const float* x;
@@ -44,12 +46,19 @@ struct LArgs {
   int L, P, left, pad_mode, M;
   int span;             // floats staged per half unit: 15 P + 400 + 24, rounded up to 4
   int bulk_in, bulk_out;
+  int stagger;          // start-up offset between the warps of one scheduler, cycles (stagger_start)
   double eps;
 };
 
 // FULL: frame_length == 400 exactly -- every chunk sample is inside the frame, and only lane 15's halo
 // (samples 400..423) must be forced to zero; otherwise every load is compared with the per-lane limit.
-template <bool FULL, int kLWarps>
+//
+// V (variant bits, knob LPC_V; FULL builds only): 1 = the last lane reads its halo through the zero tail of the window
+// table instead of selecting zeros (48 FSEL per lane and sub-step); 2 = the window product is one packed multiply per
+// sample pair; 4 = lpc_order == 24 exactly: the Levinson recursion is unrolled without its per-order guards.
+constexpr int kLvHalo = 1, kLvMul2 = 2, kLvM24 = 4;
+
+template <bool FULL, int kLWarps, int V = 0>
 __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A) {
   constexpr int kLThreads = kLWarps * 32;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -89,6 +98,7 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
   bool cur_bulk = false;
   if (u < A.n_units) cur_bulk = stage_half(b, g, 0);
   bool store_pending = false;
+  stagger_start(A.stagger);
 
   while (u < A.n_units) {
     const int f0 = kUnit * g;                       // first frame of the unit
@@ -117,12 +127,24 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
         const float* pa = span + fa * A.P + kCh * l;
         const float* pb = pa + 2 * A.P;
         const float* pw = win + kCh * l;
+        // kLvHalo: the last lane's halo (samples 400..423) is read from win[400..423] = 0 (0 * 0, never sample * 0)
+        const bool redirect = FULL && (V & kLvHalo) && last_lane;
+        const float* pah = redirect ? pw : pa;
+        const float* pbh = redirect ? pw : pb;
         auto ld = [&](int i) {                      // windowed sample pair i of this lane's chunk (+ halo)
           // samples past the frame end are structural zeros (selected, never multiplied: 0 * inf = nan)
-          const bool out = FULL ? (last_lane && i >= kCh) : (i >= lim);
-          float xa = pa[i], xb = pb[i];
           const float w = pw[i];
-          if (out) { xa = 0.0f; xb = 0.0f; }
+          float xa, xb;
+          if (FULL && (V & kLvHalo)) {
+            xa = (i >= kCh) ? pah[i] : pa[i];
+            xb = (i >= kCh) ? pbh[i] : pb[i];
+          } else {
+            const bool out = FULL ? (last_lane && i >= kCh) : (i >= lim);
+            xa = pa[i];
+            xb = pb[i];
+            if (out) { xa = 0.0f; xb = 0.0f; }
+          }
+          if (V & kLvMul2) return __fmul2_rn(make_float2(xa, xb), make_float2(w, w));
           return make_float2(xa * w, xb * w);
         };
         float2 x2[kCh + kHalo];
@@ -169,7 +191,7 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
     double E = r[0] + A.eps;
 #pragma unroll
     for (int i = 1; i < kLag; ++i) {
-      if (i <= A.M) {
+      if ((V & kLvM24) || i <= A.M) {
         double acc = r[i];
 #pragma unroll
         for (int j = 1; j < i; ++j) acc = fma(a[j], r[i - j], acc);
@@ -192,7 +214,7 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
     double gain = r[0];
 #pragma unroll
     for (int j = 1; j < kLag; ++j)
-      if (j <= A.M) gain = fma(r[j], a[j], gain);
+      if ((V & kLvM24) || j <= A.M) gain = fma(r[j], a[j], gain);
     a[0] = sqrt(gain);
 
     const int64_t row0 = static_cast<int64_t>(b) * A.n_frames + f0;
@@ -202,7 +224,7 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
       float* o = rbuf + lane * D;                   // dense [32][D] tile (D <= 25 fits in the row storage)
 #pragma unroll
       for (int k = 0; k < kLag; ++k)
-        if (k < D) o[k] = static_cast<float>(a[k]);
+        if ((V & kLvM24) || k < D) o[k] = static_cast<float>(a[k]);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) bulk_s2g(A.y + row0 * D, rbuf, static_cast<uint32_t>(kUnit * D) * 4u);
@@ -230,12 +252,8 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
   const int left = fp->center ? fp->frame_length / 2 : 0;
   const int span = ((kHalfUnit - 1) * fp->frame_period + 16 * kCh + kHalo + 3) & ~3;
   const size_t per_warp = static_cast<size_t>(span) * 4 + 2 * 16 * kLag * 8 + kUnit * kLag * 4;
-  // DSB200_LPC_W=8|12 (tuning knob, read once): warps per CTA
-  static const int w_knob = [] {
-    const char* e = getenv("DSB200_LPC_W");
-    return e != nullptr ? atoi(e) : 12;
-  }();
-  int kLWarps = (w_knob == 8) ? 8 : 12;
+  // knob LPC_W = 8 | 12: warps per CTA
+  int kLWarps = (knob("LPC_W", 12) == 8) ? 8 : 12;
   if (8 * kLWarps + 448 * sizeof(float) + kLWarps * per_warp > static_cast<size_t>(max_dynamic_smem(device))) kLWarps = 8;
   const size_t smem = 8 * kLWarps + 448 * sizeof(float) + kLWarps * per_warp;
   if (smem > static_cast<size_t>(max_dynamic_smem(device))) return DSB200_E_UNSUPPORTED;
@@ -258,6 +276,7 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
               ((kHalfUnit * fp->frame_period) % 4 == 0);
   A.bulk_out = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
   A.eps = eps;
+  A.stagger = knob("LPC_STAGGER", kLpcStagger);
   const bool full = fp->frame_length == 16 * kCh;
   const int blocks = static_cast<int>(std::min<int64_t>((A.n_units + kLWarps - 1) / kLWarps, sm_count(device)));
   auto launch = [&](auto kern) -> int {
@@ -266,8 +285,18 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
     return DSB200_OK;
   };
   int rc;
+  int v = full ? knob("LPC_V", kLpcVariant) : 0;
+  if (M != kLag - 1) v &= ~kLvM24;
   if (kLWarps == 8) rc = full ? launch(lpc_wave_kernel<true, 8>) : launch(lpc_wave_kernel<false, 8>);
-  else rc = full ? launch(lpc_wave_kernel<true, 12>) : launch(lpc_wave_kernel<false, 12>);
+  else if (!full) rc = launch(lpc_wave_kernel<false, 12>);
+  else switch (v) {
+    case 1: rc = launch(lpc_wave_kernel<true, 12, 1>); break;
+    case 2: rc = launch(lpc_wave_kernel<true, 12, 2>); break;
+    case 3: rc = launch(lpc_wave_kernel<true, 12, 3>); break;
+    case 4: rc = launch(lpc_wave_kernel<true, 12, 4>); break;
+    case 7: rc = launch(lpc_wave_kernel<true, 12, 7>); break;
+    default: rc = launch(lpc_wave_kernel<true, 12>); break;
+  }
   if (rc != DSB200_OK) return rc;
   return after_launch("lpc_wave_kernel");
 }

@@ -53,7 +53,10 @@ struct MArgs {
   const float* av;   // [D]
   int64_t rows;
   int D, J, n_iter;
+  int stagger;       // start-up offset between the warps of one scheduler, cycles (stagger_start)
 };
+
+constexpr int kMcepStagger = 0;  // default of the knob MCEP_STAGGER
 
 // Compile-time loop: the elimination below indexes register arrays with the loop variable, so it must be
 // expanded even when the body is too large for `#pragma unroll` heuristics.
@@ -136,6 +139,7 @@ __global__ void __launch_bounds__(kMW * 32, 1) mcep_fast_kernel(const MArgs A) {
 
   for (int g = 0; g < 2; ++g) col[64 * g + 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
   __syncwarp();
+  stagger_start(A.stagger);
   const int64_t n_oct = (A.rows + 7) / 8;
   for (int64_t oct = static_cast<int64_t>(blockIdx.x) * kMW + warp; oct < n_oct;
        oct += static_cast<int64_t>(gridDim.x) * kMW) {
@@ -589,12 +593,10 @@ int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_para
   A.D = p->cep_order + 1;
   A.J = 2 * p->cep_order + 1;
   A.n_iter = p->n_iter;
-  // DSB200_MCEP_V=8 | 120 | 12 | 16 | 122 | 162 (tuning knob, read once): warps per CTA (x frame pairs per elimination pass:
+  // knob MCEP_V = 8 | 120 | 12 | 16 | 122 | 162: warps per CTA (x frame pairs per elimination pass:
   // 4 at 8 warps, else 2); 8 and 120 keep the fully unrolled elimination + back substitution for A/B runs
-  static const int variant = [] {
-    const char* e = getenv("DSB200_MCEP_V");
-    return e != nullptr ? atoi(e) : 12;
-  }();
+  const int variant = knob("MCEP_V", 12);
+  A.stagger = knob("MCEP_STAGGER", kMcepStagger);
   if (variant == 8) return launch_mcep_fast<8, 4, 0>(A, device, stream);      // round-1 shape
   if (variant == 120) return launch_mcep_fast<12, 2, 0>(A, device, stream);   // 12 warps, unrolled elimination
   if (variant == 122) return launch_mcep_fast<12, 2, 2>(A, device, stream);   // four rows of one system per lane

@@ -84,7 +84,11 @@ struct Args {
   int mf_tail;             // floats per warp BEHIND the exchange planes: the run's parked feature rows (the planes
                            // are overwritten by the next quad's transposes, the rows must survive them)
   int64_t mf_row_off;
+  int stagger;             // start-up offset between the warps of one scheduler, cycles (stagger_start)
 };
+
+constexpr int kStftStagger = 0;  // defaults of the knobs STFT_STAGGER / MFCC_STAGGER
+constexpr int kMfccStagger = 0;
 
 constexpr int kFmtMfcc = 5;  // internal: stage amplitudes, then filter bank + DCT + lifter on chip
 constexpr int kSegLen = kPlanSegLen;     // bins per filter-bank segment
@@ -294,6 +298,7 @@ __global__ void __launch_bounds__(W * 32, 1) stft512_kernel(const Args A) {
 #pragma unroll
     for (int k1 = 0; k1 < 8; ++k1) hreg[RT ? k1 : 0] = htw[16 * k1 + l];
   }
+  stagger_start(A.stagger);
   const int n_warps = gridDim.x * kWarps;
   // consecutive warps take consecutive quads (L2 locality); the MFCC build takes them in RUNS of `run` quads per warp
   // so that the feature rows of a run (contiguous in the output) leave in one burst -- with the all-gather fused in,
@@ -826,17 +831,12 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
               (f.frame_period % 4 == 0);
   A.eps = static_cast<float>(s.eps);
   A.rel_floor = s.has_relative_floor ? static_cast<float>(s.relative_floor) : 0.0f;
+  A.stagger = knob("STFT_STAGGER", kStftStagger);
   return DSB200_OK;
 }
 
-// DSB200_STFT_V=0|1 (tuning knob, read once): kernel variant bits, see stft512_kernel
-static int stft_variant_knob() {
-  static const int v = [] {
-    const char* e = getenv("DSB200_STFT_V");
-    return e != nullptr ? atoi(e) : kDefaultVariant;
-  }();
-  return v;
-}
+// knob STFT_V: kernel variant bits, see stft512_kernel
+static int stft_variant_knob() { return knob("STFT_V", kDefaultVariant); }
 
 static size_t smem_bytes(const Args& A, int mf_floats, int kWarps, int variant = 0) {
   const size_t bufs = (variant & kVSingleBuf) ? 1 : 2, tws = (variant & kVTwSmem) ? 256 : 0;
@@ -884,11 +884,7 @@ int stft512_try(const float* x, const float* window, float* y, int64_t batch, in
     const int v = stft_variant_knob();
     if ((v & kVPair2) && A.P == 80) {
       if ((v & 6) == 6) {   // single buffer + shared-memory twiddles: 16 or 20 warps (DSB200_STFT_W)
-        static const int w_knob = [] {
-          const char* e = getenv("DSB200_STFT_W");
-          return e != nullptr ? atoi(e) : kDefaultWarpsV7;
-        }();
-        if (w_knob == 20) {
+        if (knob("STFT_W", kDefaultWarpsV7) == 20) {
           const size_t sm20 = smem_bytes(A, 0, 20, 7);
           if (sm20 <= static_cast<size_t>(max_dynamic_smem(device)))
             return launch_fmt<13, false, 20, 7>(A, p->spec.out_format, sm20, device, stream);
@@ -922,10 +918,7 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   const int D = M + (mp->out_format == DSB200_MFCC_Y ? 0 : (mp->out_format == DSB200_MFCC_YCE ? 2 : 1));
   // amplitude rows, segment sums, mel rows and the quad's feature rows live inside the per-warp exchange region
   if (mf_warp_floats(C) * 4 > kXchBytesPerWarp) return DSB200_E_UNSUPPORTED;
-  static const int run_knob = [] {   // DSB200_MFCC_RUN=1|4 (tuning knob, read once)
-    const char* e = getenv("DSB200_MFCC_RUN");
-    return e != nullptr ? atoi(e) : 4;
-  }();
+  const int run_knob = knob("MFCC_RUN", 4);   // 1 | 4
   const size_t smem_max = static_cast<size_t>(max_dynamic_smem(device));
   int mf_run = run_knob == 4 ? 4 : 1;
   A.mf_tail = (mf_run * 4 * D + 3) & ~3;
@@ -935,10 +928,7 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   }
   // 12 warps (168 registers) by default: with the planned filter bank the epilogue is short enough that the extra
   // registers beat the extra warps (round 2, 1024 x 10 s: 1.39 ms at 12 warps, 1.44 ms at 16).
-  static const int warps_knob = [] {   // DSB200_MFCC_WARPS=12|16 (tuning knob, read once)
-    const char* e = getenv("DSB200_MFCC_WARPS");
-    return e != nullptr ? atoi(e) : 12;
-  }();
+  const int warps_knob = knob("MFCC_WARPS", 12);   // 12 | 16
   const bool w16 = NJ == 13 && warps_knob == 16 && smem_bytes(A, mf_floats, kWarpsSpectrum) <= smem_max;
   const int kWarps = w16 ? kWarpsSpectrum : kWarpsMfcc;
   const size_t smem = smem_bytes(A, mf_floats, kWarps);
@@ -956,6 +946,7 @@ int mfcc_wave_try(const float* x, const float* window, const float* H, const int
   A.n_dst = n_dst;
   A.mf_run = mf_run;
   A.mf_row_off = row_off;
+  A.stagger = knob("MFCC_STAGGER", kMfccStagger);
   A.mf_vec = 1;
   for (int d = 0; d < n_dst; ++d) {
     A.y_dst[d] = y_dst[d];

@@ -121,6 +121,12 @@ DSB200_API const char* dsb200_last_kernel(void);
  * margin of n SMs the kernels launch on (SM count - n) SMs and leave the rest to it.  Process-wide; returns the
  * previous margin (>= 0), or DSB200_E_BAD_PARAM. */
 DSB200_API int dsb200_set_sm_margin(int32_t n_sms);
+/* Tuning knobs of the kernels (warps per CTA, kernel variants, start-up stagger; the table in README.md).  A knob is an
+ * integer looked up at every launch: a value set here wins over the environment variable DSB200_<name>, which wins over
+ * the built-in default (the measured winner).  No reference counterpart: measurement plumbing (tools/sweep_knobs.py).
+ * dsb200_clear_knobs forgets every value set through dsb200_set_knob. */
+DSB200_API int dsb200_set_knob(const char* name, int32_t value);
+DSB200_API int dsb200_clear_knobs(void);
 
 /* Number of frames for a waveform of T samples: (T-1)/P + 1 (frame.py:138); 0 if T <= 0. */
 DSB200_API int64_t dsb200_num_frames(int64_t T, int32_t frame_period);
