@@ -11,7 +11,9 @@ python -c "import __graft_entry__ as g; g.build()" > $O/e1_build.txt 2>&1
   "lpc:LPC_W=8+LPC_STAGGER=0,12000,25000,40000" \
   "stft:STFT_STAGGER=400,800,1600,3000" \
   "mfcc:MFCC_STAGGER=1000,3000,6000,12000,24000" \
-  "mcep:MCEP_STAGGER=10000,20000,44000,80000" ) > $O/e1_sweep.txt 2> $O/e1_sweep.err
+  "mcep:MCEP_STAGGER=10000,20000,44000,80000" \
+  "mfcc:MFCC_WARPS=16+MFCC_STAGGER=0,2000,5000" \
+  "mcep:MCEP_V=122+MCEP_STAGGER=0,20000,44000" ) > $O/e1_sweep.txt 2> $O/e1_sweep.err
 cat $O/e1_sweep.txt | cut -c1-260
 tail -3 $O/e1_sweep.err
 (time timeout 300 python -m pytest tests/test_gpu_autograd.py -q -x -p no:cacheprovider -k "learnable_dft_basis") > $O/e1_pytest.txt 2>&1
