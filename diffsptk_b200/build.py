@@ -63,22 +63,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ_DIR, exist_ok=True)
     nvcc = _nvcc()
 
+    headers = [d for d in deps if not d.endswith(".cu")]
+
     def compile_one(src):
+        # an object is reused when its source, every header and the flags are unchanged (build/ is scratch: it is
+        # neither tracked nor shipped, so a fresh checkout compiles everything)
         obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+        obj_digest = _digest([src] + headers)
+        if not force and not verbose and os.path.exists(obj) and os.path.exists(obj + ".digest") \
+                and open(obj + ".digest").read() == obj_digest:
+            return obj
         cmd = [nvcc, *NVCC_FLAGS, "-Xptxas", "-v" if verbose else "-warn-spills", "-c", src, "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             sys.stderr.write(r.stderr)
+        with open(obj + ".digest", "w") as f:
+            f.write(obj_digest)
         return obj
 
     with cf.ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
+    # link beside the target and rename: a reader (a loader, a snapshot of the tree) never sees a partial library
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB_PATH)
     with open(stamp, "w") as f:
         f.write(digest)
     return LIB_PATH

@@ -57,6 +57,9 @@ struct LArgs {
 // table instead of selecting zeros (48 FSEL per lane and sub-step); 2 = the window product is one packed multiply per
 // sample pair; 4 = lpc_order == 24 exactly: the Levinson recursion is unrolled without its per-order guards.
 constexpr int kLvHalo = 1, kLvMul2 = 2, kLvM24 = 4;
+// Timing diagnostics (WRONG results by construction; compiled only with -DDSB200_LPC_DIAG): 8 = no Levinson phase
+// (the lane's autocorrelation row is stored instead), 16 = no cross-lane reduction of the lag sums.
+constexpr int kLvNoLev = 8, kLvNoRed = 16;
 
 template <bool FULL, int kLWarps, int V = 0>
 __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A) {
@@ -160,14 +163,20 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
           for (int k = 0; k < kLag; ++k) acc[k] = __ffma2_rn(x2[i], x2[i + k], acc[k]);
         }
         // reduce the 16 per-lane partial sums of every lag through shared memory
-#pragma unroll
-        for (int k = 0; k < kLag; ++k) part[l * kLag + k] = acc[k];
-        __syncwarp();
         float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+        if (V & kLvNoRed) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          s0 = __fadd2_rn(s0, part[j * kLag + l]);
-          if (l < kLag - 16) s1 = __fadd2_rn(s1, part[j * kLag + 16 + l]);
+          for (int k = 0; k < kLag; ++k) s0 = __fadd2_rn(s0, acc[k]);
+          s1 = s0;
+        } else {
+#pragma unroll
+          for (int k = 0; k < kLag; ++k) part[l * kLag + k] = acc[k];
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            s0 = __fadd2_rn(s0, part[j * kLag + l]);
+            if (l < kLag - 16) s1 = __fadd2_rn(s1, part[j * kLag + 16 + l]);
+          }
         }
         const int fu = kHalfUnit * half + fa;       // frame within the unit
         rbuf[fu * kLag + l] = s0.x;
@@ -189,8 +198,13 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
 #pragma unroll
     for (int k = 0; k < kLag; ++k) r[k] = static_cast<double>(rbuf[lane * kLag + k]);
     double E = r[0] + A.eps;
+    if (V & kLvNoLev) {
+#pragma unroll
+      for (int i = 1; i < kLag; ++i) a[i] = r[i];
+    }
 #pragma unroll
     for (int i = 1; i < kLag; ++i) {
+      if (V & kLvNoLev) break;
       if ((V & kLvM24) || i <= A.M) {
         double acc = r[i];
 #pragma unroll
@@ -295,6 +309,11 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
     case 3: rc = launch(lpc_wave_kernel<true, 12, 3>); break;
     case 4: rc = launch(lpc_wave_kernel<true, 12, 4>); break;
     case 7: rc = launch(lpc_wave_kernel<true, 12, 7>); break;
+#ifdef DSB200_LPC_DIAG
+    case 8: rc = launch(lpc_wave_kernel<true, 12, 8>); break;
+    case 16: rc = launch(lpc_wave_kernel<true, 12, 16>); break;
+    case 24: rc = launch(lpc_wave_kernel<true, 12, 24>); break;
+#endif
     default: rc = launch(lpc_wave_kernel<true, 12>); break;
   }
   if (rc != DSB200_OK) return rc;

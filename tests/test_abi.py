@@ -60,6 +60,17 @@ def test_sm_margin_setter(native_lib):
     assert N.set_sm_margin(0) == 0
 
 
+def test_knob_setter(native_lib):
+    """Tuning knobs are host-side state: set / clear / reject an empty name without any CUDA call."""
+    from diffsptk_b200 import _native as N
+    N.set_knob("LPC_STAGGER", 12000)
+    N.set_knob("LPC_STAGGER", 0)
+    N.clear_knobs()
+    assert native_lib.dsb200_set_knob(b"", 1) == N.E_BAD_PARAM
+    assert b"knob" in native_lib.dsb200_last_error()
+    assert native_lib.dsb200_set_knob(None, 1) == N.E_BAD_PARAM
+
+
 def test_sass_is_sm100a(native_lib):
     from diffsptk_b200 import _native
     out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True)
