@@ -21,6 +21,7 @@
 // Envelope: float32, frame_length <= 400, lpc_order <= 24, even frame_period, no zmean.
 #include <algorithm>
 #include <cstdlib>
+#include <type_traits>
 
 #include "bulk.cuh"
 
@@ -56,10 +57,10 @@ struct LArgs {
 // V (variant bits, knob LPC_V; FULL builds only): 1 = the last lane reads its halo through the zero tail of the window
 // table instead of selecting zeros (48 FSEL per lane and sub-step); 2 = the window product is one packed multiply per
 // sample pair; 4 = lpc_order == 24 exactly: the Levinson recursion is unrolled without its per-order guards.
-constexpr int kLvHalo = 1, kLvMul2 = 2, kLvM24 = 4;
-// Timing diagnostics (WRONG results by construction; compiled only with -DDSB200_LPC_DIAG): 8 = no Levinson phase
-// (the lane's autocorrelation row is stored instead), 16 = no cross-lane reduction of the lag sums.
-constexpr int kLvNoLev = 8, kLvNoRed = 16;
+constexpr int kLvHalo = 1, kLvMul2 = 2, kLvM24 = 4, kLvRolled = 8;   // 8: the rolled Levinson recursion (see there)
+// Timing diagnostics (WRONG results by construction; compiled only with -DDSB200_LPC_DIAG): 64 = no Levinson phase
+// (the lane's autocorrelation row is stored instead), 128 = no cross-lane reduction of the lag sums.
+constexpr int kLvNoLev = 64, kLvNoRed = 128;
 
 template <bool FULL, int kLWarps, int V = 0>
 __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A) {
@@ -194,7 +195,67 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
     }
 
     // Levinson-Durbin, one frame per lane, float64 state (see lpc.cu for the recursion)
-    double r[kLag], a[kLag];
+    double a[kLag];
+    if (V & kLvRolled) {
+      // Rolled form: one loop body serves every order, so the phase is ~250 instructions instead of ~3 000 (the
+      // unrolled recursion streams 48 KB of code per unit through the instruction cache and evicts the lag loop).
+      // No register is indexed by the order: besides a[j] the lane keeps the REVERSED predictor ar[j] = a[i - j]
+      // (ar[i] = a[0] = 1, zero beyond), so that
+      //     acc_i   = r[i] + sum_{j<i} a[j] r[i-j] = sum_m ar[m] r[m]              (r[m]: float64 column in `part`)
+      //     a'[j]   = a[j] + k ar[j]            (j = i gives a'[i] = k, positions beyond i stay 0)
+      //     ar'[j]  = ar[j-1] + k a[j-1],  ar'[1] = k                               (the reversal pivot moves with i)
+      // are the same statements for every i.  Orders 1..11 touch positions <= 12 only (half-width body).
+      double* rd = reinterpret_cast<double*>(wbase + static_cast<size_t>(A.span) * 4) + lane;   // [24][32]
+#pragma unroll
+      for (int k = 1; k < kLag; ++k) rd[(k - 1) * 32] = static_cast<double>(rbuf[lane * kLag + k]);
+      const double r0 = static_cast<double>(rbuf[lane * kLag]);
+      double ar[kLag];   // positions 1..24 at indices 1..24 (index 0 unused)
+#pragma unroll
+      for (int j = 1; j < kLag; ++j) { a[j] = 0.0; ar[j] = 0.0; }
+      ar[1] = 1.0;
+      double E = r0 + A.eps;
+      auto orders = [&](auto width, int i0, int i1) {
+        constexpr int W = decltype(width)::value;
+#pragma unroll 1
+        for (int i = i0; i <= i1; ++i) {
+          double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+          for (int m = 1; m <= W; m += 4) {
+            s0 = fma(ar[m], rd[(m - 1) * 32], s0);
+            s1 = fma(ar[m + 1], rd[m * 32], s1);
+            s2 = fma(ar[m + 2], rd[(m + 1) * 32], s2);
+            s3 = fma(ar[m + 3], rd[(m + 2) * 32], s3);
+          }
+          const double acc = (s0 + s1) + (s2 + s3);
+          double inv = static_cast<double>(__frcp_rn(static_cast<float>(E)));
+          inv = fma(inv, fma(-E, inv, 1.0), inv);
+          inv = fma(inv, fma(-E, inv, 1.0), inv);
+          const bool tame = fabs(E) > 1e-30 && fabs(E) < 1e30;
+          const double kk = tame ? (-acc * inv) : (-acc / E);
+#pragma unroll
+          for (int j = W; j >= 2; --j) {   // descending: positions j - 1 are still the old ones when j reads them
+            const double ta = fma(kk, ar[j], a[j]);
+            ar[j] = fma(kk, a[j - 1], ar[j - 1]);
+            a[j] = ta;
+          }
+          a[1] = fma(kk, ar[1], a[1]);
+          ar[1] = kk;
+          E *= fma(-kk, kk, 1.0);
+        }
+      };
+      orders(std::integral_constant<int, 12>{}, 1, A.M < 11 ? A.M : 11);
+      orders(std::integral_constant<int, 24>{}, 12, A.M);
+      double g0 = r0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+      for (int m = 1; m < kLag; m += 4) {
+        g0 = fma(a[m], rd[(m - 1) * 32], g0);
+        g1 = fma(a[m + 1], rd[m * 32], g1);
+        g2 = fma(a[m + 2], rd[(m + 1) * 32], g2);
+        g3 = fma(a[m + 3], rd[(m + 2) * 32], g3);
+      }
+      a[0] = sqrt((g0 + g1) + (g2 + g3));
+    } else {
+    double r[kLag];
 #pragma unroll
     for (int k = 0; k < kLag; ++k) r[k] = static_cast<double>(rbuf[lane * kLag + k]);
     double E = r[0] + A.eps;
@@ -230,6 +291,7 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
     for (int j = 1; j < kLag; ++j)
       if ((V & kLvM24) || j <= A.M) gain = fma(r[j], a[j], gain);
     a[0] = sqrt(gain);
+    }
 
     const int64_t row0 = static_cast<int64_t>(b) * A.n_frames + f0;
     const bool staged = A.bulk_out && nvalid == kUnit && (((row0 * D) & 3) == 0);
@@ -301,18 +363,19 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
   int rc;
   int v = full ? knob("LPC_V", kLpcVariant) : 0;
   if (M != kLag - 1) v &= ~kLvM24;
+  if (v & kLvRolled) v &= ~kLvM24;
   if (kLWarps == 8) rc = full ? launch(lpc_wave_kernel<true, 8>) : launch(lpc_wave_kernel<false, 8>);
   else if (!full) rc = launch(lpc_wave_kernel<false, 12>);
   else switch (v) {
-    case 1: rc = launch(lpc_wave_kernel<true, 12, 1>); break;
-    case 2: rc = launch(lpc_wave_kernel<true, 12, 2>); break;
     case 3: rc = launch(lpc_wave_kernel<true, 12, 3>); break;
-    case 4: rc = launch(lpc_wave_kernel<true, 12, 4>); break;
     case 7: rc = launch(lpc_wave_kernel<true, 12, 7>); break;
-#ifdef DSB200_LPC_DIAG
     case 8: rc = launch(lpc_wave_kernel<true, 12, 8>); break;
-    case 16: rc = launch(lpc_wave_kernel<true, 12, 16>); break;
-    case 24: rc = launch(lpc_wave_kernel<true, 12, 24>); break;
+    case 11: rc = launch(lpc_wave_kernel<true, 12, 11>); break;
+#ifdef DSB200_LPC_DIAG
+    case 64: rc = launch(lpc_wave_kernel<true, 12, 64>); break;
+    case 128: rc = launch(lpc_wave_kernel<true, 12, 128>); break;
+    case 192: rc = launch(lpc_wave_kernel<true, 12, 192>); break;
+    case 195: rc = launch(lpc_wave_kernel<true, 12, 195>); break;
 #endif
     default: rc = launch(lpc_wave_kernel<true, 12>); break;
   }
