@@ -37,6 +37,7 @@ constexpr int kCh = 25;       // samples per lane (16 lanes x 25 = 400 >= frame_
 constexpr int kLag = 25;      // lags 0..24
 constexpr int kHalo = kLag - 1;
 constexpr int kLpcVariant = 0;  // default of the knob LPC_V (kLv* bits)
+constexpr int kLpcWarps2 = 12;  // default of the knob LPC_W2 (warps per CTA of the lag-pair kernel)
 constexpr int kLpcStagger = 0;  // default of the knob LPC_STAGGER (cycles per scheduler slot)
 
 struct LArgs {
@@ -316,6 +317,195 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
   if (store_pending && lane == 0) bulk_wait_read();
 }
 
+
+// ---- lag-pair form (frame_length = 400 exactly; knob LPC_V bit 16) -------------------------------------------
+// Measured on B200 (tools/bench_ffma2.cu): a packed FFMA2 whose three operands are three different register pairs
+// issues every 3 cycles per scheduler (register-file read bandwidth); with one operand a broadcast scalar (or a
+// reused pair) it issues every 2.  The frame-pair form above, acc[k] += x2[i] * x2[i + k], is the 3-cycle kind.
+// Here a half-warp owns ONE frame and the pair is two adjacent lags of it:
+//     (r[2m], r[2m+1]) += x[i] * (x[i + 2m], x[i + 2m + 1])            -- scalar x[i] times a pair of samples
+// Lane l owns samples [26 l, 26 l + 26) and reads 50 (25 aligned pairs E[j] = (x[2j], x[2j+1]), windowed by one
+// FMUL2 each, 64-bit loads).  An even sample i = 2t multiplies E[t + m] into (r[2m], r[2m+1]); an odd sample multiplies
+// the same kind of aligned pair, E[t + 1 + m], into a SECOND accumulator set (r[2m+1], r[2m+2]); the two sets are
+// merged once per frame (lag 0 of the odd samples is one scalar FFMA each).  13 + 12 accumulator pairs, 13 x 25 =
+// 325 FFMA2 per frame and lane.  Samples past the frame
+// end (lane 14 from pair 18, lane 15 from pair 5) are read from the zero tail of the window table instead of the
+// staged waveform: 0 * 0, never sample * 0.
+constexpr int kCh2 = 26, kPairs2 = 25, kAcc2 = 13;
+constexpr int kLvLagPair = 16;
+
+template <int kLWarps, int V>
+__global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave2_kernel(const LArgs A) {
+  constexpr int kLThreads = kLWarps * 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int l = lane & 15, h = lane >> 4;
+  const int D = A.M + 1;
+
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw) + warp;
+  float* win = reinterpret_cast<float*>(smem_raw + 8 * kLWarps);  // [448], zero from 400 on
+  constexpr int kPartBytes = 2 * 16 * kAcc2 * 8;
+  const size_t per_warp = static_cast<size_t>(A.span) * 4 + kPartBytes + kUnit * kLag * 4;
+  unsigned char* wbase = reinterpret_cast<unsigned char*>(win + 448) + warp * per_warp;
+  float* span = reinterpret_cast<float*>(wbase);
+  float2* part = reinterpret_cast<float2*>(wbase + static_cast<size_t>(A.span) * 4) + h * (16 * kAcc2);  // [16][13]
+  float* rbuf = reinterpret_cast<float*>(wbase + static_cast<size_t>(A.span) * 4 + kPartBytes);          // [32][25]
+
+  for (int i = tid; i < 448; i += kLThreads) win[i] = i < A.L ? A.window[i] : 0.0f;
+  if (lane == 0) {
+    mbar_init(mbar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();  // the only CTA-wide barrier
+
+  const int n_warps = gridDim.x * kLWarps;
+  int u = blockIdx.x * kLWarps + warp;
+  int b = u / A.units_per_utt, g = u - b * A.units_per_utt;
+  const int db = n_warps / A.units_per_utt, dg = n_warps - db * A.units_per_utt;
+  uint32_t phase = 0u;
+  auto stage_half = [&](int bq, int gq, int half) {
+    stage_span_fast(A.x + static_cast<int64_t>(bq) * A.T, A.T, (kUnit * gq + kHalfUnit * half) * A.P - A.left,
+                    A.span, A.pad_mode, A.bulk_in != 0, span, mbar, lane);
+  };
+  bool cur = false;
+  if (u < A.n_units) { stage_half(b, g, 0); cur = true; }
+  bool store_pending = false;
+  const float2* pw = reinterpret_cast<const float2*>(win + kCh2 * l);
+  const float2* zero = reinterpret_cast<const float2*>(win + 400);
+
+  while (u < A.n_units) {
+    const int f0 = kUnit * g;
+    const int nvalid = (A.n_frames - f0) < kUnit ? (A.n_frames - f0) : kUnit;
+    const int un = u + n_warps;
+    int bn = b + db, gn = g + dg;
+    if (gn >= A.units_per_utt) { gn -= A.units_per_utt; ++bn; }
+
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      if (cur) {
+        mbar_wait(mbar, phase);
+        phase ^= 1u;
+      }
+      __syncwarp();
+      if (half == 0 && store_pending) {             // rbuf doubles as the output staging tile
+        if (lane == 0) bulk_wait_read();
+        store_pending = false;
+        __syncwarp();
+      }
+#pragma unroll 1
+      for (int sub = 0; sub < kHalfUnit / 2; ++sub) {
+        const int fa = 2 * sub + h;                 // this half-warp's frame within the staged half unit
+        const float2* pa = reinterpret_cast<const float2*>(span + fa * A.P + kCh2 * l);
+        const float2* pb = (l == 15) ? zero - 5 : pa;     // pairs 5..17: past the frame end for lane 15
+        const float2* pc = (l >= 14) ? zero - 18 : pa;    // pairs 18..25: past it for lanes 14 and 15
+        auto ld = [&](int j) {
+          const float2 x = j < 5 ? pa[j] : (j < 18 ? pb[j] : pc[j]);
+          return __fmul2_rn(x, pw[j]);
+        };
+        float2 E[kPairs2], ae[kAcc2], ao[kAcc2 - 1];
+        float r0o = 0.0f;                           // lag 0 of the odd samples (no aligned pair starts at lag 0 there)
+#pragma unroll
+        for (int m = 0; m < kAcc2; ++m) ae[m] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int m = 0; m < kAcc2 - 1; ++m) ao[m] = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int j = 0; j < kAcc2; ++j) E[j] = ld(j);
+#pragma unroll
+        for (int t = 0; t < kAcc2; ++t) {           // samples 2t and 2t + 1 of the lane's chunk
+          if (t + kAcc2 < kPairs2) E[t + kAcc2] = ld(t + kAcc2);
+          const float xe = E[t].x, xo = E[t].y;
+          // even sample: lags (2m, 2m+1) from the aligned pair E[t + m]; odd sample: the SAME aligned pairs give
+          // lags (2m+1, 2m+2), kept in a second accumulator set -- no odd-aligned pair is ever formed
+#pragma unroll
+          for (int m = 0; m < kAcc2; ++m) ae[m] = __ffma2_rn(E[t + m], make_float2(xe, xe), ae[m]);
+#pragma unroll
+          for (int m = 0; m < kAcc2 - 1; ++m) ao[m] = __ffma2_rn(E[t + 1 + m], make_float2(xo, xo), ao[m]);
+          r0o = fmaf(xo, xo, r0o);
+        }
+        float2 acc[kAcc2];                          // (r[2m], r[2m+1]) = (ae[m].x + ao[m-1].y, ae[m].y + ao[m].x)
+#pragma unroll
+        for (int m = 0; m < kAcc2; ++m) {
+          acc[m].x = ae[m].x + (m > 0 ? ao[m - 1].y : r0o);
+          acc[m].y = m < kAcc2 - 1 ? ae[m].y + ao[m].x : ae[m].y;
+        }
+        // reduce the 16 per-lane partial sums of every lag pair through shared memory
+#pragma unroll
+        for (int m = 0; m < kAcc2; ++m) part[l * kAcc2 + m] = acc[m];
+        __syncwarp();
+        if (l < kAcc2) {
+          float2 s0 = make_float2(0.0f, 0.0f), s1 = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            s0 = __fadd2_rn(s0, part[j * kAcc2 + l]);
+            s1 = __fadd2_rn(s1, part[(j + 1) * kAcc2 + l]);
+          }
+          s0 = __fadd2_rn(s0, s1);
+          const int fu = kHalfUnit * half + fa;     // frame within the unit
+          rbuf[fu * kLag + 2 * l] = s0.x;
+          if (2 * l + 1 < kLag) rbuf[fu * kLag + 2 * l + 1] = s0.y;
+        }
+        __syncwarp();
+      }
+      if (half == 0) { stage_half(b, g, 1); cur = true; }
+      else if (un < A.n_units) { stage_half(bn, gn, 0); cur = true; }
+      else cur = false;
+    }
+
+    // Levinson-Durbin, one frame per lane, float64 state (as in lpc_wave_kernel)
+    double r[kLag], a[kLag];
+#pragma unroll
+    for (int k = 0; k < kLag; ++k) r[k] = static_cast<double>(rbuf[lane * kLag + k]);
+    double E = r[0] + A.eps;
+#pragma unroll
+    for (int i = 1; i < kLag; ++i) {
+      if ((V & kLvM24) || i <= A.M) {
+        double acc = r[i];
+#pragma unroll
+        for (int j = 1; j < i; ++j) acc = fma(a[j], r[i - j], acc);
+        double inv = static_cast<double>(__frcp_rn(static_cast<float>(E)));
+        inv = fma(inv, fma(-E, inv, 1.0), inv);
+        inv = fma(inv, fma(-E, inv, 1.0), inv);
+        const bool tame = fabs(E) > 1e-30 && fabs(E) < 1e30;
+        const double kk = tame ? (-acc * inv) : (-acc / E);
+#pragma unroll
+        for (int j = 1; 2 * j <= i; ++j) {
+          const double lo = a[j], hi = a[i - j];
+          a[j] = fma(kk, hi, lo);
+          if (2 * j != i) a[i - j] = fma(kk, lo, hi);
+        }
+        a[i] = kk;
+        E *= fma(-kk, kk, 1.0);
+      }
+    }
+    double gain = r[0];
+#pragma unroll
+    for (int j = 1; j < kLag; ++j)
+      if ((V & kLvM24) || j <= A.M) gain = fma(r[j], a[j], gain);
+    a[0] = sqrt(gain);
+
+    const int64_t row0 = static_cast<int64_t>(b) * A.n_frames + f0;
+    const bool staged = A.bulk_out && nvalid == kUnit && (((row0 * D) & 3) == 0);
+    __syncwarp();  // every lane has read its rbuf row
+    if (staged) {
+      float* o = rbuf + lane * D;
+#pragma unroll
+      for (int k = 0; k < kLag; ++k)
+        if ((V & kLvM24) || k < D) o[k] = static_cast<float>(a[k]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) bulk_s2g(A.y + row0 * D, rbuf, static_cast<uint32_t>(kUnit * D) * 4u);
+      store_pending = true;
+    } else if (lane < nvalid) {
+      float* o = A.y + (row0 + lane) * D;
+#pragma unroll
+      for (int k = 0; k < kLag; ++k)
+        if (k < D) o[k] = static_cast<float>(a[k]);
+    }
+    u = un; b = bn; g = gn;
+  }
+  if (store_pending && lane == 0) bulk_wait_read();
+}
+
 }  // namespace
 
 int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t batch, int64_t T_len,
@@ -364,6 +554,27 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
   int v = full ? knob("LPC_V", kLpcVariant) : 0;
   if (M != kLag - 1) v &= ~kLvM24;
   if (v & kLvRolled) v &= ~kLvM24;
+  if (v & kLvLagPair) {
+    // lag-pair form: only samples < 400 of a frame are ever read from the staged span
+    A.span = ((kHalfUnit - 1) * fp->frame_period + 16 * kCh + 3) & ~3;
+    const size_t per_warp2 = static_cast<size_t>(A.span) * 4 + 2 * 16 * kAcc2 * 8 + kUnit * kLag * 4;
+    const int w2 = knob("LPC_W2", kLpcWarps2) == 16 ? 16 : 12;
+    const size_t smem2 = 8 * w2 + 448 * sizeof(float) + w2 * per_warp2;
+    if (smem2 <= static_cast<size_t>(max_dynamic_smem(device))) {
+      const int blocks2 = static_cast<int>(std::min<int64_t>((A.n_units + w2 - 1) / w2, sm_count(device)));
+      auto launch2 = [&](auto kern) -> int {
+        DSB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem2)));
+        kern<<<blocks2, w2 * 32, smem2, stream>>>(A);
+        return DSB200_OK;
+      };
+      const bool m24 = (v & kLvM24) != 0;
+      if (w2 == 16) rc = m24 ? launch2(lpc_wave2_kernel<16, kLvM24>) : launch2(lpc_wave2_kernel<16, 0>);
+      else rc = m24 ? launch2(lpc_wave2_kernel<12, kLvM24>) : launch2(lpc_wave2_kernel<12, 0>);
+      if (rc != DSB200_OK) return rc;
+      return after_launch("lpc_wave2_kernel");
+    }
+    A.span = span;
+  }
   if (kLWarps == 8) rc = full ? launch(lpc_wave_kernel<true, 8>) : launch(lpc_wave_kernel<false, 8>);
   else if (!full) rc = launch(lpc_wave_kernel<false, 12>);
   else switch (v) {

@@ -187,6 +187,64 @@ def lpc_wave_model(frame, M, eps):
     return out
 
 
+def lpc_lagpair_autocorr_model(xw):
+    """Lag sums of one windowed 400-sample frame as lpc_wave2_kernel forms them: lane l owns samples [26 l, 26 l + 26)
+    and 25 ALIGNED pairs E[j] = (x[2j], x[2j+1]) of its 50-sample reach; an even sample multiplies E[t + m] into
+    (r[2m], r[2m+1]), an odd sample multiplies E[t + 1 + m] into a second set (r[2m+1], r[2m+2]), its lag 0 is a
+    scalar product; samples past the frame end are zeros.  Returns r[0..24]."""
+    x = np.zeros(16 * 26 + 50)
+    x[:400] = np.asarray(xw, dtype=np.float64)
+    r = np.zeros(26)
+    for l in range(16):
+        E = [x[26 * l + 2 * j: 26 * l + 2 * j + 2] for j in range(25)]
+        ae, ao, r0o = np.zeros((13, 2)), np.zeros((12, 2)), 0.0
+        for t in range(13):
+            xe, xo = E[t]
+            for m in range(13):
+                ae[m] += xe * E[t + m]
+            for m in range(12):
+                ao[m] += xo * E[t + 1 + m]
+            r0o += xo * xo
+        for m in range(13):
+            r[2 * m] += ae[m, 0] + (ao[m - 1, 1] if m > 0 else r0o)
+            r[2 * m + 1] += ae[m, 1] + (ao[m, 0] if m < 12 else 0.0)
+    return r[:25]
+
+
+def levinson_rolled_model(r, M, eps):
+    """The rolled recursion of lpc_wave_kernel (variant bit 8): no array is indexed by the order.  Besides a[j] the
+    lane keeps the reversed predictor ar[j] = a[i - j] (ar[i] = a[0] = 1), so that every order runs the same statements:
+    acc = sum_m ar[m] r[m];  a'[j] = a[j] + k ar[j];  ar'[j] = ar[j-1] + k a[j-1], ar'[1] = k.  Orders 1..11 use the
+    half-width body (positions <= 12).  Returns [K, a_1..a_M] like lpc_wave_model."""
+    r = np.asarray(r, dtype=np.float64)
+    a, ar, rd = np.zeros(25), np.zeros(25), np.zeros(25)
+    rd[1:len(r)] = r[1:]
+    ar[1] = 1.0
+    E = r[0] + eps
+
+    def orders(W, i0, i1):
+        nonlocal E
+        for _ in range(i0, i1 + 1):
+            s = [0.0, 0.0, 0.0, 0.0]
+            for m in range(1, W + 1):
+                s[(m - 1) & 3] += ar[m] * rd[m]
+            k = -((s[0] + s[1]) + (s[2] + s[3])) / E
+            for j in range(W, 1, -1):          # descending: positions j - 1 are still the old ones
+                ta = a[j] + k * ar[j]
+                ar[j] = ar[j - 1] + k * a[j - 1]
+                a[j] = ta
+            a[1] = a[1] + k * ar[1]
+            ar[1] = k
+            E *= 1 - k * k
+
+    orders(12, 1, min(M, 11))
+    orders(24, 12, M)
+    assert not a[M + 1:].any(), "positions beyond the order must stay zero"
+    out = a[:M + 1].copy()
+    out[0] = np.sqrt(r[0] + np.dot(a[1:], rd[1:]))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 # istft512.cu / stft512_bwd.cu: lane-level data flow of the synthesis half.  The 256-point FFT itself is the
 # forward kernel's (modelled above); what is new is how its input conj(E + i O) is built from the spectrum rows,

@@ -1,6 +1,7 @@
 """The numpy lane-level models of the specialised kernels agree with the oracle (CPU test)."""
 
 import numpy as np
+import pytest
 
 import kernel_models as KM
 from oracle import np_oracle as O
@@ -48,6 +49,27 @@ def test_lpc_wave_model_matches_oracle():
     want = O.lpc(fr, 24, eps=1e-5)
     got = np.stack([KM.lpc_wave_model(f, 24, 1e-5) for f in fr])
     np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)
+
+
+def test_lpc_lagpair_lag_sums_match_the_direct_sums():
+    """Two accumulator sets on aligned sample pairs (no odd-aligned pair, scalar lag 0 for odd samples) give every
+    lag exactly once."""
+    rng = np.random.default_rng(31)
+    fr = O.window(O.frame(rng.standard_normal(1000), 400, 80), None)
+    for f in fr[2:6]:
+        want = np.array([np.dot(f[:400 - k], f[k:]) for k in range(25)])
+        np.testing.assert_allclose(KM.lpc_lagpair_autocorr_model(f), want, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("M", [1, 5, 11, 12, 13, 24])
+def test_rolled_levinson_model_matches_oracle(M):
+    """The order-independent form of the recursion (reversed predictor) equals the reference's Levinson-Durbin."""
+    rng = np.random.default_rng(20 + M)
+    fr = O.window(O.frame(rng.standard_normal(1200), 400, 80), None)
+    want = O.lpc(fr, M, eps=1e-5)
+    for f, w in zip(fr, want):
+        r = np.array([np.dot(f[:400 - k], f[k:]) for k in range(M + 1)])
+        np.testing.assert_allclose(KM.levinson_rolled_model(r, M, 1e-5), w, rtol=1e-8, atol=1e-10)
 
 
 def test_istft512_lane_model_matches_oracle():
