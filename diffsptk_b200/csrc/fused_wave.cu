@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave_kernel(const LArgs A
 // end (lane 14 from pair 18, lane 15 from pair 5) are read from the zero tail of the window table instead of the
 // staged waveform: 0 * 0, never sample * 0.
 constexpr int kCh2 = 26, kPairs2 = 25, kAcc2 = 13;
-constexpr int kLvLagPair = 16;
+constexpr int kLvLagPair = 16, kLvSplit = 32;   // 32: split accumulation chains in the Levinson phase
 
 template <int kLWarps, int V>
 __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave2_kernel(const LArgs A) {
@@ -429,6 +429,14 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave2_kernel(const LArgs 
           acc[m].y = m < kAcc2 - 1 ? ae[m].y + ao[m].x : ae[m].y;
         }
         // reduce the 16 per-lane partial sums of every lag pair through shared memory
+        if (V & kLvNoRed) {
+          float2 s0 = make_float2(0.0f, 0.0f);
+#pragma unroll
+          for (int m = 0; m < kAcc2; ++m) s0 = __fadd2_rn(s0, acc[m]);
+          if (l < kAcc2) rbuf[(kHalfUnit * half + fa) * kLag + 2 * l] = s0.x + s0.y;
+          __syncwarp();
+          continue;
+        }
 #pragma unroll
         for (int m = 0; m < kAcc2; ++m) part[l * kAcc2 + m] = acc[m];
         __syncwarp();
@@ -456,12 +464,29 @@ __global__ void __launch_bounds__(kLWarps * 32, 1) lpc_wave2_kernel(const LArgs 
 #pragma unroll
     for (int k = 0; k < kLag; ++k) r[k] = static_cast<double>(rbuf[lane * kLag + k]);
     double E = r[0] + A.eps;
+    if (V & kLvNoLev) {
+#pragma unroll
+      for (int i = 1; i < kLag; ++i) a[i] = r[i];
+    }
 #pragma unroll
     for (int i = 1; i < kLag; ++i) {
+      if (V & kLvNoLev) break;
       if ((V & kLvM24) || i <= A.M) {
         double acc = r[i];
+        if (V & kLvSplit) {   // four interleaved partial sums: the dependent chain is i / 4 long instead of i
+          double c1 = 0.0, c2 = 0.0, c3 = 0.0;
 #pragma unroll
-        for (int j = 1; j < i; ++j) acc = fma(a[j], r[i - j], acc);
+          for (int j = 1; j < i; ++j) {
+            if ((j & 3) == 0) acc = fma(a[j], r[i - j], acc);
+            if ((j & 3) == 1) c1 = fma(a[j], r[i - j], c1);
+            if ((j & 3) == 2) c2 = fma(a[j], r[i - j], c2);
+            if ((j & 3) == 3) c3 = fma(a[j], r[i - j], c3);
+          }
+          if (i > 1) acc = (acc + c1) + (c2 + c3);
+        } else {
+#pragma unroll
+          for (int j = 1; j < i; ++j) acc = fma(a[j], r[i - j], acc);
+        }
         double inv = static_cast<double>(__frcp_rn(static_cast<float>(E)));
         inv = fma(inv, fma(-E, inv, 1.0), inv);
         inv = fma(inv, fma(-E, inv, 1.0), inv);
@@ -568,7 +593,17 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
         return DSB200_OK;
       };
       const bool m24 = (v & kLvM24) != 0;
-      if (w2 == 16) rc = m24 ? launch2(lpc_wave2_kernel<16, kLvM24>) : launch2(lpc_wave2_kernel<16, 0>);
+      const int extra = v & ~(kLvLagPair | kLvM24 | kLvHalo | kLvMul2 | kLvRolled);
+      if (m24 && extra == kLvSplit)
+        rc = w2 == 16 ? launch2(lpc_wave2_kernel<16, kLvM24 | kLvSplit>) : launch2(lpc_wave2_kernel<12, kLvM24 | kLvSplit>);
+#ifdef DSB200_LPC_DIAG
+      else if (m24 && extra == kLvNoLev)
+        rc = w2 == 16 ? launch2(lpc_wave2_kernel<16, kLvM24 | kLvNoLev>) : launch2(lpc_wave2_kernel<12, kLvM24 | kLvNoLev>);
+      else if (m24 && extra == (kLvNoLev | kLvNoRed))
+        rc = w2 == 16 ? launch2(lpc_wave2_kernel<16, kLvM24 | kLvNoLev | kLvNoRed>)
+                      : launch2(lpc_wave2_kernel<12, kLvM24 | kLvNoLev | kLvNoRed>);
+#endif
+      else if (w2 == 16) rc = m24 ? launch2(lpc_wave2_kernel<16, kLvM24>) : launch2(lpc_wave2_kernel<16, 0>);
       else rc = m24 ? launch2(lpc_wave2_kernel<12, kLvM24>) : launch2(lpc_wave2_kernel<12, 0>);
       if (rc != DSB200_OK) return rc;
       return after_launch("lpc_wave2_kernel");
