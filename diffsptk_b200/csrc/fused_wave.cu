@@ -36,8 +36,8 @@ constexpr int kHalfUnit = 16; // frames staged at a time
 constexpr int kCh = 25;       // samples per lane (16 lanes x 25 = 400 >= frame_length)
 constexpr int kLag = 25;      // lags 0..24
 constexpr int kHalo = kLag - 1;
-constexpr int kLpcVariant = 0;  // default of the knob LPC_V (kLv* bits)
-constexpr int kLpcWarps2 = 12;  // default of the knob LPC_W2 (warps per CTA of the lag-pair kernel)
+constexpr int kLpcVariant = 16 | 4;  // default of the knob LPC_V (kLv* bits): lag-pair form, order-24 Levinson unguarded
+constexpr int kLpcWarps2 = 16;  // default of the knob LPC_W2 (warps per CTA of the lag-pair kernel; 12 when M < 24)
 constexpr int kLpcStagger = 0;  // default of the knob LPC_STAGGER (cycles per scheduler slot)
 
 struct LArgs {
@@ -583,7 +583,9 @@ int lpc_wave_fast_try(const float* x, const float* window, float* y, int64_t bat
     // lag-pair form: only samples < 400 of a frame are ever read from the staged span
     A.span = ((kHalfUnit - 1) * fp->frame_period + 16 * kCh + 3) & ~3;
     const size_t per_warp2 = static_cast<size_t>(A.span) * 4 + 2 * 16 * kAcc2 * 8 + kUnit * kLag * 4;
-    const int w2 = knob("LPC_W2", kLpcWarps2) == 16 ? 16 : 12;
+    // 16 warps at 128 registers: the lag loop needs 123, the unguarded order-24 recursion fits with ~100 B of spills; with
+    // the per-order guards of M < 24 it would spill 1 KB, so those launches stay at 12 warps
+    const int w2 = ((v & kLvM24) && knob("LPC_W2", kLpcWarps2) == 16) ? 16 : 12;
     const size_t smem2 = 8 * w2 + 448 * sizeof(float) + w2 * per_warp2;
     if (smem2 <= static_cast<size_t>(max_dynamic_smem(device))) {
       const int blocks2 = static_cast<int>(std::min<int64_t>((A.n_units + w2 - 1) / w2, sm_count(device)));

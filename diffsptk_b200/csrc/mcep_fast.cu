@@ -57,6 +57,7 @@ struct MArgs {
 };
 
 constexpr int kMcepStagger = 0;  // default of the knob MCEP_STAGGER
+constexpr int kMcepVariant = 122; // default of the knob MCEP_V
 
 // Compile-time loop: the elimination below indexes register arrays with the loop variable, so it must be
 // expanded even when the body is too large for `#pragma unroll` heuristics.
@@ -595,7 +596,7 @@ int mcep_fast_try(const float* x, float* y, int64_t rows, const dsb200_mcep_para
   A.n_iter = p->n_iter;
   // knob MCEP_V = 8 | 120 | 12 | 16 | 122 | 162: warps per CTA (x frame pairs per elimination pass:
   // 4 at 8 warps, else 2); 8 and 120 keep the fully unrolled elimination + back substitution for A/B runs
-  const int variant = knob("MCEP_V", 12);
+  const int variant = knob("MCEP_V", kMcepVariant);
   A.stagger = knob("MCEP_STAGGER", kMcepStagger);
   if (variant == 8) return launch_mcep_fast<8, 4, 0>(A, device, stream);      // round-1 shape
   if (variant == 120) return launch_mcep_fast<12, 2, 0>(A, device, stream);   // 12 warps, unrolled elimination
