@@ -27,7 +27,9 @@ def lib():
     os.makedirs(out, exist_ok=True)
     so = os.path.join(out, "libconvert_host.so")
     src = os.path.join(ROOT, "tests", "native", "convert_host.cu")
-    subprocess.run([nvcc, "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
+    # the device half of the shared headers is compiled too (and never run here): it needs the product's architecture
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler",
+                    "-fPIC", "-I", os.path.join(ROOT, "include"),
                     "-I", os.path.join(ROOT, "diffsptk_b200", "csrc"), src, "-o", so], check=True)
     return C.CDLL(so)
 
