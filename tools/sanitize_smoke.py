@@ -44,8 +44,21 @@ def main():
             Pw = B.STFT(400, 80, 512).to(dev)(xd)
             close(F.mfcc_from_waveform(xd, out_format="ycE").cpu().numpy(),
                   O.mfcc(O.stft(x64), 13, 40, 16000, out_format="ycE"), f"mfcc_wave {Bn}x{T}")
-            a = F.lpc_from_waveform(xd, lpc_order=24)
+            a = F.lpc_from_waveform(xd, lpc_order=24)          # lag-pair kernel, 16 warps
             close(a.cpu().numpy(), O.lpc(O.window(O.frame(x64), None), 24, eps=1e-5), f"lpc_wave {Bn}x{T}", 2e-2, 2e-3)
+            a = F.lpc_from_waveform(xd, lpc_order=12)          # lag-pair kernel with the guarded recursion, 12 warps
+            close(a.cpu().numpy(), O.lpc(O.window(O.frame(x64), None), 12, eps=1e-5), f"lpc_wave M=12 {Bn}x{T}", 2e-2, 2e-3)
+            a = F.lpc_from_waveform(xd, lpc_order=16, frame_length=320, frame_period=160)   # frame-pair kernel
+            close(a.cpu().numpy(), O.lpc(O.window(O.frame(x64, 320, 160), None), 16, eps=1e-5),
+                  f"lpc_wave fl=320 {Bn}x{T}", 2e-2, 2e-3)
+            for nn, hop in ((1024, 160), (2048, 441)):         # shared-memory FFT kernel
+                if T >= 333:
+                    Pn = B.STFT(nn, hop, nn, window="hanning", norm="none", zmean=(nn == 1024)).to(dev)(xd)
+                    close(Pn.cpu().numpy(), O.stft(x64, frame_length=nn, frame_period=hop, fft_length=nn, zmean=(nn == 1024),
+                                                   window="hanning", norm="none"),
+                          f"stft {nn} {Bn}x{T}")
+            Pz = B.STFT(400, 80, 512, zmean=True, relative_floor=-60.0).to(dev)(xd)
+            close(Pz.cpu().numpy(), O.stft(x64, zmean=True, relative_floor=-60.0), f"stft zmean+floor {Bn}x{T}")
             mc = B.MelCepstralAnalysis(fft_length=512, cep_order=24, alpha=0.42, n_iter=10).to(dev)(Pw)
             close(mc.cpu().numpy(), O.mcep(O.stft(x64), 24, 0.42, 10), f"mcep {Bn}x{T}")
             Y = B.STFT(400, 80, 512, out_format="complex").to(dev)(xd)
