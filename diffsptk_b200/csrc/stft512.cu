@@ -89,6 +89,7 @@ struct Args {
 
 constexpr int kStftStagger = 0;  // defaults of the knobs STFT_STAGGER / MFCC_STAGGER
 constexpr int kMfccStagger = 0;
+constexpr int kInPad = 0;        // default of the knob STFT_INPAD (floats, multiple of 4)
 
 constexpr int kFmtMfcc = 5;  // internal: stage amplitudes, then filter bank + DCT + lifter on chip
 constexpr int kSegLen = kPlanSegLen;     // bins per filter-bank segment
@@ -824,7 +825,10 @@ static int setup_args(Args& A, const float* x, const float* window, float* y, in
   // The quad's samples: 3 P + L.  The column loads below run up to 32 NJ - L floats past that into the next
   // shared-memory region; those lanes are masked (p0 >= L), so the span is not padded to 32 NJ.
   A.span = (3 * f.frame_period + f.frame_length + 3) & ~3;
-  A.in_floats = A.span;
+  // Frame B of a pair (two hops on) reads its masked tail columns up to 16 floats past the span: the padding keeps
+  // those reads inside the warp's own buffer instead of the first floats of the other one, which the next bulk copy
+  // is filling at that moment (the values are discarded either way; compute-sanitizer racecheck flags the overlap).
+  A.in_floats = A.span + (knob("STFT_INPAD", kInPad) & ~3);
   // bulk copies need 16-byte aligned global addresses and sizes: every span start (4 g P - left) and
   // every utterance start (b T) must be a multiple of 4 floats.
   A.bulk_in = ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && (T_len % 4 == 0) && (left % 4 == 0) &&

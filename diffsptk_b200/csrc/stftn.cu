@@ -18,7 +18,8 @@
 // One 16-byte pad per M elements makes every pass and the split free of shared-memory bank conflicts (pass 1 walks
 // consecutive j, passes 2 / 3 and the split walk consecutive t at pitch M + 1).  tests/kernel_models.py holds the
 // numpy model of this index arithmetic (stftn_frame_model).  The frames of a pair are staged with guarded loads (any
-// hop, all four pad modes, utterance edges), so the envelope is: float32, fft_length 1024 or 2048, frame_length <=
+// hop, all four pad modes, utterance edges; interior pairs are prefetched into registers one iteration ahead), so the
+// envelope is: float32, fft_length 1024 or 2048, frame_length <=
 // fft_length; zmean, relative floor and every output format included.
 #include <algorithm>
 
@@ -81,18 +82,46 @@ __global__ void __launch_bounds__(W * 32, 1) stftn_kernel(const NArgs A) {
   __syncthreads();
 
   const int64_t stride = static_cast<int64_t>(gridDim.x) * W;
+  // Software pipeline of the staging: the samples of the NEXT pair (one contiguous span of L + P floats when both of
+  // its frames lie inside the utterance) are fetched into registers before the transform of the current pair and
+  // written to shared memory at the top of the next iteration, so their HBM / L2 latency hides behind three FFT
+  // passes (round 2: long_scoreboard was 29 % of the stall samples with loads issued right before their use).
+  constexpr int kSR = (LOGN == 10) ? 38 : 80;        // span registers per lane: L + P <= 32 kSR is prefetched
+  float sp[kSR];
+  bool have = false;                                 // sp holds the span of this iteration's pair (warp-uniform)
+  const bool can_prefetch = A.L + A.P <= 32 * kSR;
+  auto pair_geometry = [&](int64_t pr, int64_t& b, int& f, bool& vB, int64_t& s0, int64_t& s1) {
+    b = pr / A.pairs_per_utt;
+    f = 2 * static_cast<int>(pr - b * A.pairs_per_utt);
+    vB = f + 1 < A.n_frames;
+    s0 = static_cast<int64_t>(f) * A.P - A.left;
+    s1 = vB ? s0 + A.P : s0;
+  };
   for (int64_t pr = static_cast<int64_t>(blockIdx.x) * W + warp; pr < A.n_pairs; pr += stride) {
-    const int64_t b = pr / A.pairs_per_utt;
-    const int f = 2 * static_cast<int>(pr - b * A.pairs_per_utt);
-    const bool vB = f + 1 < A.n_frames;
+    int64_t b, s0, s1;
+    int f;
+    bool vB;
+    pair_geometry(pr, b, f, vB, s0, s1);
     const float* xb = A.x + b * A.T;
 
     // ---- stage the two frames (frame.py:130-141: padding modes, utterance edges); sums for zmean ----------------
     float sumA = 0.0f, sumB = 0.0f;
-    {
-      const int64_t s0 = static_cast<int64_t>(f) * A.P - A.left, s1 = vB ? s0 + A.P : s0;
+    if (have) {
+      // prefetched span: register i holds x[s0 + lane + 32 i]; frame A takes [0, L), frame B [P, P + L)
+#pragma unroll
+      for (int i = 0; i < kSR; ++i) {
+        const int j = lane + 32 * i, jb = j - A.P;
+        const float v = sp[i];
+        if (j < A.L) { sA[j] = v; sumA += v; }
+        if (jb >= 0 && jb < A.L) { sB[jb] = v; sumB += v; }
+      }
+      for (int j = A.L + lane; j < n; j += 32) {
+        sA[j] = 0.0f;
+        sB[j] = 0.0f;
+      }
+    } else {
       if (s0 >= 0 && s1 + A.L <= A.T) {
-        // both frames inside the utterance (all but a few pairs per utterance): plain coalesced loads, no index map
+        // both frames inside the utterance: plain coalesced loads, no index map
         const float* pa = xb + s0;
         const float* pb = xb + s1;
 #pragma unroll 8
@@ -120,6 +149,24 @@ __global__ void __launch_bounds__(W * 32, 1) stftn_kernel(const NArgs A) {
           sumA += va;
           sumB += vb;
         }
+      }
+    }
+    // fetch the next pair's span now; it is consumed at the top of the next iteration
+    have = false;
+    if (can_prefetch && pr + stride < A.n_pairs) {
+      int64_t bn, t0, t1;
+      int fn;
+      bool vn;
+      pair_geometry(pr + stride, bn, fn, vn, t0, t1);
+      if (vn && t0 >= 0 && t1 + A.L <= A.T) {
+        const float* pn = A.x + bn * A.T + t0;
+        const int len = A.L + A.P;
+#pragma unroll
+        for (int i = 0; i < kSR; ++i) {
+          const int j = lane + 32 * i;
+          sp[i] = j < len ? __ldg(pn + j) : 0.0f;
+        }
+        have = true;
       }
     }
     float2 mean2 = make_float2(0.0f, 0.0f);
