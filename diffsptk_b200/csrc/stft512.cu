@@ -89,7 +89,7 @@ struct Args {
 
 constexpr int kStftStagger = 0;  // defaults of the knobs STFT_STAGGER / MFCC_STAGGER
 constexpr int kMfccStagger = 0;
-constexpr int kInPad = 0;        // default of the knob STFT_INPAD (floats, multiple of 4)
+constexpr int kInPad = 16;       // default of the knob STFT_INPAD (floats, multiple of 4)
 
 constexpr int kFmtMfcc = 5;  // internal: stage amplitudes, then filter bank + DCT + lifter on chip
 constexpr int kSegLen = kPlanSegLen;     // bins per filter-bank segment

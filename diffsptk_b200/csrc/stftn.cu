@@ -86,10 +86,13 @@ __global__ void __launch_bounds__(W * 32, 1) stftn_kernel(const NArgs A) {
   // its frames lie inside the utterance) are fetched into registers before the transform of the current pair and
   // written to shared memory at the top of the next iteration, so their HBM / L2 latency hides behind three FFT
   // passes (round 2: long_scoreboard was 29 % of the stall samples with loads issued right before their use).
-  constexpr int kSR = (LOGN == 10) ? 38 : 80;        // span registers per lane: L + P <= 32 kSR is prefetched
+  // Measured (config of bench.py's stft1024 / stft2048): 2048 at 6 warps and 255 registers 0.742 -> 0.687 ms; 1024 at 12
+  // warps has 168 registers, the 38 span registers squeeze the butterflies and it LOSES (0.601 -> 0.644 ms): off there.
+  constexpr bool kPrefetch = (LOGN == 11);
+  constexpr int kSR = kPrefetch ? 80 : 1;            // span registers per lane: L + P <= 32 kSR is prefetched
   float sp[kSR];
   bool have = false;                                 // sp holds the span of this iteration's pair (warp-uniform)
-  const bool can_prefetch = A.L + A.P <= 32 * kSR;
+  const bool can_prefetch = kPrefetch && A.L + A.P <= 32 * kSR;
   auto pair_geometry = [&](int64_t pr, int64_t& b, int& f, bool& vB, int64_t& s0, int64_t& s1) {
     b = pr / A.pairs_per_utt;
     f = 2 * static_cast<int>(pr - b * A.pairs_per_utt);
