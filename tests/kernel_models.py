@@ -187,6 +187,25 @@ def lpc_wave_model(frame, M, eps):
     return out
 
 
+def stftn_prefetch_scatter_model(L, P, n, k_regs=80):
+    """stftn_kernel's register prefetch: lane l, register i hold span element j = l + 32 i of the contiguous span
+    x[s0 .. s0 + L + P); at the top of the next iteration element j goes to frame A at j (j < L) and to frame B at
+    j - P (0 <= j - P < L).  Returns (A, B) index arrays into the span (-1 = zero padding) for fft_length n."""
+    assert L + P <= 32 * k_regs
+    A = -np.ones(n, dtype=np.int64)
+    B = -np.ones(n, dtype=np.int64)
+    for i in range(k_regs):
+        for lane in range(32):
+            j = lane + 32 * i
+            if j >= L + P:
+                continue
+            if j < L:
+                A[j] = j
+            if 0 <= j - P < L:
+                B[j - P] = j
+    return A, B
+
+
 def lpc_lagpair_autocorr_model(xw):
     """Lag sums of one windowed 400-sample frame as lpc_wave2_kernel forms them: lane l owns samples [26 l, 26 l + 26)
     and 25 ALIGNED pairs E[j] = (x[2j], x[2j+1]) of its 50-sample reach; an even sample multiplies E[t + m] into

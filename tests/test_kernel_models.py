@@ -1,5 +1,7 @@
 """The numpy lane-level models of the specialised kernels agree with the oracle (CPU test)."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -49,6 +51,20 @@ def test_lpc_wave_model_matches_oracle():
     want = O.lpc(fr, 24, eps=1e-5)
     got = np.stack([KM.lpc_wave_model(f, 24, 1e-5) for f in fr])
     np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize("L,P,n", [(2048, 441, 2048), (1500, 300, 2048), (2048, 512, 2048), (700, 1201, 2048)])
+def test_stftn_prefetched_span_reaches_both_frames(L, P, n):
+    """Every sample of frame A (span[j]) and of frame B (span[P + j]) is written exactly once; the rest is padding."""
+    A, B = KM.stftn_prefetch_scatter_model(L, P, n)
+    assert (A[:L] == np.arange(L)).all() and (A[L:] == -1).all()
+    assert (B[:L] == np.arange(L) + P).all() and (B[L:] == -1).all()
+
+
+def test_sweep_tool_spec_parser():
+    from tools.sweep_knobs import parse_spec
+    wl, settings = parse_spec("lpc:LPC_V=0,7+LPC_W2=12,16")
+    assert wl == "lpc" and len(settings) == 4 and settings[-1] == {"LPC_V": 7, "LPC_W2": 16}
 
 
 def test_lpc_lagpair_lag_sums_match_the_direct_sums():

@@ -15,11 +15,6 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-import torch  # noqa: E402
-
-import bench  # noqa: E402
-from diffsptk_b200 import _native  # noqa: E402
-
 
 def parse_spec(spec):
     wl, rest = spec.split(":", 1)
@@ -32,6 +27,10 @@ def parse_spec(spec):
 
 
 def main():
+    import torch
+
+    import bench
+    from diffsptk_b200 import _native
     ap = argparse.ArgumentParser()
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--repeat", type=int, default=2, help="timed passes per setting (the best mean is reported)")
